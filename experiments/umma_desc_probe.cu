@@ -202,6 +202,9 @@ int main() {
   cfgs.push_back({2, 0, 1024, 8192, 0, 2048});   // 16: MN-major, second 64-wide atom 64 rows further (canonical-ish)
   cfgs.push_back({2, 0, 1024, 128, 0, 2048});    // 17: MN-major, second atom shifted by ONE row (tap-pair trick)
   cfgs.push_back({2, 3, 1024, 256, 0, 2048});    // 18: MN-major, row off 3, second atom +2 rows
+  cfgs.push_back({2, 3, 1280, 128, 0, 2560});    // 19: MN-major, K-groups 10 rows apart (brick rows inside a halo slab)
+  cfgs.push_back({2, 3, 1280, 0, 0, 2560});      // 20: same, LBO = 0 (second atom duplicates the first)
+  cfgs.push_back({2, 3, 1280, 1024, 0, 2560});   // 21: same, second atom 8 rows further
   int ncfg = (int)cfgs.size();
 
   std::vector<__nv_bfloat16> hB(64 * 64);
@@ -236,7 +239,7 @@ int main() {
       int er, ek;
       if (c.kind == 0) { er = c.row_off + (m / 8) * (c.sbo_bytes / 128) + m % 8; ek = n; }
       else if (c.kind == 1) { er = c.row_off + (m / 8) * (c.sbo_bytes / 16) + m % 8; ek = n; }
-      else { er = c.row_off + (m >= 64 ? c.lbo_bytes / 128 : 0) + n; ek = m % 64; }
+      else { er = c.row_off + (m >= 64 ? c.lbo_bytes / 128 : 0) + (n / 16) * (c.kadv_bytes / 128) + ((n % 16) / 8) * (c.sbo_bytes / 128) + n % 8; ek = m % 64; }
       int gr = (int)rowdec[((size_t)t * 128 + m) * 64 + n], gk = (int)kdec[((size_t)t * 128 + m) * 64 + n];
       if (gr != er % 256 || gk != ek) { if (!bad) { first_m = m; first_n = n; } ++bad; }
     }

@@ -1,0 +1,85 @@
+// libhpvg: process-wide state of the C-ABI (error string, backend switch, launch counter, tensor-map encoder).
+#include "common.cuh"
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+namespace hpvg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_backend{HPVG_BACKEND_AUTO};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int conv_backend() { return g_backend.load(std::memory_order_relaxed); }
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::atomic<int> state{0};
+  if (state.load(std::memory_order_acquire) == 2) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  state.store(2, std::memory_order_release);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return -3;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  uint64_t stride = 2;  // bytes of one bf16
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstrides[i] = stride;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu %llu)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)(rank > 4 ? dims[4] : 0));
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace hpvg
+
+extern "C" {
+
+const char* hpvg_last_error(void) { return hpvg::g_err; }
+int hpvg_version(void) { return 100; }
+int hpvg_set_conv_backend(int backend) {
+  if (backend < 0 || backend > 2) {
+    hpvg::set_error("hpvg_set_conv_backend: unknown backend %d", backend);
+    return -1;
+  }
+  hpvg::g_backend.store(backend);
+  return 0;
+}
+int hpvg_get_conv_backend(void) { return hpvg::g_backend.load(); }
+long long hpvg_launch_count(void) { return hpvg::g_launches.load(); }
+
+}  // extern "C"

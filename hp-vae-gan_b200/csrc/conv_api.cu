@@ -1,0 +1,98 @@
+// C-ABI entry points of the convolution family: argument validation and dispatch between the tcgen05 kernels
+// (conv_tc.cu, wgrad_tc.cu) and the CUDA-core kernels (conv_direct.cu).
+#include "common.cuh"
+
+namespace hpvg {
+int conv_direct(const void* x, int x_fmt, const float* w, const float* bias, void* y, int y_fmt, const ConvGeom& g, int transposed,
+                int act, float slope, float* stats, const void* mask_src, cudaStream_t st);
+int wgrad_direct(const void* x, int x_fmt, const void* gy, int gy_fmt, float* dw, const ConvGeom& g, cudaStream_t st);
+bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_packed);
+int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
+            const void* mask_src, cudaStream_t st);
+bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
+size_t wgrad_tc_workspace(const ConvGeom& g);
+int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
+
+static int make_geom(ConvGeom& g, int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, const char* who) {
+  if (!(N > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0)) {
+    set_error("%s: extents must be positive (N=%d Cin=%d Cout=%d D=%d H=%d W=%d)", who, N, Cin, Cout, D, H, W);
+    return -1;
+  }
+  if (!(KD == 1 || KD == 3)) {
+    set_error("%s: KD must be 1 (3x3) or 3 (3x3x3), got %d", who, KD);
+    return -1;
+  }
+  if (pad < 0 || pad > 2) {
+    set_error("%s: pad must be 0, 1 or 2, got %d", who, pad);
+    return -1;
+  }
+  g.N = N; g.Cin = Cin; g.Cout = Cout;
+  g.Di = D; g.Hi = H; g.Wi = W;
+  g.KD = KD; g.taps = KD * 9; g.pad = pad; g.pad_d = (KD == 3) ? pad : 0;
+  g.Do = D + 2 * g.pad_d - (KD - 1);
+  g.Ho = H + 2 * pad - 2;
+  g.Wo = W + 2 * pad - 2;
+  if (g.Do <= 0 || g.Ho <= 0 || g.Wo <= 0) {
+    set_error("%s: empty output (%d x %d x %d) for input %d x %d x %d, pad %d", who, g.Do, g.Ho, g.Wo, D, H, W, pad);
+    return -1;
+  }
+  return 0;
+}
+}  // namespace hpvg
+
+using namespace hpvg;
+
+extern "C" {
+
+int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* w_packed, const float* bias, void* y, int y_fmt, int N,
+                      int Cin, int Cout, int D, int H, int W, int KD, int pad, int transposed, int act, float lrelu_slope, float* stats,
+                      const void* mask_src, void* stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_forward")) return rc;
+  HPVG_CHECK_ARG(x && y, "conv_forward: null tensor");
+  HPVG_CHECK_ARG((x_fmt == 0 || x_fmt == 1) && (y_fmt == 0 || y_fmt == 1), "conv_forward: unknown tensor format");
+  HPVG_CHECK_ARG(act == HPVG_ACT_NONE || act == HPVG_ACT_LRELU, "conv_forward: unknown activation %d", act);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int backend = conv_backend();
+  const bool tc_ok = conv_tc_supported(x_fmt, y_fmt, g, w_packed);
+  if (backend == HPVG_BACKEND_TCGEN05 && !tc_ok) {
+    set_error("conv_forward: tcgen05 backend required but shape/format unsupported (Cin=%d Cout=%d fmt %d->%d packed=%p)", Cin, Cout,
+              x_fmt, y_fmt, w_packed);
+    return -1;
+  }
+  if (tc_ok && backend != HPVG_BACKEND_DIRECT) return conv_tc(x, w_packed, bias, y, g, act, lrelu_slope, stats, mask_src, st);
+  HPVG_CHECK_ARG(w_f32 != nullptr, "conv_forward: the CUDA-core kernel needs the float32 weights");
+  HPVG_CHECK_ARG(mask_src == nullptr || y_fmt == HPVG_FMT_NDHWC_BF16, "conv_forward: mask_src requires an NDHWC_BF16 output");
+  return conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
+}
+
+size_t hpvg_conv_wgrad_workspace(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int gy_fmt) {
+  ConvGeom g;
+  if (make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_wgrad_workspace")) return 0;
+  if (wgrad_tc_supported(x_fmt, gy_fmt, g)) return wgrad_tc_workspace(g);
+  return 0;
+}
+
+int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float* dw, float* dbias, int N, int Cin, int Cout, int D, int H,
+                    int W, int KD, int pad, void* workspace, size_t workspace_bytes, void* stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_wgrad")) return rc;
+  HPVG_CHECK_ARG(x && gy && dw, "conv_wgrad: null tensor");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int backend = conv_backend();
+  const bool tc_ok = wgrad_tc_supported(x_fmt, gy_fmt, g);
+  if (backend == HPVG_BACKEND_TCGEN05 && !tc_ok) {
+    set_error("conv_wgrad: tcgen05 backend required but shape/format unsupported (Cin=%d Cout=%d)", Cin, Cout);
+    return -1;
+  }
+  int rc;
+  if (tc_ok && backend != HPVG_BACKEND_DIRECT)
+    rc = wgrad_tc(x, gy, dw, g, workspace, workspace_bytes, st);
+  else
+    rc = wgrad_direct(x, x_fmt, gy, gy_fmt, dw, g, st);
+  if (rc) return rc;
+  if (dbias) return hpvg_channel_sum(gy, gy_fmt, dbias, N, Cout, (long long)g.Do * g.Ho * g.Wo, stream);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,781 @@
+// HBM-bound kernels of the path: BatchNorm(+LeakyReLU) forward/backward, LeakyReLU backward, trilinear/bilinear
+// resize (+noise) and its adjoint, tanh(+residual), the VAE head (reparameterisation, KL), the WGAN-GP penalty,
+// layout conversion, weight packing and spectral normalisation.  All are one pass over their operands with
+// 128-bit accesses where the layout allows; reductions use warp shuffles and one atomic per warp or block.
+#include "common.cuh"
+
+namespace hpvg {
+
+static inline int ew_blocks(long long work_items, int threads) {
+  long long b = cdiv(work_items, threads);
+  long long cap = (long long)num_sms() * 16;
+  return (int)max(1LL, min(b, cap));
+}
+
+// ===============================================================================================================
+// BatchNorm (training) + LeakyReLU        reference: modules/networks_3d.py:54-56 (nn.BatchNorm3d, nn.LeakyReLU(0.2))
+// ===============================================================================================================
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps, long long count,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const double inv = 1.0 / (double)count;
+    const double mean = (double)stats[c] * inv;
+    double var = (double)stats[C + c] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = beta[c] - (float)mean * sc;
+    mean_invstd[c] = (float)mean;
+    mean_invstd[C + c] = invstd;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+      const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (c == 0 && nbt) nbt[0] += 1;
+}
+
+__global__ void __launch_bounds__(256) bn_apply_lrelu_kernel(const uint4* __restrict__ y, const float* __restrict__ scale_shift,
+                                                             uint4* __restrict__ out, long long nvec, int C, float slope) {
+  extern __shared__ float ss[];  // scale[C], shift[C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ss[i] = scale_shift[i];
+  __syncthreads();
+  const int cvec = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) << 3;
+    uint4 v = __ldg(y + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = unpack_bf16x2(w[k]);
+      float a = fmaf(f.x, ss[c0 + 2 * k], ss[C + c0 + 2 * k]);
+      float b = fmaf(f.y, ss[c0 + 2 * k + 1], ss[C + c0 + 2 * k + 1]);
+      a = a > 0.f ? a : a * slope;
+      b = b > 0.f ? b : b * slope;
+      w[k] = pack_bf16x2(a, b);
+    }
+    out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// thread = (row lane, 8-channel group); per-thread partial sums in registers, block reduction through shared memory
+__global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gout,
+                                                                  const float* __restrict__ scale_shift,
+                                                                  const float* __restrict__ mean_invstd, float* __restrict__ sums,
+                                                                  long long nvox, int C, float slope) {
+  extern __shared__ float sm[];  // [4*C] params, then [rows][2*C] partials
+  float* prm = sm;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    prm[i] = scale_shift[i];
+    prm[2 * C + i] = mean_invstd[i];
+  }
+  __syncthreads();
+  const int cvec = C >> 3;
+  const int rows = blockDim.x / cvec;
+  const int cg = threadIdx.x % cvec, rl = threadIdx.x / cvec;
+  const int c0 = cg << 3;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
+  if (rl < rows) {
+    for (long long r = (long long)blockIdx.x * rows + rl; r < nvox; r += (long long)gridDim.x * rows) {
+      const uint4 yv = __ldg(y + r * cvec + cg);
+      const uint4 gv = __ldg(gout + r * cvec + cg);
+      const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 yf = unpack_bf16x2(yw[k]), gf = unpack_bf16x2(gw[k]);
+        const float ye[2] = {yf.x, yf.y}, ge[2] = {gf.x, gf.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = c0 + 2 * k + e;
+          const float z = fmaf(ye[e], prm[c], prm[C + c]);
+          const float dz = z > 0.f ? ge[e] : ge[e] * slope;
+          const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
+          s0[2 * k + e] += dz;
+          s1[2 * k + e] = fmaf(dz, xh, s1[2 * k + e]);
+        }
+      }
+    }
+  }
+  float* part = sm + 4 * C;  // [rows][2*C]
+  if (rl < rows) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      part[rl * 2 * C + c0 + k] = s0[k];
+      part[rl * 2 * C + C + c0 + k] = s1[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += part[r * 2 * C + i];
+    atomicAdd(sums + i, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gout,
+                                                                 const float* __restrict__ scale_shift,
+                                                                 const float* __restrict__ mean_invstd, const float* __restrict__ sums,
+                                                                 uint4* __restrict__ gy, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, long long nvox, int C, float slope) {
+  extern __shared__ float prm[];  // scale, shift, mean, invstd, m0 = sum dz / M, m1 = sum dz*xhat / M
+  const float invM = 1.f / (float)nvox;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    prm[i] = scale_shift[i];
+    prm[2 * C + i] = mean_invstd[i];
+    prm[4 * C + i] = sums[i] * invM;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (dbeta) dbeta[i] = sums[i];
+      if (dgamma) dgamma[i] = sums[C + i];
+    }
+  }
+  __syncthreads();
+  const int cvec = C >> 3;
+  const long long nvec = nvox * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) << 3;
+    const uint4 yv = __ldg(y + i), gv = __ldg(gout + i);
+    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 yf = unpack_bf16x2(yw[k]), gf = unpack_bf16x2(gw[k]);
+      const float ye[2] = {yf.x, yf.y}, ge[2] = {gf.x, gf.y};
+      float res[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * k + e;
+        const float z = fmaf(ye[e], prm[c], prm[C + c]);
+        const float dz = z > 0.f ? ge[e] : ge[e] * slope;
+        const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
+        res[e] = prm[c] * (dz - prm[4 * C + c] - xh * prm[5 * C + c]);
+      }
+      ow[k] = pack_bf16x2(res[0], res[1]);
+    }
+    gy[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict__ gout, const uint4* __restrict__ outv,
+                                                        uint4* __restrict__ gz, long long nvec, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 g = __ldg(gout + i), o = __ldg(outv + i);
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gf = unpack_bf16x2(gw[k]), of = unpack_bf16x2(ow[k]);
+      r[k] = pack_bf16x2(of.x > 0.f ? gf.x : gf.x * slope, of.y > 0.f ? gf.y : gf.y * slope);
+    }
+    gz[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ===============================================================================================================
+// linear resize, align_corners=True      reference: utils/images.py:22-26 (F.interpolate trilinear), :9-19 (bilinear)
+// ===============================================================================================================
+__device__ __forceinline__ void lin_src(int o, float scale, int in, int& i0, int& i1, float& l0, float& l1) {
+  const float s = scale * (float)o;   // align_corners=True: src = o * (in-1)/(out-1)
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                           const float* __restrict__ noise, float amp, int NC, int Di, int Hi, int Wi,
+                                                           int Do, int Ho, int Wo, float sd, float sh, float sw) {
+  const long long total = (long long)NC * Do * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho); t /= Ho;
+    const int od = (int)(t % Do);
+    const long long nc = t / Do;
+    int d0, d1, h0, h1, w0, w1;
+    float ld0, ld1, lh0, lh1, lw0, lw1;
+    lin_src(od, sd, Di, d0, d1, ld0, ld1);
+    lin_src(oh, sh, Hi, h0, h1, lh0, lh1);
+    lin_src(ow, sw, Wi, w0, w1, lw0, lw1);
+    const float* p = x + nc * (long long)Di * Hi * Wi;
+#define X_(d, h, w) __ldg(p + ((long long)(d) * Hi + (h)) * Wi + (w))
+    float v = ld0 * (lh0 * (lw0 * X_(d0, h0, w0) + lw1 * X_(d0, h0, w1)) + lh1 * (lw0 * X_(d0, h1, w0) + lw1 * X_(d0, h1, w1))) +
+              ld1 * (lh0 * (lw0 * X_(d1, h0, w0) + lw1 * X_(d1, h0, w1)) + lh1 * (lw0 * X_(d1, h1, w0) + lw1 * X_(d1, h1, w1)));
+#undef X_
+    if (noise) v = fmaf(amp, __ldg(noise + i), v);
+    out[i] = v;
+  }
+}
+
+// adjoint as a gather: every input voxel sums the outputs that interpolate from it (no atomics, deterministic)
+__device__ __forceinline__ void adj_range(int i, float scale, int out, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
+  lo = (int)floorf(((float)i - 1.f) / scale) - 1;
+  hi = (int)ceilf(((float)i + 1.f) / scale) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+}
+__device__ __forceinline__ float adj_weight(int o, int i, float scale, int in) {
+  int i0, i1;
+  float l0, l1;
+  lin_src(o, scale, in, i0, i1, l0, l1);
+  float w = 0.f;
+  if (i0 == i) w += l0;
+  if (i1 == i) w += l1;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int NC, int Di, int Hi,
+                                                           int Wi, int Do, int Ho, int Wo, float sd, float sh, float sw) {
+  const long long total = (long long)NC * Di * Hi * Wi;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int iw = (int)(t % Wi); t /= Wi;
+    const int ih = (int)(t % Hi); t /= Hi;
+    const int id = (int)(t % Di);
+    const long long nc = t / Di;
+    int dlo, dhi, hlo, hhi, wlo, whi;
+    adj_range(id, sd, Do, dlo, dhi);
+    adj_range(ih, sh, Ho, hlo, hhi);
+    adj_range(iw, sw, Wo, wlo, whi);
+    const float* g = gout + nc * (long long)Do * Ho * Wo;
+    float acc = 0.f;
+    for (int od = dlo; od <= dhi; ++od) {
+      const float wd = adj_weight(od, id, sd, Di);
+      if (wd == 0.f) continue;
+      for (int oh = hlo; oh <= hhi; ++oh) {
+        const float wh = adj_weight(oh, ih, sh, Hi);
+        if (wh == 0.f) continue;
+        float row = 0.f;
+        for (int ow = wlo; ow <= whi; ++ow) {
+          const float ww = adj_weight(ow, iw, sw, Wi);
+          if (ww != 0.f) row = fmaf(ww, __ldg(g + ((long long)od * Ho + oh) * Wo + ow), row);
+        }
+        acc = fmaf(wd * wh, row, acc);
+      }
+    }
+    gx[i] = acc;
+  }
+}
+
+// ===============================================================================================================
+// tanh(+residual)                          reference: modules/networks_3d.py:377,404
+// ===============================================================================================================
+__global__ void tanh_add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a[i];
+    if (b) v += b[i];
+    out[i] = tanhf(v);
+  }
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, float* __restrict__ g, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = out[i];
+    g[i] = gout[i] * (1.f - o * o);
+  }
+}
+
+// ===============================================================================================================
+// VAE head                                 reference: modules/networks_3d.py:29-35, modules/losses.py:7-9
+// ===============================================================================================================
+// thread = (voxel, 8-channel group): NDHWC bf16 mu/logvar, NCDHW fp32 eps (torch's normal_() order), NDHWC bf16 z
+__global__ void __launch_bounds__(256) reparam_fwd_kernel(const uint4* __restrict__ mu, const uint4* __restrict__ logvar,
+                                                          const float* __restrict__ eps, uint4* __restrict__ z, int N, int C,
+                                                          long long S) {
+  const int cvec = C >> 3;
+  const long long total = (long long)N * S * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // adjacent threads walk voxels (coalesced eps reads), channel groups are the slow index
+    const long long s = i % S;
+    const int cg = (int)((i / S) % cvec);
+    const long long n = i / (S * cvec);
+    const long long vi = (n * S + s) * cvec + cg;
+    const uint4 m = __ldg(mu + vi), l = __ldg(logvar + vi);
+    const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 mf = unpack_bf16x2(mw[k]), lf = unpack_bf16x2(lw[k]);
+      const float e0 = __ldg(eps + (n * C + (cg * 8 + 2 * k)) * S + s);
+      const float e1 = __ldg(eps + (n * C + (cg * 8 + 2 * k + 1)) * S + s);
+      r[k] = pack_bf16x2(fmaf(e0, expf(0.5f * lf.x), mf.x), fmaf(e1, expf(0.5f * lf.y), mf.y));
+    }
+    z[vi] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) reparam_bwd_kernel(const uint4* __restrict__ gz, const uint4* __restrict__ logvar,
+                                                          const float* __restrict__ eps, uint4* __restrict__ gmu,
+                                                          uint4* __restrict__ glogvar, int N, int C, long long S) {
+  const int cvec = C >> 3;
+  const long long total = (long long)N * S * cvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i % S;
+    const int cg = (int)((i / S) % cvec);
+    const long long n = i / (S * cvec);
+    const long long vi = (n * S + s) * cvec + cg;
+    const uint4 g = __ldg(gz + vi), l = __ldg(logvar + vi);
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gf = unpack_bf16x2(gw[k]), lf = unpack_bf16x2(lw[k]);
+      const float e0 = __ldg(eps + (n * C + (cg * 8 + 2 * k)) * S + s);
+      const float e1 = __ldg(eps + (n * C + (cg * 8 + 2 * k + 1)) * S + s);
+      r[k] = pack_bf16x2(gf.x * e0 * 0.5f * expf(0.5f * lf.x), gf.y * e1 * 0.5f * expf(0.5f * lf.y));
+    }
+    gmu[vi] = g;
+    glogvar[vi] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, float* __restrict__ out,
+                                                     long long n, float inv_n) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mu[i], l = logvar[i];
+    acc += -0.5f * (1.f + l - m * m - expf(l));
+  }
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, s * inv_n);
+}
+__global__ void kl_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ mu, const float* __restrict__ logvar,
+                              float* __restrict__ gmu, float* __restrict__ glogvar, long long n, float inv_n) {
+  const float g = gout[0] * inv_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    gmu[i] = g * mu[i];
+    glogvar[i] = g * 0.5f * (expf(logvar[i]) - 1.f);
+  }
+}
+
+// ===============================================================================================================
+// WGAN-GP penalty                          reference: modules/utils.py:18
+// ===============================================================================================================
+__global__ void __launch_bounds__(256) gp_fwd_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int C, long long S,
+                                                     float coef) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const long long total = (long long)N * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, s = i % S;
+    float q = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = g[(n * C + c) * S + s];
+      q = fmaf(v, v, q);
+    }
+    const float d = sqrtf(q) - 1.f;
+    acc = fmaf(d, d, acc);
+  }
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, s * coef);
+}
+__global__ void gp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ g, float* __restrict__ gg, int N, int C,
+                              long long S, float coef) {
+  const float go = gout[0] * coef * 2.f;
+  const long long total = (long long)N * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, s = i % S;
+    float q = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = g[(n * C + c) * S + s];
+      q = fmaf(v, v, q);
+    }
+    const float nrm = sqrtf(q);
+    const float f = nrm > 0.f ? go * (nrm - 1.f) / nrm : 0.f;
+    for (int c = 0; c < C; ++c) gg[(n * C + c) * S + s] = f * g[(n * C + c) * S + s];
+  }
+}
+
+// ===============================================================================================================
+// layout / dtype conversion, lerp, channel sums, weight packing
+// ===============================================================================================================
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C, long long S) {
+  const long long total = (long long)N * S * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long s = (i / C) % S, n = i / (C * S);
+    dst[i] = f2bf(src[(n * C + c) * S + s]);
+  }
+}
+__global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int N, int C, long long S) {
+  const long long total = (long long)N * S * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i % S;
+    const int c = (int)((i / S) % C);
+    const long long n = i / (S * C);
+    dst[i] = bf2f(src[(n * S + s) * C + c]);
+  }
+}
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, float alpha, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = alpha * a[i] + (1.f - alpha) * b[i];
+}
+
+// NDHWC bf16: block = 256 threads = (256/C rows) x C channels
+__global__ void __launch_bounds__(256) channel_sum_ndhwc_kernel(const __nv_bfloat16* __restrict__ t, float* __restrict__ out, long long rows,
+                                                                int C) {
+  __shared__ float part[256];
+  const int rpb = blockDim.x / C;
+  const int c = threadIdx.x % C, rl = threadIdx.x / C;
+  float acc = 0.f;
+  if (rl < rpb)
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) acc += bf2f(t[r * C + c]);
+  part[threadIdx.x] = (rl < rpb) ? acc : 0.f;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int r = 0; r < rpb; ++r) s += part[r * C + threadIdx.x];
+    atomicAdd(out + threadIdx.x, s);
+  }
+}
+// NCDHW fp32: blockIdx.y = n*C + c, blockIdx.x = chunk of the spatial run
+__global__ void __launch_bounds__(256) channel_sum_ncdhw_kernel(const float* __restrict__ t, float* __restrict__ out, int C, long long S) {
+  __shared__ float red[8];
+  const int c = blockIdx.y % C;
+  const float* p = t + (long long)blockIdx.y * S;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x) acc += p[i];
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out + c, s);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int transposed,
+                                    const float* __restrict__ sigma) {
+  const float inv = sigma ? 1.f / sigma[0] : 1.f;
+  const long long total = (long long)taps * Cout * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int t = (int)(i / ((long long)Cin * Cout));
+    const float v = transposed ? w[((size_t)ci * Cout + co) * taps + (taps - 1 - t)] : w[((size_t)co * Cin + ci) * taps + t];
+    out[i] = f2bf(v * inv);
+  }
+}
+
+// ===============================================================================================================
+// spectral normalisation                   reference: nn.utils.spectral_norm as used at modules/networks_3d.py:63
+// ===============================================================================================================
+// v_raw[k] = sum_r W[r][k] u[r] ; norm2_v += v_raw[k]^2
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ v_raw,
+                                                     float* __restrict__ norm2_v, int Cout, int K) {
+  __shared__ float red[8];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (k < K)
+    for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
+  if (k < K) v_raw[k] = acc;
+  const float s = block_sum_256(k < K ? acc * acc : 0.f, red);
+  if (threadIdx.x == 0) atomicAdd(norm2_v, s);
+}
+// t_raw[r] = sum_k W[r][k] vec[k] ; norm2 += t_raw[r]^2
+__global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ vec, float* __restrict__ t_raw,
+                                                    float* __restrict__ norm2, int K) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) acc = fmaf(W[(size_t)r * K + k], vec[k], acc);
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) {
+    t_raw[r] = s;
+    atomicAdd(norm2, s * s);
+  }
+}
+__global__ void __launch_bounds__(256) sn_finalize_kernel(float* __restrict__ u, float* __restrict__ v, float* __restrict__ sigma,
+                                                          const float* __restrict__ v_raw, const float* __restrict__ t_raw,
+                                                          const float* __restrict__ norms, int Cout, int K, int update_uv, float eps) {
+  __shared__ float red[8];
+  if (update_uv) {
+    const float nv = fmaxf(sqrtf(norms[0]), eps);
+    const float tn = sqrtf(norms[1]) / nv;  // || W v ||
+    const float nu = fmaxf(tn, eps);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) v[k] = v_raw[k] / nv;
+    for (int r = threadIdx.x; r < Cout; r += blockDim.x) u[r] = (t_raw[r] / nv) / nu;
+    if (threadIdx.x == 0) sigma[0] = tn * tn / nu;  // u^T (W v)
+  } else {
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < Cout; r += blockDim.x) acc = fmaf(u[r], t_raw[r], acc);
+    const float s = block_sum_256(acc, red);
+    if (threadIdx.x == 0) sigma[0] = s;
+  }
+}
+__global__ void sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ sigma, float* __restrict__ w_sn, long long n) {
+  const float inv = 1.f / sigma[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w_sn[i] = w[i] * inv;
+}
+__global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(a[i], b[i], acc);
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+__global__ void sn_bwd_kernel(const float* __restrict__ gw_sn, const float* __restrict__ u, const float* __restrict__ v,
+                              const float* __restrict__ sigma, const float* __restrict__ dot, float* __restrict__ gw, int Cout, int K) {
+  const float inv = 1.f / sigma[0], d = dot[0];
+  const long long total = (long long)Cout * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K), r = (int)(i / K);
+    gw[i] = (gw_sn[i] - d * u[r] * v[k]) * inv;
+  }
+}
+
+}  // namespace hpvg
+
+// =================================================================================================================
+// C-ABI
+// =================================================================================================================
+using namespace hpvg;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define MEMSET0(ptr, bytes, st, name)                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = cudaMemsetAsync(ptr, 0, bytes, st);                                \
+    if (e_ != cudaSuccess) {                                                            \
+      set_error("%s: memset failed: %s", name, cudaGetErrorString(e_));                 \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+extern "C" {
+
+int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     long long* nbt, float momentum, float eps, long long count, float* scale_shift, float* mean_invstd, int C,
+                     void* stream) {
+  HPVG_CHECK_ARG(C > 0 && count > 0, "bn_finalize: bad C=%d count=%lld", C, count);
+  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, ST(stream)>>>(stats, gamma, beta, running_mean, running_var, nbt, momentum, eps,
+                                                                      count, scale_shift, mean_invstd, C);
+  HPVG_CHECK_LAUNCH("bn_finalize");
+  return 0;
+}
+
+int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long long nvox, int C, float slope, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 1024, "bn_apply_lrelu: C=%d must be a multiple of 8 (<= 1024)", C);
+  const long long nvec = nvox * (C / 8);
+  bn_apply_lrelu_kernel<<<ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream)>>>(
+      reinterpret_cast<const uint4*>(y), scale_shift, reinterpret_cast<uint4*>(out), nvec, C, slope);
+  HPVG_CHECK_LAUNCH("bn_apply_lrelu");
+  return 0;
+}
+
+int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
+                             long long nvox, int C, float slope, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 256, "bn_lrelu_bwd_reduce: C=%d must be a multiple of 8 (<= 256)", C);
+  MEMSET0(sums, 2 * C * sizeof(float), ST(stream), "bn_lrelu_bwd_reduce");
+  const int rows = 256 / (C / 8);
+  const size_t smem = (size_t)(4 * C + rows * 2 * C) * sizeof(float);
+  const int blocks = (int)max(1LL, min(cdiv(nvox, rows), (long long)num_sms() * 4));
+  bn_lrelu_bwd_reduce_kernel<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout),
+                                                                scale_shift, mean_invstd, sums, nvox, C, slope);
+  HPVG_CHECK_LAUNCH("bn_lrelu_bwd_reduce");
+  return 0;
+}
+
+int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, const float* sums,
+                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 1024, "bn_lrelu_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long nvec = nvox * (C / 8);
+  bn_lrelu_bwd_apply_kernel<<<ew_blocks(nvec, 256), 256, 6 * C * sizeof(float), ST(stream)>>>(
+      reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift, mean_invstd, sums,
+      reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope);
+  HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
+  return 0;
+}
+
+int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, void* stream) {
+  HPVG_CHECK_ARG(numel % 8 == 0, "lrelu_bwd: numel=%lld must be a multiple of 8", numel);
+  const long long nvec = numel / 8;
+  lrelu_bwd_kernel<<<ew_blocks(nvec, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(gout),
+                                                                 reinterpret_cast<const uint4*>(out_saved), reinterpret_cast<uint4*>(gz),
+                                                                 nvec, slope);
+  HPVG_CHECK_LAUNCH("lrelu_bwd");
+  return 0;
+}
+
+static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+int hpvg_upsample_linear_fwd(const float* x, float* out, const float* noise, float noise_amp, int NC, int Di, int Hi, int Wi, int Do,
+                             int Ho, int Wo, void* stream) {
+  HPVG_CHECK_ARG(NC > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample_linear_fwd: bad extents");
+  const long long total = (long long)NC * Do * Ho * Wo;
+  upsample_fwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(x, out, noise, noise_amp, NC, Di, Hi, Wi, Do, Ho, Wo,
+                                                                     ac_scale(Di, Do), ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  HPVG_CHECK_LAUNCH("upsample_linear_fwd");
+  return 0;
+}
+
+int hpvg_upsample_linear_bwd(const float* gout, float* gx, int NC, int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream) {
+  HPVG_CHECK_ARG(NC > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample_linear_bwd: bad extents");
+  const long long total = (long long)NC * Di * Hi * Wi;
+  upsample_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(gout, gx, NC, Di, Hi, Wi, Do, Ho, Wo, ac_scale(Di, Do),
+                                                                     ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+  HPVG_CHECK_LAUNCH("upsample_linear_bwd");
+  return 0;
+}
+
+int hpvg_tanh_add_fwd(const float* a, const float* b, float* out, long long numel, void* stream) {
+  tanh_add_fwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(a, b, out, numel);
+  HPVG_CHECK_LAUNCH("tanh_add_fwd");
+  return 0;
+}
+int hpvg_tanh_bwd(const float* gout, const float* out, float* g, long long numel, void* stream) {
+  tanh_bwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(gout, out, g, numel);
+  HPVG_CHECK_LAUNCH("tanh_bwd");
+  return 0;
+}
+
+int hpvg_reparam_fwd(const void* mu, const void* logvar, const float* eps, void* z, int N, int C, long long spatial, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0, "reparam_fwd: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * spatial * (C / 8);
+  reparam_fwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(mu), reinterpret_cast<const uint4*>(logvar),
+                                                                    eps, reinterpret_cast<uint4*>(z), N, C, spatial);
+  HPVG_CHECK_LAUNCH("reparam_fwd");
+  return 0;
+}
+int hpvg_reparam_bwd(const void* gz, const void* logvar, const float* eps, void* gmu, void* glogvar, int N, int C, long long spatial,
+                     void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0, "reparam_bwd: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * spatial * (C / 8);
+  reparam_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(gz), reinterpret_cast<const uint4*>(logvar),
+                                                                    eps, reinterpret_cast<uint4*>(gmu), reinterpret_cast<uint4*>(glogvar), N, C,
+                                                                    spatial);
+  HPVG_CHECK_LAUNCH("reparam_bwd");
+  return 0;
+}
+
+int hpvg_kl_fwd(const float* mu, const float* logvar, float* out, long long numel, void* stream) {
+  HPVG_CHECK_ARG(numel > 0, "kl_fwd: empty input");
+  MEMSET0(out, sizeof(float), ST(stream), "kl_fwd");
+  kl_fwd_kernel<<<(int)min((long long)num_sms() * 2, cdiv(numel, 256)), 256, 0, ST(stream)>>>(mu, logvar, out, numel, 1.f / (float)numel);
+  HPVG_CHECK_LAUNCH("kl_fwd");
+  return 0;
+}
+int hpvg_kl_bwd(const float* gout, const float* mu, const float* logvar, float* gmu, float* glogvar, long long numel, void* stream) {
+  kl_bwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(gout, mu, logvar, gmu, glogvar, numel, 1.f / (float)numel);
+  HPVG_CHECK_LAUNCH("kl_bwd");
+  return 0;
+}
+
+int hpvg_gp_penalty_fwd(const float* g, float* out, int N, int C, long long spatial, float lambda, void* stream) {
+  HPVG_CHECK_ARG(N > 0 && C > 0 && spatial > 0, "gp_penalty_fwd: bad extents");
+  MEMSET0(out, sizeof(float), ST(stream), "gp_penalty_fwd");
+  const long long total = (long long)N * spatial;
+  gp_fwd_kernel<<<(int)min((long long)num_sms() * 2, cdiv(total, 256)), 256, 0, ST(stream)>>>(g, out, N, C, spatial, lambda / (float)total);
+  HPVG_CHECK_LAUNCH("gp_penalty_fwd");
+  return 0;
+}
+int hpvg_gp_penalty_bwd(const float* gout, const float* g, float* gg, int N, int C, long long spatial, float lambda, void* stream) {
+  const long long total = (long long)N * spatial;
+  gp_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(gout, g, gg, N, C, spatial, lambda / (float)total);
+  HPVG_CHECK_LAUNCH("gp_penalty_bwd");
+  return 0;
+}
+
+int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, int N, int C, long long spatial, void* stream) {
+  const long long total = (long long)N * C * spatial;
+  if (src_fmt == HPVG_FMT_NCDHW_F32 && dst_fmt == HPVG_FMT_NDHWC_BF16) {
+    ncdhw_to_ndhwc_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src),
+                                                                         reinterpret_cast<__nv_bfloat16*>(dst), N, C, spatial);
+  } else if (src_fmt == HPVG_FMT_NDHWC_BF16 && dst_fmt == HPVG_FMT_NCDHW_F32) {
+    ndhwc_to_ncdhw_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                                         reinterpret_cast<float*>(dst), N, C, spatial);
+  } else {
+    set_error("convert_format: unsupported conversion %d -> %d", src_fmt, dst_fmt);
+    return -1;
+  }
+  HPVG_CHECK_LAUNCH("convert_format");
+  return 0;
+}
+
+int hpvg_lerp(const float* a, const float* b, float* out, float alpha, long long numel, void* stream) {
+  lerp_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(a, b, out, alpha, numel);
+  HPVG_CHECK_LAUNCH("lerp");
+  return 0;
+}
+
+int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long spatial, void* stream) {
+  HPVG_CHECK_ARG(N > 0 && C > 0 && spatial > 0, "channel_sum: bad extents");
+  MEMSET0(out, C * sizeof(float), ST(stream), "channel_sum");
+  if (fmt == HPVG_FMT_NDHWC_BF16) {
+    HPVG_CHECK_ARG(C <= 256, "channel_sum: C=%d too large for the NDHWC kernel", C);
+    const long long rows = (long long)N * spatial;
+    const int rpb = 256 / C;
+    const int blocks = (int)max(1LL, min(cdiv(rows, (long long)rpb * 8), (long long)num_sms() * 4));
+    channel_sum_ndhwc_kernel<<<blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(t), out, rows, C);
+  } else {
+    dim3 grid((unsigned)max(1LL, min(cdiv(spatial, 2048), 64LL)), (unsigned)(N * C));
+    channel_sum_ncdhw_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(t), out, C, spatial);
+  }
+  HPVG_CHECK_LAUNCH("channel_sum");
+  return 0;
+}
+
+int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed, const float* inv_scale_of,
+                      void* stream) {
+  const long long total = (long long)taps * Cout * Cin;
+  pack_weights_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(w_f32, reinterpret_cast<__nv_bfloat16*>(w_packed), Cout, Cin, taps,
+                                                                     transposed, inv_scale_of);
+  HPVG_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, float* w_sn, float* scratch, int Cout, int K,
+                       int update_uv, float eps, void* stream) {
+  HPVG_CHECK_ARG(Cout > 0 && K > 0, "sn_power_iter: bad shape");
+  float* v_raw = scratch;
+  float* t_raw = scratch + K;
+  float* norms = scratch + K + Cout;
+  MEMSET0(norms, 4 * sizeof(float), ST(stream), "sn_power_iter");
+  if (update_uv) {
+    sn_wtu_kernel<<<(unsigned)cdiv(K, 256), 256, 0, ST(stream)>>>(w_orig, u, v_raw, norms, Cout, K);
+    HPVG_CHECK_LAUNCH("sn_wtu");
+    sn_wv_kernel<<<Cout, 256, 0, ST(stream)>>>(w_orig, v_raw, t_raw, norms + 1, K);
+  } else {
+    sn_wv_kernel<<<Cout, 256, 0, ST(stream)>>>(w_orig, v, t_raw, norms + 1, K);
+  }
+  HPVG_CHECK_LAUNCH("sn_wv");
+  sn_finalize_kernel<<<1, 256, 0, ST(stream)>>>(u, v, sigma, v_raw, t_raw, norms, Cout, K, update_uv, eps);
+  HPVG_CHECK_LAUNCH("sn_finalize");
+  if (w_sn) {
+    const long long n = (long long)Cout * K;
+    sn_scale_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(w_orig, sigma, w_sn, n);
+    HPVG_CHECK_LAUNCH("sn_scale");
+  }
+  return 0;
+}
+
+int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, const float* v, const float* sigma, float* gw_orig,
+                     float* scratch, int Cout, int K, void* stream) {
+  const long long n = (long long)Cout * K;
+  MEMSET0(scratch, sizeof(float), ST(stream), "sn_backward");
+  dot_kernel<<<(int)min((long long)num_sms(), cdiv(n, 256)), 256, 0, ST(stream)>>>(gw_sn, w_sn, scratch, n);
+  HPVG_CHECK_LAUNCH("sn_dot");
+  sn_bwd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(gw_sn, u, v, sigma, scratch, gw_orig, Cout, K);
+  HPVG_CHECK_LAUNCH("sn_bwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// tcgen05 weight-gradient kernel for the wide layers (Cin, Cout multiples of 64, NDHWC bf16 operands).
+//
+// Replaces aten::convolution_backward(grad_weight) of nn.Conv3d/Conv2d (modules/networks_3d.py:51,63) and the
+// "wgrad-as-conv" nodes of the WGAN-GP double backward (modules/utils.py:14-18).
+//
+//   dw[co][ci][kd,kh,kw] = sum_{n,od,oh,ow} gy[n,od,oh,ow,co] * x[n,od+kd-p,oh+kh-p,ow+kw-p,ci]
+//
+// GEMM view per tap: D[ci][co] += X_tap^T[ci][voxel] * GY[voxel][co], K = voxels.  Both operands are MN-major views of
+// NDHWC rows (128 B = 64 channels per voxel), so TMA tiles feed tcgen05 directly:
+//  * B = the gy brick (16 x 8 output voxels x 64 co), a plain 128-row tile.
+//  * A = the x halo slab of the matching input slice ((16+2) x (8+2) voxels x 64 ci); tap (kh,kw) is the same slab read
+//    with the descriptor start moved by kh*10+kw rows and K-groups (8 voxels of one brick row) 10 rows apart.
+//  * Two taps share one M = 128 instruction: the second 64-row atom of A is the slab shifted by the row distance
+//    between the taps (descriptor LBO), so the tensor core runs at full M (verified by experiments/umma_desc_probe.cu
+//    tests 17-21).  9 taps of one kd -> 5 accumulators x 64 TMEM columns.
+//  * grid = (voxel splits, 64x64 channel blocks, KD); each CTA reduces its bricks into TMEM, then writes one fp32
+//    partial; a second kernel sums the splits in fixed order (deterministic) into PyTorch [Cout][Cin][taps] layout.
+#include "common.cuh"
+
+namespace hpvg {
+
+constexpr int WG_BH = 16, WG_BW = 8;
+constexpr int WG_SLAB_W = WG_BW + 2, WG_SLAB_H = WG_BH + 2;
+constexpr int WG_SLAB_BYTES = WG_SLAB_H * WG_SLAB_W * 128;   // 23040
+constexpr int WG_SLAB_STRIDE = 23 * 1024;
+constexpr int WG_GY_BYTES = 128 * 128;                        // 16384
+constexpr int WG_STAGE_BYTES = WG_SLAB_STRIDE + WG_GY_BYTES;  // 39936 (multiple of 1024)
+constexpr int WG_STAGES = 5;
+constexpr int WG_THREADS = 192;
+constexpr int WG_NACC = 5;
+constexpr int WG_TMEM_COLS = 512;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+
+struct WgParams {
+  ConvGeom g;
+  int bricks_h, bricks_w;
+  long long num_bricks;       // N * Do * bricks_h * bricks_w  (over gy / output voxels)
+  long long bricks_per_split;
+  int splits;
+  float* partial;             // [splits][taps][Cin][Cout] fp32
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_gy, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const uint32_t s_bar = sbase + WG_STAGES * WG_STAGE_BYTES;
+  auto bar_full = [&](int i) { return s_bar + 8u * i; };
+  auto bar_empty = [&](int i) { return s_bar + 8u * (WG_STAGES + i); };
+  const uint32_t bar_acc = s_bar + 8u * (2 * WG_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  const int split = blockIdx.x;
+  const int cblocks_in = g.Cin / 64;
+  const int ci_blk = blockIdx.y % cblocks_in, co_blk = blockIdx.y / cblocks_in;
+  const int kd = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(bar_full(i), 1);
+      mbar_init(bar_empty(i), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_gy);
+  }
+  if (warp == 1) tmem_alloc<WG_TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long b_begin = (long long)split * p.bricks_per_split;
+  const long long b_end = min(p.num_bricks, b_begin + p.bricks_per_split);
+
+  // brick -> (n, od, h0, w0); returns false when the input slice of this kd is outside the tensor (zero contribution)
+  auto decode = [&](long long b, int& n, int& od, int& h0, int& w0) -> bool {
+    w0 = (int)(b % p.bricks_w) * WG_BW;
+    b /= p.bricks_w;
+    h0 = (int)(b % p.bricks_h) * WG_BH;
+    b /= p.bricks_h;
+    od = (int)(b % g.Do);
+    n = (int)(b / g.Do);
+    const int d = od + kd - g.pad_d;
+    return d >= 0 && d < g.Di;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long b = b_begin; b < b_end; ++b) {
+        int n, od, h0, w0;
+        if (!decode(b, n, od, h0, w0)) continue;
+        mbar_wait(bar_empty(stage), phase ^ 1u);
+        mbar_expect_tx(bar_full(stage), WG_SLAB_BYTES + WG_GY_BYTES);
+        const uint32_t sa = sbase + stage * WG_STAGE_BYTES;
+        tma_load_5d(sa, &tmap_x, bar_full(stage), ci_blk * 64, w0 - g.pad, h0 - g.pad, od + kd - g.pad_d, n);
+        tma_load_5d(sa + WG_SLAB_STRIDE, &tmap_gy, bar_full(stage), co_blk * 64, w0, h0, od, n);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);   // A and B MN-major
+    uint32_t stage = 0, phase = 0;
+    uint32_t first = 1;
+    for (long long b = b_begin; b < b_end; ++b) {
+      int n, od, h0, w0;
+      if (!decode(b, n, od, h0, w0)) continue;
+      mbar_wait(bar_full(stage), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = sbase + stage * WG_STAGE_BYTES;
+        const uint32_t sb = sa + WG_SLAB_STRIDE;
+#pragma unroll
+        for (int pr = 0; pr < WG_NACC; ++pr) {
+          // taps q0 = 2*pr and q1 = 2*pr+1 (q = kh*3 + kw); the last pair duplicates tap 8
+          const int q0 = 2 * pr, q1 = (2 * pr + 1 <= 8) ? 2 * pr + 1 : 8;
+          const int off0 = (q0 / 3) * WG_SLAB_W + (q0 % 3), off1 = (q1 / 3) * WG_SLAB_W + (q1 % 3);
+          const uint32_t lbo = (uint32_t)(off1 - off0) * 128u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            // K step = 16 voxels = brick rows 2ks, 2ks+1 (8 voxels each)
+            const uint64_t ad = umma_desc(sa + (uint32_t)(off0 + 2 * ks * WG_SLAB_W) * 128u, lbo, WG_SLAB_W * 128, 2);
+            const uint64_t bd = umma_desc(sb + ks * 2048, 16, 1024, 2);
+            umma_bf16(tmem_base + pr * 64, ad, bd, IDESC, (uint32_t)((!first) | (ks > 0)));
+          }
+        }
+        umma_commit(bar_empty(stage));
+      }
+      first = 0;
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (lane == 0) umma_commit(bar_acc);
+    __syncwarp();
+  } else {
+    // ===================== drain: TMEM -> fp32 partial [tap][ci][co] =====================
+    bool any = false;
+    for (long long b = b_begin; b < b_end; ++b) {
+      int n, od, h0, w0;
+      if (decode(b, n, od, h0, w0)) { any = true; break; }
+    }
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;           // TMEM lane: (m / 64) selects the tap of the pair, m % 64 = ci
+    const int ci = ci_blk * 64 + (m & 63);
+    for (int pr = 0; pr < WG_NACC; ++pr) {
+      const int tap9 = 2 * pr + (m >> 6);
+      uint32_t r[64];
+      if (any) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + pr * 64;
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + 32, r + 32);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) r[j] = 0u;
+      }
+      if (tap9 <= 8) {
+        const int tap = kd * 9 + tap9;
+        float4* dst = reinterpret_cast<float4*>(p.partial + (((size_t)split * g.taps + tap) * g.Cin + ci) * g.Cout + co_blk * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
+}
+
+// dw[co][ci][tap] = sum_s partial[s][tap][ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps, int Cin, int Cout) {
+  const long long total = (long long)taps * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int tap = (int)(i / ((long long)Cout * Cin));
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * total + i];
+    dw[((size_t)co * Cin + ci) * taps + tap] = s;
+  }
+}
+
+bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g) {
+  return x_fmt == HPVG_FMT_NDHWC_BF16 && gy_fmt == HPVG_FMT_NDHWC_BF16 && g.Cin % 64 == 0 && g.Cout % 64 == 0 && g.Cin >= 64 &&
+         g.Cout >= 64;
+}
+
+static void wgrad_plan(const ConvGeom& g, int& bricks_h, int& bricks_w, long long& num_bricks, int& splits, long long& per_split) {
+  bricks_h = (int)cdiv(g.Ho, WG_BH);
+  bricks_w = (int)cdiv(g.Wo, WG_BW);
+  num_bricks = (long long)g.N * g.Do * bricks_h * bricks_w;
+  const int others = g.KD * (g.Cin / 64) * (g.Cout / 64);
+  long long want = max(1LL, (long long)num_sms() / others);
+  want = min(want, num_bricks);
+  per_split = cdiv(num_bricks, want);
+  splits = (int)cdiv(num_bricks, per_split);
+}
+
+size_t wgrad_tc_workspace(const ConvGeom& g) {
+  int bh, bw, splits;
+  long long nb, per;
+  wgrad_plan(g, bh, bw, nb, splits, per);
+  return (size_t)splits * g.taps * g.Cin * g.Cout * sizeof(float);
+}
+
+int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  WgParams p;
+  p.g = g;
+  wgrad_plan(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
+  const size_t need = (size_t)p.splits * g.taps * g.Cin * g.Cout * sizeof(float);
+  if (ws_bytes < need || workspace == nullptr) {
+    set_error("wgrad_tc: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return -1;
+  }
+  p.partial = reinterpret_cast<float*>(workspace);
+  CUtensorMap mx, mg;
+  {
+    uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.Di, (uint64_t)g.N};
+    uint32_t box[5] = {64, WG_SLAB_W, WG_SLAB_H, 1, 1};
+    if (int rc = make_tmap_bf16(&mx, x, 5, dims, box)) return rc;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)g.N};
+    uint32_t box[5] = {64, WG_BW, WG_BH, 1, 1};
+    if (int rc = make_tmap_bf16(&mg, gy, 5, dims, box)) return rc;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("wgrad_tc: cannot opt in to %d bytes of shared memory: %s", WG_SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_done = true;
+  }
+  dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), (unsigned)g.KD);
+  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(mx, mg, p);
+  HPVG_CHECK_LAUNCH("wgrad_tc_kernel");
+  const long long total = (long long)g.taps * g.Cin * g.Cout;
+  const int rblocks = (int)min((long long)num_sms() * 4, cdiv(total, 256));
+  wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(p.partial, dw, p.splits, g.taps, g.Cin, g.Cout);
+  HPVG_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return 0;
+}
+
+}  // namespace hpvg

@@ -1,0 +1,323 @@
+"""Dimension-agnostic building blocks behind the drop-in `modules.networks_3d` / `modules.networks_2d`.
+
+Every class keeps the reference's parameter containers (nn.ConvNd, nn.BatchNormNd, legacy spectral_norm buffers),
+so construction consumes the RNG exactly like the reference, `state_dict()` has identical keys and shapes
+(SURVEY.md App. E), and `copy.deepcopy`, `.to()`, `nn.DataParallel.replicate` and optimizers work unchanged.  Only
+`forward` differs: it hands the parameters to the libhpvg kernels through hpvg.ops.  Internally activations are
+"wide" ([N,D,H,W,C] bf16) between layers and "thin" ([N,C,D,H,W] fp32) at the module boundary.
+
+Reference classes restated here: ConvBlock3D/2D (modules/networks_3d.py:48-56, networks_2d.py:53-61),
+ConvBlock3DSN/2DSN (:59-70 / :64-75), FeatureExtractor (:73-85 / :78-90), Encode3DVAE/Encode2DVAE (:88-107 / :93-112),
+WDiscriminator3D/2D (:163-181 / :168-185), GeneratorHPVAEGAN (:325-406 / :188-269), GeneratorSG (:272-322).
+"""
+import copy
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import images, ops
+
+LRELU_SLOPE = 0.2
+
+
+def _conv_cls(dims):
+    return nn.Conv3d if dims == 3 else nn.Conv2d
+
+
+def _bn_cls(dims):
+    return nn.BatchNorm3d if dims == 3 else nn.BatchNorm2d
+
+
+def as5d(t):
+    """[N,C,H,W] -> [N,C,1,H,W] (2-D networks run the same kernels with D == 1)"""
+    return t.unsqueeze(2) if t.dim() == 4 else t
+
+
+def like_input(t5, dims):
+    return t5.squeeze(2) if dims == 2 else t5
+
+
+def _check_device(t):
+    if not t.is_cuda:
+        raise ops.lib.HpvgError("hpvg-b200 modules run on CUDA tensors only (got %s); there is no CPU fallback" % t.device)
+
+
+class ConvBlock(nn.Sequential):
+    """conv + BatchNorm(train statistics) + LeakyReLU(0.2); with bn=False, act=None it is a bare conv (mu/logvar heads)."""
+    dims = 3
+
+    def __init__(self, in_channel, out_channel, ker_size, padding, stride, bn=True, act='lrelu'):
+        super().__init__()
+        if ker_size != 3 or stride != 1:
+            raise NotImplementedError("hpvg-b200 kernels cover 3x3(x3), stride 1 convolutions (the reference's only configuration)")
+        if act not in (None, 'lrelu'):
+            raise NotImplementedError("only LeakyReLU(0.2) is fused; got act=%r" % (act,))
+        self.add_module('conv', _conv_cls(self.dims)(in_channel, out_channel, kernel_size=ker_size, stride=stride, padding=padding))
+        if bn:
+            self.add_module('norm', _bn_cls(self.dims)(out_channel))
+        if act is not None:
+            self.add_module(act, nn.LeakyReLU(LRELU_SLOPE, inplace=True))
+        self.pad = int(padding)
+        self.has_bn, self.has_act = bool(bn), act is not None
+
+    def run(self, x, out_wide=True):
+        """x: wide or thin 5-D tensor -> wide (or thin when out_wide=False and no BN/activation)"""
+        conv = self.conv
+        if self.has_bn:
+            norm = self.norm
+            if not self.has_act:
+                raise NotImplementedError("BatchNorm without LeakyReLU is not on the reference path")
+            if norm.training or not norm.track_running_stats:
+                return ops.conv_bn_lrelu(x, conv.weight, conv.bias, norm.weight, norm.bias, norm.running_mean, norm.running_var,
+                                         norm.num_batches_tracked, self.pad, momentum=norm.momentum, eps=norm.eps, slope=LRELU_SLOPE)
+            raise NotImplementedError("eval-mode BatchNorm is never reached by the reference (the generator stays in train mode)")
+        return ops.conv(x, conv.weight, conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None)
+
+    def forward(self, x):
+        _check_device(x)
+        y = self.run(as5d(x).contiguous(), out_wide=True)
+        return like_input(ops.ToThin.apply(y), self.dims)
+
+
+class ConvBlockSN(nn.Sequential):
+    """spectral-normalised conv + LeakyReLU(0.2) (no BatchNorm: in the reference the `bn` flag selects spectral norm)."""
+    dims = 3
+
+    def __init__(self, in_channel, out_channel, ker_size, padding, stride, bn=True, act='lrelu'):
+        super().__init__()
+        if ker_size != 3 or stride != 1:
+            raise NotImplementedError("hpvg-b200 kernels cover 3x3(x3), stride 1 convolutions")
+        if not bn:
+            raise NotImplementedError("the reflect-padded non-spectral branch is never used by the reference networks")
+        if act not in (None, 'lrelu'):
+            raise NotImplementedError("only LeakyReLU(0.2) is fused; got act=%r" % (act,))
+        self.add_module('conv', nn.utils.spectral_norm(
+            _conv_cls(self.dims)(in_channel, out_channel, kernel_size=ker_size, stride=stride, padding=padding)))
+        if act is not None:
+            self.add_module(act, nn.LeakyReLU(LRELU_SLOPE, inplace=True))
+        self.pad = int(padding)
+        self.has_act = act is not None
+
+    def weight(self):
+        """one power iteration (training mode) + W/sigma, as torch's legacy spectral_norm pre-forward hook does"""
+        conv = self.conv
+        return ops.SpectralWeight.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, 1e-12)
+
+    def run(self, x, out_wide=True):
+        return ops.conv(x, self.weight(), self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None)
+
+    def forward(self, x):
+        _check_device(x)
+        return like_input(ops.ToThin.apply(self.run(as5d(x))), self.dims)
+
+
+def _run_chain(seq, x):
+    for m in seq:
+        x = m.run(x)
+    return x
+
+
+def make_family(dims):
+    """Build the 2-D or 3-D family of classes (the reference keeps two copies of this code)."""
+
+    class _ConvBlock(ConvBlock):
+        pass
+
+    class _ConvBlockSN(ConvBlockSN):
+        pass
+
+    _ConvBlock.dims = dims
+    _ConvBlockSN.dims = dims
+    Conv = _conv_cls(dims)
+
+    class FeatureExtractor(nn.Sequential):
+        def __init__(self, in_channel, out_channel, ker_size, padding, stride, num_blocks=2, return_linear=False):
+            super().__init__()
+            if return_linear:
+                raise NotImplementedError("return_linear=True is never used by the reference networks")
+            for i in range(num_blocks + 1):
+                cin = in_channel if i == 0 else out_channel
+                self.add_module('conv_block_{}'.format(i), _ConvBlockSN(cin, out_channel, ker_size, padding, stride))
+
+        def run(self, x):
+            return _run_chain(self, x)
+
+        def forward(self, x):
+            _check_device(x)
+            return like_input(ops.ToThin.apply(self.run(as5d(x))), dims)
+
+    class EncodeVAE(nn.Module):
+        def __init__(self, opt, out_dim=None, num_blocks=2):
+            super().__init__()
+            if out_dim is None:
+                out_dim = opt.nfc
+            elif type(out_dim) is not int:
+                raise AssertionError("out_dim must be an int")
+            half = opt.ker_size // 2
+            self.features = FeatureExtractor(opt.nc_im, opt.nfc, opt.ker_size, half, 1, num_blocks=num_blocks)
+            self.mu = _ConvBlock(opt.nfc, out_dim, opt.ker_size, half, 1, bn=False, act=None)
+            self.logvar = _ConvBlock(opt.nfc, out_dim, opt.ker_size, half, 1, bn=False, act=None)
+
+        def run(self, x5):
+            """thin video -> (mu, logvar) wide"""
+            feat = self.features.run(x5)
+            return self.mu.run(feat), self.logvar.run(feat)
+
+        def forward(self, x):
+            _check_device(x)
+            mu, logvar = self.run(as5d(x))
+            return like_input(ops.ToThin.apply(mu), dims), like_input(ops.ToThin.apply(logvar), dims)
+
+    class WDiscriminator(nn.Module):
+        def __init__(self, opt):
+            super().__init__()
+            self.opt = opt
+            nfc = int(opt.nfc)
+            half = opt.ker_size // 2
+            self.head = _ConvBlockSN(opt.nc_im, nfc, opt.ker_size, half, stride=1, bn=True, act='lrelu')
+            self.body = nn.Sequential()
+            for i in range(opt.num_layer):
+                self.body.add_module('block%d' % i, _ConvBlockSN(nfc, nfc, opt.ker_size, half, stride=1, bn=True, act='lrelu'))
+            self.tail = Conv(nfc, 1, kernel_size=opt.ker_size, padding=1, stride=1)
+
+        def forward(self, x):
+            _check_device(x)
+            h = self.head.run(as5d(x).contiguous())
+            h = _run_chain(self.body, h)
+            out = ops.conv(h, self.tail.weight, self.tail.bias, 1, False)   # thin critic map [N,1,(T,)H,W]
+            return like_input(out, dims)
+
+    def _stage(opt, nfc, in_channels, padding):
+        """head ConvBlock + num_layer ConvBlocks + bare tail conv: the decoder and every refinement stage"""
+        seq = nn.Sequential()
+        seq.add_module('head', _ConvBlock(in_channels, nfc, opt.ker_size, padding, stride=1))
+        for i in range(opt.num_layer):
+            seq.add_module('block%d' % i, _ConvBlock(nfc, nfc, opt.ker_size, padding, stride=1))
+        return seq
+
+    def _run_stage(seq, x5, tail_pad):
+        """thin (or wide) input -> thin output of the stage's tail conv"""
+        h = x5
+        for name, m in seq.named_children():
+            if name == 'tail':
+                return ops.conv(h, m.weight, m.bias, tail_pad, False)
+            h = m.run(h)
+        raise RuntimeError("stage has no tail conv")
+
+    class GeneratorHPVAEGAN(nn.Module):
+        def __init__(self, opt):
+            super().__init__()
+            self.opt = opt
+            self.N = int(opt.nfc)
+            self.encode = EncodeVAE(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks)
+            self.decoder = _stage(opt, self.N, opt.latent_dim, opt.padd_size)
+            self.decoder.add_module('tail', Conv(self.N, opt.nc_im, opt.ker_size, 1, opt.ker_size // 2))
+            self.body = torch.nn.ModuleList([])
+
+        def init_next_stage(self):
+            if len(self.body) == 0:
+                first = _stage(self.opt, self.N, self.opt.nc_im, self.opt.padd_size)
+                first.add_module('tail', Conv(self.N, self.opt.nc_im, self.opt.ker_size, 1, self.opt.ker_size // 2))
+                self.body.append(first)
+            else:
+                self.body.append(copy.deepcopy(self.body[-1]))
+
+        def forward(self, video, noise_amp, noise_init=None, sample_init=None, mode='rand'):
+            if sample_init is not None:
+                assert len(self.body) > sample_init[0], "Strating index must be lower than # of body blocks"
+            opt = self.opt
+            half = opt.ker_size // 2
+            if noise_init is None:
+                _check_device(video)
+                mu_w, logvar_w = self.encode.run(as5d(video).contiguous())
+                mu5, logvar5 = ops.ToThin.apply(mu_w), ops.ToThin.apply(logvar_w)
+                if self.training:
+                    eps = torch.zeros_like(mu5).normal_()          # same draw as reparameterize (reference :31-32)
+                    z = ops.Reparam.apply(mu_w, logvar_w, eps)
+                else:
+                    z = ops.ToWide.apply(torch.zeros_like(mu5).normal_())
+                mu, logvar = like_input(mu5, dims), like_input(logvar5, dims)
+            else:
+                _check_device(noise_init)
+                z = ops.ToWide.apply(as5d(noise_init).contiguous())
+            # tanh runs on the caller-visible shape so that the result is not a view (refinement may detach_() it in place)
+            vae_out = ops.TanhAdd.apply(like_input(_run_stage(self.decoder, z, half), dims), None)
+
+            if sample_init is not None:
+                x_prev_out = self.refinement_layers(sample_init[0], sample_init[1], noise_amp, mode)
+            else:
+                x_prev_out = self.refinement_layers(0, vae_out, noise_amp, mode)
+
+            if noise_init is None:
+                return x_prev_out, vae_out, (mu, logvar)
+            return x_prev_out, vae_out
+
+        def refinement_layers(self, start_idx, x_prev_out, noise_amp, mode):
+            opt = self.opt
+            half = opt.ker_size // 2
+            for idx, block in enumerate(self.body[start_idx:], start_idx):
+                if opt.vae_levels == idx + 1 and not opt.train_all:
+                    x_prev_out.detach_()
+                x5 = as5d(x_prev_out)
+                size = images.video_target_size(idx + 1, opt) if dims == 3 else [1] + images.image_target_size(idx + 1, opt)
+                x_up = images.resize(x5, size)
+                # 3-D adds noise only from the first GAN level on; 2-D adds it at every level (networks_2d.py:261-263)
+                if mode == 'rand' and (dims == 2 or opt.vae_levels <= idx + 1):
+                    noise = images.generate_noise(ref=x_up)
+                    x_in = images.resize(x5, size, noise=noise, amp=float(noise_amp[idx + 1]))
+                else:
+                    x_in = x_up
+                x_prev_out = ops.TanhAdd.apply(like_input(_run_stage(block, x_in, half), dims), like_input(x_up, dims))
+            return x_prev_out
+
+    class GeneratorSG(nn.Module):
+        """SinGAN-style baseline: valid (pad 0) convolutions on inputs zero-padded by num_layer + 2 voxels (3-D only)."""
+
+        def __init__(self, opt):
+            super().__init__()
+            if dims != 3:
+                raise NotImplementedError("GeneratorSG exists only in networks_3d")
+            self.opt = opt
+            nfc = int(opt.nfc)
+            self.margin = opt.num_layer + 2
+            self.p3d = (self.margin,) * 6
+            self.body = nn.ModuleList([])
+            first = _stage(opt, nfc, opt.nc_im, 0)
+            first.add_module('tail', Conv(nfc, opt.nc_im, kernel_size=opt.ker_size, padding=0, stride=1))
+            self.body.append(first)
+            self.apply(weights_init)
+
+        def init_next_stage(self):
+            self.body.append(copy.deepcopy(self.body[-1]))
+
+        def forward(self, noise_init, noise_amp, mode='rand'):
+            _check_device(noise_init)
+            x_prev_out = _run_stage(self.body[0], F.pad(noise_init, self.p3d).contiguous(), 0)
+            for idx, block in enumerate(self.body[1:], 1):
+                x_prev_out = ops.TanhAdd.apply(x_prev_out, None)
+                size = images.video_target_size(idx, self.opt)
+                x_up = images.resize(x_prev_out, size)
+                if mode == 'rand':
+                    big = [s + 2 * self.margin for s in size]
+                    noise = images.generate_noise(size=[x_prev_out.shape[0], x_prev_out.shape[1]] + big, device=x_prev_out.device)
+                    x_in = images.resize(x_prev_out, big, noise=noise, amp=float(noise_amp[idx]))
+                else:
+                    x_in = F.pad(x_up, self.p3d).contiguous()
+                x_prev_out = _run_stage(block, x_in, 0) + x_up
+            return ops.TanhAdd.apply(x_prev_out, None)
+
+    return {
+        'ConvBlock': _ConvBlock, 'ConvBlockSN': _ConvBlockSN, 'FeatureExtractor': FeatureExtractor, 'EncodeVAE': EncodeVAE,
+        'WDiscriminator': WDiscriminator, 'GeneratorHPVAEGAN': GeneratorHPVAEGAN, 'GeneratorSG': GeneratorSG,
+    }
+
+
+def weights_init(m):
+    """N(0, 0.02) conv weights, N(1, 0.02) norm scales — applied by the SinGAN-style baselines only (reference :9-15)."""
+    name = m.__class__.__name__
+    if 'Conv2d' in name or 'Conv3d' in name:
+        m.weight.data.normal_(0.0, 0.02)
+    elif 'Norm' in name:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0)

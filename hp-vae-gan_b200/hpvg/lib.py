@@ -1,0 +1,95 @@
+"""ctypes binding of libhpvg.so.  Signatures mirror include/hpvg.h one to one."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpvg.so")
+
+FMT_NCDHW_F32 = 0
+FMT_NDHWC_BF16 = 1
+ACT_NONE = 0
+ACT_LRELU = 1
+BACKEND_AUTO, BACKEND_DIRECT, BACKEND_TCGEN05 = 0, 1, 2
+
+# name -> (restype, argtypes); the single source for the "every symbol exports" test
+PROTOTYPES = {
+    "hpvg_last_error": (c_char_p, []),
+    "hpvg_version": (c_int, []),
+    "hpvg_set_conv_backend": (c_int, [c_int]),
+    "hpvg_get_conv_backend": (c_int, []),
+    "hpvg_launch_count": (c_longlong, []),
+    "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "hpvg_conv_wgrad_workspace": (c_size_t, [c_int] * 10),
+    "hpvg_conv_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "hpvg_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hpvg_channel_sum": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_longlong, c_void_p]),
+    "hpvg_bn_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_longlong,
+                                 c_void_p, c_void_p, c_int, c_void_p]),
+    "hpvg_bn_apply_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "hpvg_bn_lrelu_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "hpvg_bn_lrelu_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_longlong, c_int, c_float, c_void_p]),
+    "hpvg_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
+    "hpvg_upsample_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
+    "hpvg_upsample_linear_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpvg_tanh_add_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "hpvg_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "hpvg_reparam_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p]),
+    "hpvg_reparam_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p]),
+    "hpvg_kl_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "hpvg_kl_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "hpvg_gp_penalty_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_float, c_void_p]),
+    "hpvg_gp_penalty_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float, c_void_p]),
+    "hpvg_convert_format": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p]),
+    "hpvg_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_longlong, c_void_p]),
+    "hpvg_sn_power_iter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_void_p]),
+    "hpvg_sn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class HpvgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libhpvg.so (built by hp-vae-gan_b200/build.py).  Fails loudly: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HpvgError("libhpvg.so not found at %s - run `python hp-vae-gan_b200/build.py` (needs nvcc); "
+                        "hpvg-b200 has no CPU or library fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise HpvgError(hpvg_last_error()) on a non-zero return."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise HpvgError("%s failed (%d): %s" % (name, rc, lib.hpvg_last_error().decode(errors="replace")))
+
+
+def launch_count():
+    return int(load().hpvg_launch_count())
+
+
+def set_conv_backend(backend):
+    call("hpvg_set_conv_backend", int(backend))
+
+
+def get_conv_backend():
+    return int(load().hpvg_get_conv_backend())

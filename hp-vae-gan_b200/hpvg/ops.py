@@ -1,0 +1,504 @@
+"""torch.autograd.Function wrappers over libhpvg.so.
+
+Tensor conventions inside the networks
+  wide : torch.bfloat16, shape [N, D, H, W, C], contiguous  (NDHWC_BF16; every 64/128-channel activation)
+  thin : torch.float32,  shape [N, C, D, H, W], contiguous  (NCDHW_F32; videos, critic maps, the latent at the API)
+2-D networks use D == 1 and 3x3 weights (KD == 1).
+
+The conv family {ConvFwd, ConvDgrad, ConvWgrad, LReluBwd} is closed under differentiation: each backward is
+written with the other Functions (never `once_differentiable`), so `torch.autograd.grad(..., create_graph=True)`
+in calc_gradient_penalty (reference modules/utils.py:14-16) builds the second-order graph out of the same
+kernels.
+"""
+import threading
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import lib
+from .lib import ACT_LRELU, ACT_NONE, FMT_NCDHW_F32, FMT_NDHWC_BF16
+
+_tls = threading.local()
+
+
+class input_grad_only:
+    """Context: conv backward passes inside it skip weight/bias gradients (used around the first-order
+    autograd.grad of the gradient penalty, which only asks for d/d(interpolates))."""
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "input_only", False)
+        _tls.input_only = True
+
+    def __exit__(self, *a):
+        _tls.input_only = self.prev
+
+
+def _input_only():
+    return getattr(_tls, "input_only", False)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise lib.HpvgError("hpvg ops run on CUDA tensors only (got a %s tensor); there is no CPU fallback" % t.device)
+
+
+def is_wide(t):
+    return t.dtype == torch.bfloat16
+
+
+def fmt_of(t):
+    return FMT_NDHWC_BF16 if t.dtype == torch.bfloat16 else FMT_NCDHW_F32
+
+
+def dims_of(t):
+    """-> (N, C, D, H, W) of a wide or thin tensor"""
+    if t.dim() != 5:
+        raise ValueError("expected a 5-D tensor, got shape %s" % (tuple(t.shape),))
+    if is_wide(t):
+        n, d, h, w, c = t.shape
+    else:
+        n, c, d, h, w = t.shape
+    return n, c, d, h, w
+
+
+def _empty(n, c, d, h, w, wide, device):
+    if wide:
+        return torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=device)
+    return torch.empty((n, c, d, h, w), dtype=torch.float32, device=device)
+
+
+def _kd_of(weight):
+    return 3 if weight.dim() == 5 else 1
+
+
+def _tc_eligible(cin, cout, x_wide, y_wide):
+    return x_wide and y_wide and cin in (64, 128) and cout % 64 == 0 and lib.get_conv_backend() != lib.BACKEND_DIRECT
+
+
+def pack_weights(w, cout, cin, taps, transposed, sigma=None):
+    out = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
+    lib.call("hpvg_pack_weights", _ptr(w), _ptr(out), cout, cin, taps, int(transposed), _ptr(sigma), _stream())
+    return out
+
+
+def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None):
+    """One hpvg_conv_forward call.  `w` is the float32 weight of the *forward* convolution ([Cout_f, Cin_f, (3,)3,3]);
+    transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f)."""
+    _require_cuda(x, w)
+    x = x.contiguous()
+    w = w.contiguous()
+    if w.dtype != torch.float32:
+        raise TypeError("conv weights must be float32 masters")
+    n, cx, d, h, wd = dims_of(x)
+    kd = _kd_of(w)
+    taps = kd * 9
+    cout_f, cin_f = w.shape[0], w.shape[1]
+    cin, cout = (cout_f, cin_f) if transposed else (cin_f, cout_f)
+    if cx != cin:
+        raise ValueError("conv: input has %d channels, weight expects %d" % (cx, cin))
+    if kd == 1 and d != 1:
+        raise ValueError("2-D convolution needs D == 1")
+    pad_d = pad if kd == 3 else 0
+    do, ho, wo = d + 2 * pad_d - (kd - 1), h + 2 * pad - 2, wd + 2 * pad - 2
+    y = _empty(n, cout, do, ho, wo, out_wide, x.device)
+    packed = None
+    if _tc_eligible(cin, cout, is_wide(x), out_wide):
+        packed = pack_weights(w, cout, cin, taps, transposed)
+    if bias is not None:
+        bias = bias.contiguous()
+    lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,
+             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE,
+             float(act_slope) if act_slope is not None else 0.0, _ptr(stats), _ptr(mask_src), _stream())
+    return y
+
+
+def wgrad_raw(x, gy, pad, wshape, want_bias=False):
+    """dw (float32, `wshape` = forward weight shape) [and dbias] from input x and output gradient gy."""
+    _require_cuda(x, gy)
+    x = x.contiguous()
+    gy = gy.contiguous()
+    n, cin, d, h, wd = dims_of(x)
+    n2, cout, do, ho, wo = dims_of(gy)
+    kd = 3 if len(wshape) == 5 else 1
+    pad_d = pad if kd == 3 else 0
+    if (n2, do, ho, wo) != (n, d + 2 * pad_d - (kd - 1), h + 2 * pad - 2, wd + 2 * pad - 2) or cout != wshape[0] or cin != wshape[1]:
+        raise ValueError("wgrad: inconsistent shapes x=%s gy=%s w=%s pad=%d" % (tuple(x.shape), tuple(gy.shape), tuple(wshape), pad))
+    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    nbytes = lib.load().hpvg_conv_wgrad_workspace(n, cin, cout, d, h, wd, kd, pad, fmt_of(x), fmt_of(gy))
+    ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=x.device)
+    lib.call("hpvg_conv_wgrad", _ptr(x), fmt_of(x), _ptr(gy), fmt_of(gy), _ptr(dw), _ptr(db), n, cin, cout, d, h, wd, kd, pad,
+             _ptr(ws), int(nbytes), _stream())
+    return dw, db
+
+
+def channel_sum(t):
+    n, c, d, h, w = dims_of(t)
+    out = torch.empty((c,), dtype=torch.float32, device=t.device)
+    lib.call("hpvg_channel_sum", _ptr(t), fmt_of(t), _ptr(out), n, c, d * h * w, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution family (double differentiable)
+# ---------------------------------------------------------------------------------------------------------------
+class ConvFwd(Function):
+    """y = [lrelu](conv(x, w) + b); optional BatchNorm sums of y accumulate into `stats` (a side output)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, pad, out_wide, act_slope, stats):
+        y = conv_raw(x, w, bias, pad, False, out_wide, act_slope=act_slope, stats=stats)
+        ctx.pad, ctx.act_slope, ctx.has_bias = pad, act_slope, bias is not None
+        ctx.save_for_backward(x, w, y if act_slope is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope) if ctx.act_slope is not None else gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
+        if not _input_only():
+            if ctx.needs_input_grad[1]:
+                gw = ConvWgrad.apply(x, gz, ctx.pad, tuple(w.shape))
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ChannelSum.apply(gz)
+        return gx, gw, gb, None, None, None, None
+
+
+class ConvDgrad(Function):
+    """gx = data gradient of conv(x, w) w.r.t. x given gz (a forward-type conv with flipped/transposed weights)."""
+
+    @staticmethod
+    def forward(ctx, gz, w, pad, out_wide):
+        gx = conv_raw(gz, w, None, 2 - pad, True, out_wide)
+        ctx.pad = pad
+        ctx.save_for_backward(gz, w)
+        return gx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gz, w = ctx.saved_tensors
+        ggx = ggx.contiguous()
+        g_gz = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_gz = ConvFwd.apply(ggx, w, None, ctx.pad, is_wide(gz), None, None)
+        if ctx.needs_input_grad[1] and not _input_only():
+            g_w = ConvWgrad.apply(ggx, gz, ctx.pad, tuple(w.shape))
+        return g_gz, g_w, None, None
+
+
+class ConvWgrad(Function):
+    """gw[co][ci][k] = sum gz[.., co] * x[.. + k - pad, ci]"""
+
+    @staticmethod
+    def forward(ctx, x, gz, pad, wshape):
+        gw, _ = wgrad_raw(x, gz, pad, wshape)
+        ctx.pad = pad
+        ctx.save_for_backward(x, gz)
+        return gw
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gz = ctx.saved_tensors
+        ggw = ggw.contiguous()
+        g_x = g_gz = None
+        if ctx.needs_input_grad[0]:
+            g_x = ConvDgrad.apply(gz, ggw, ctx.pad, is_wide(x))
+        if ctx.needs_input_grad[1]:
+            g_gz = ConvFwd.apply(x, ggw, None, ctx.pad, is_wide(gz), None, None)
+        return g_x, g_gz, None, None
+
+
+class LReluBwd(Function):
+    """gz = gy * lrelu'(y) with the derivative read from the saved activation output (sign(y) == sign(pre-activation))."""
+
+    @staticmethod
+    def forward(ctx, gy, y, slope):
+        _require_cuda(gy, y)
+        if not (is_wide(gy) and is_wide(y)):
+            raise TypeError("LReluBwd works on wide (bf16 NDHWC) tensors")
+        gz = torch.empty_like(gy)
+        lib.call("hpvg_lrelu_bwd", _ptr(gy), _ptr(y), _ptr(gz), gy.numel(), float(slope), _stream())
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return gz
+
+    @staticmethod
+    def backward(ctx, ggz):
+        (y,) = ctx.saved_tensors
+        return LReluBwd.apply(ggz.contiguous(), y, ctx.slope), None, None
+
+
+class ChannelSum(Function):
+    """bias gradient: per-channel sum of a wide or thin tensor"""
+
+    @staticmethod
+    def forward(ctx, t):
+        ctx.shape, ctx.wide = tuple(t.shape), is_wide(t)
+        return channel_sum(t.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.wide:
+            return g.to(torch.bfloat16).view(1, 1, 1, 1, -1).expand(ctx.shape).contiguous()
+        return g.view(1, -1, 1, 1, 1).expand(ctx.shape).contiguous()
+
+
+def conv(x, w, bias, pad, out_wide, act_slope=None, stats=None):
+    return ConvFwd.apply(x, w, bias, pad, out_wide, act_slope, stats)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BatchNorm(train) + LeakyReLU on the conv output whose per-channel sums the conv epilogue already produced
+# ---------------------------------------------------------------------------------------------------------------
+class BnLrelu(Function):
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, slope):
+        _require_cuda(y, stats, gamma, beta)
+        n, c, d, h, w = dims_of(y)
+        nvox = n * d * h * w
+        dev = y.device
+        scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=dev)
+        mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=dev)
+        lib.call("hpvg_bn_finalize", _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+                 float(momentum), float(eps), nvox, _ptr(scale_shift), _ptr(mean_invstd), c, _stream())
+        out = torch.empty_like(y)
+        lib.call("hpvg_bn_apply_lrelu", _ptr(y), _ptr(scale_shift), _ptr(out), nvox, c, float(slope), _stream())
+        ctx.slope, ctx.c, ctx.nvox = slope, c, nvox
+        ctx.save_for_backward(y, scale_shift, mean_invstd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        y, scale_shift, mean_invstd = ctx.saved_tensors
+        gout = gout.contiguous()
+        c, nvox = ctx.c, ctx.nvox
+        sums = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+        lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
+                 float(ctx.slope), _stream())
+        gy = torch.empty_like(y)
+        dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
+        dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
+        lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), _stream())
+        return gy, None, dgamma, dbeta, None, None, None, None, None, None
+
+
+def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum=0.1, eps=1e-5, slope=0.2):
+    """ConvBlock3D/2D forward (reference modules/networks_3d.py:48-56): conv (+bias) with fused batch sums, then
+    normalise + affine + LeakyReLU in one pass."""
+    cout = w.shape[0]
+    stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
+    y = ConvFwd.apply(x, w, bias, pad, True, None, stats)
+    return BnLrelu.apply(y, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, slope)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# thin-tensor ops: resize(+noise), tanh(+residual), KL, GP penalty, format conversion
+# ---------------------------------------------------------------------------------------------------------------
+class UpsampleLinear(Function):
+    """F.interpolate(mode='trilinear'|'bilinear', align_corners=True) [+ amp*noise] (reference utils/images.py:9-26)."""
+
+    @staticmethod
+    def forward(ctx, x, size, noise, amp):
+        _require_cuda(x, noise)
+        x = x.contiguous()
+        n, c, d, h, w = dims_of(x)
+        do, ho, wo = size
+        out = torch.empty((n, c, do, ho, wo), dtype=torch.float32, device=x.device)
+        if noise is not None:
+            noise = noise.contiguous()
+            if tuple(noise.shape) != tuple(out.shape):
+                raise ValueError("noise shape %s != output shape %s" % (tuple(noise.shape), tuple(out.shape)))
+        lib.call("hpvg_upsample_linear_fwd", _ptr(x), _ptr(out), _ptr(noise), float(amp), n * c, d, h, w, do, ho, wo, _stream())
+        ctx.in_shape = (n, c, d, h, w)
+        ctx.size = (do, ho, wo)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        n, c, d, h, w = ctx.in_shape
+        do, ho, wo = ctx.size
+        gout = gout.contiguous()
+        gx = torch.empty((n, c, d, h, w), dtype=torch.float32, device=gout.device)
+        lib.call("hpvg_upsample_linear_bwd", _ptr(gout), _ptr(gx), n * c, d, h, w, do, ho, wo, _stream())
+        return gx, None, None, None
+
+
+class TanhAdd(Function):
+    """tanh(a + b) (b optional) on thin tensors (reference modules/networks_3d.py:377,404)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        out = torch.empty_like(a)
+        lib.call("hpvg_tanh_add_fwd", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+        ctx.has_b = b is not None
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        (out,) = ctx.saved_tensors
+        g = torch.empty_like(out)
+        lib.call("hpvg_tanh_bwd", _ptr(gout.contiguous()), _ptr(out), _ptr(g), out.numel(), _stream())
+        return g, (g if ctx.has_b else None)
+
+
+class Reparam(Function):
+    """z = eps * exp(0.5*logvar) + mu on wide mu/logvar with thin eps (reference modules/networks_3d.py:29-35)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        _require_cuda(mu, logvar, eps)
+        n, c, d, h, w = dims_of(mu)
+        z = torch.empty_like(mu)
+        lib.call("hpvg_reparam_fwd", _ptr(mu), _ptr(logvar), _ptr(eps), _ptr(z), n, c, d * h * w, _stream())
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz):
+        logvar, eps = ctx.saved_tensors
+        n, c, d, h, w = dims_of(logvar)
+        gz = gz.contiguous()
+        gmu = torch.empty_like(logvar)
+        glv = torch.empty_like(logvar)
+        lib.call("hpvg_reparam_bwd", _ptr(gz), _ptr(logvar), _ptr(eps), _ptr(gmu), _ptr(glv), n, c, d * h * w, _stream())
+        return gmu, glv, None
+
+
+class KlCriterion(Function):
+    """mean(-0.5*(1 + logvar - mu^2 - exp(logvar))) (reference modules/losses.py:7-9)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        _require_cuda(mu, logvar)
+        mu, logvar = mu.contiguous(), logvar.contiguous()
+        out = torch.empty((1,), dtype=torch.float32, device=mu.device)
+        lib.call("hpvg_kl_fwd", _ptr(mu), _ptr(logvar), _ptr(out), mu.numel(), _stream())
+        ctx.save_for_backward(mu, logvar)
+        return out.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        mu, logvar = ctx.saved_tensors
+        gmu, glv = torch.empty_like(mu), torch.empty_like(logvar)
+        lib.call("hpvg_kl_bwd", _ptr(gout.contiguous().view(1)), _ptr(mu), _ptr(logvar), _ptr(gmu), _ptr(glv), mu.numel(), _stream())
+        return gmu, glv
+
+
+class GpPenalty(Function):
+    """lambda * mean((||g||_2 over channels - 1)^2) (reference modules/utils.py:18)."""
+
+    @staticmethod
+    def forward(ctx, g, lam):
+        _require_cuda(g)
+        g = g.contiguous()
+        n, c, d, h, w = dims_of(g)
+        out = torch.empty((1,), dtype=torch.float32, device=g.device)
+        lib.call("hpvg_gp_penalty_fwd", _ptr(g), _ptr(out), n, c, d * h * w, float(lam), _stream())
+        ctx.lam = lam
+        ctx.save_for_backward(g)
+        return out.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        n, c, d, h, w = dims_of(g)
+        gg = torch.empty_like(g)
+        lib.call("hpvg_gp_penalty_bwd", _ptr(gout.contiguous().view(1)), _ptr(g), _ptr(gg), n, c, d * h * w, float(ctx.lam), _stream())
+        return gg, None
+
+
+def convert_raw(t, to_wide):
+    n, c, d, h, w = dims_of(t)
+    out = _empty(n, c, d, h, w, to_wide, t.device)
+    lib.call("hpvg_convert_format", _ptr(t.contiguous()), fmt_of(t), _ptr(out), fmt_of(out), n, c, d * h * w, _stream())
+    return out
+
+
+class ToWide(Function):
+    @staticmethod
+    def forward(ctx, t):
+        _require_cuda(t)
+        return convert_raw(t, True)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToThin.apply(g.contiguous())
+
+
+class ToThin(Function):
+    @staticmethod
+    def forward(ctx, t):
+        _require_cuda(t)
+        return convert_raw(t, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToWide.apply(g.contiguous())
+
+
+def lerp(a, b, alpha):
+    """alpha*a + (1-alpha)*b on thin tensors, no autograd (the GP interpolates are a detached leaf)."""
+    _require_cuda(a, b)
+    a, b = a.detach().contiguous(), b.detach().contiguous()
+    out = torch.empty_like(a)
+    lib.call("hpvg_lerp", _ptr(a), _ptr(b), _ptr(out), float(alpha), a.numel(), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# spectral normalisation (legacy torch.nn.utils.spectral_norm semantics: 1 power iteration per training forward)
+# ---------------------------------------------------------------------------------------------------------------
+class SpectralWeight(Function):
+    """w_sn = w_orig / sigma(w_orig; u, v); u and v are updated in place when `update_uv` (training mode)."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, update_uv, eps):
+        _require_cuda(w_orig, u, v)
+        w_orig = w_orig.contiguous()
+        cout = w_orig.shape[0]
+        k = w_orig.numel() // cout
+        dev = w_orig.device
+        sigma = torch.empty((1,), dtype=torch.float32, device=dev)
+        w_sn = torch.empty_like(w_orig)
+        scratch = torch.empty((k + cout + 4,), dtype=torch.float32, device=dev)
+        lib.call("hpvg_sn_power_iter", _ptr(w_orig), _ptr(u), _ptr(v), _ptr(sigma), _ptr(w_sn), _ptr(scratch), cout, k,
+                 int(bool(update_uv)), float(eps), _stream())
+        # u, v are buffers mutated in place; the backward must see the values used for this sigma
+        ctx.save_for_backward(w_sn, u.clone(), v.clone(), sigma)
+        return w_sn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gw_sn):
+        w_sn, u, v, sigma = ctx.saved_tensors
+        cout = w_sn.shape[0]
+        k = w_sn.numel() // cout
+        gw = torch.empty_like(w_sn)
+        scratch = torch.empty((4,), dtype=torch.float32, device=w_sn.device)
+        lib.call("hpvg_sn_backward", _ptr(gw_sn.contiguous()), _ptr(w_sn), _ptr(u), _ptr(v), _ptr(sigma), _ptr(gw), _ptr(scratch),
+                 cout, k, _stream())
+        return gw, None, None, None, None

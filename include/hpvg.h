@@ -1,0 +1,165 @@
+/*
+ * hpvg.h — C-ABI of libhpvg.so: the B200 (sm_100a) kernels behind the HP-VAE-GAN per-scale training/generation
+ * hot path.  Every entry point takes raw device pointers, extents and a cudaStream_t (as void*); the library never
+ * allocates or frees device memory, never synchronises, and launches only on the stream it is given.
+ * Return value: 0 on success, negative on error (hpvg_last_error() returns a thread-local message).
+ *
+ * Tensor formats (the `*_fmt` arguments):
+ *   HPVG_FMT_NCDHW_F32  : float32, [N][C][D][H][W] contiguous (what the reference's nn.Module boundary sees:
+ *                         3-channel videos/images, 1-channel critic maps, the [N,128,T,H,W] latent).
+ *   HPVG_FMT_NDHWC_BF16 : bfloat16, [N][D][H][W][C] contiguous (every wide activation between layers).
+ * 2-D networks (modules/networks_2d.py) use D == 1 and KD == 1.
+ *
+ * Each function names the reference call it replaces (paths relative to the reference repository root).
+ */
+#ifndef HPVG_H_
+#define HPVG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPVG_FMT_NCDHW_F32 0
+#define HPVG_FMT_NDHWC_BF16 1
+
+#define HPVG_ACT_NONE 0
+#define HPVG_ACT_LRELU 1
+
+/* conv backend selection: 0 = auto (tcgen05 where the shape allows, CUDA-core kernel otherwise),
+ * 1 = force the CUDA-core kernels (debug/parity aid), 2 = require tcgen05 (error if the shape does not fit). */
+#define HPVG_BACKEND_AUTO 0
+#define HPVG_BACKEND_DIRECT 1
+#define HPVG_BACKEND_TCGEN05 2
+
+const char* hpvg_last_error(void);
+int hpvg_version(void);
+int hpvg_set_conv_backend(int backend);
+int hpvg_get_conv_backend(void);
+/* number of kernels this library has launched since load (all threads) — bench.py's `gpu_launches` */
+long long hpvg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Convolution, 3x3x3 (KD == 3) or 3x3 (KD == 1), stride 1, zero padding `pad` in {0,1,2} on every filtered axis.
+ * Replaces nn.Conv3d / nn.Conv2d forward inside ConvBlock3D / ConvBlock3DSN / the tail convs
+ * (modules/networks_3d.py:51,63,175,290,341,362 ; modules/networks_2d.py:56,68,179,204,225), and — with
+ * transposed = 1 — the data-gradient of the same convolution (aten::convolution_backward, grad_input).
+ *
+ *   transposed == 0 :  y[n,co,o] = act( bias[co] + sum_{ci,k} x[n,ci,o+k-pad] * w[co][ci][k] ),   w is [Cout][Cin][taps]
+ *   transposed == 1 :  y[n,co,o] = act( bias[co] + sum_{ci,k} x[n,ci,o+k-pad] * w[ci][co][taps-1-k] ), w is [Cin][Cout][taps]
+ *                      (the data gradient of a forward conv with padding p is this call with pad = 2 - p)
+ * Output extent per filtered axis = input extent + 2*pad - 2.  D is not filtered when KD == 1.
+ * `w_f32` is the float32 master weight in PyTorch layout; `w_packed` (may be NULL) is the bf16 image produced by
+ * hpvg_pack_weights for the same `transposed` flag, required for the tcgen05 path (Cin, Cout multiples of 64 and
+ * both tensors NDHWC_BF16).  `bias` may be NULL.  `stats` (may be NULL) is a float32 [2*Cout] accumulator that
+ * receives += per-channel sum and sum of squares of the *stored* output (BatchNorm batch statistics,
+ * aten::native_batch_norm's reduction, fused into the conv epilogue); the caller zeroes it.
+ * `mask_src` (may be NULL; NDHWC_BF16, same extents as y) multiplies the result by the LeakyReLU derivative of that
+ * tensor (1 where > 0, else lrelu_slope): the fused "dgrad then leaky_relu_backward" step of the critic backward.
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* w_packed, const float* bias,
+                      void* y, int y_fmt, int N, int Cin, int Cout, int D, int H, int W, int KD, int pad,
+                      int transposed, int act, float lrelu_slope, float* stats, const void* mask_src, void* stream);
+
+/* Weight gradient of the convolution above (aten::convolution_backward grad_weight, and the
+ * "wgrad-as-conv" node of the WGAN-GP double backward, modules/utils.py:14-18):
+ *   dw[co][ci][k] = sum_{n,o} gy[n,co,o] * x[n,ci,o+k-pad]        (float32, PyTorch layout, overwritten)
+ *   dbias[co]     = sum_{n,o} gy[n,co,o]                           (optional)
+ * x has extents (D,H,W); gy has extents + 2*pad - 2.  `workspace` must hold hpvg_conv_wgrad_workspace() bytes. */
+size_t hpvg_conv_wgrad_workspace(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int gy_fmt);
+int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float* dw, float* dbias,
+                    int N, int Cin, int Cout, int D, int H, int W, int KD, int pad,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* float32 [Cout][Cin][taps] (transposed == 0) or [Cin][Cout][taps] (transposed == 1) -> bf16 [taps][Cout][Cin]
+ * K-major tiles for the tcgen05 kernels; `scale_ptr` (may be NULL) points to a device float whose reciprocal
+ * multiplies every weight (spectral normalisation: W / sigma). */
+int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed,
+                      const float* inv_scale_of, void* stream);
+
+/* per-channel sum of a tensor: out[c] = sum_{n,o} t[n,c,o]   (bias gradient) */
+int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long spatial, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * BatchNorm (training mode) + LeakyReLU, replaces nn.BatchNorm3d/2d + nn.LeakyReLU(0.2) of ConvBlock3D/2D
+ * (modules/networks_3d.py:54-56, modules/networks_2d.py:59-61).
+ * bn_finalize: from the conv-epilogue sums -> scale_shift[0..C) = gamma*invstd, [C..2C) = beta - mean*scale ;
+ *   mean_invstd[0..C) = mean, [C..2C) = invstd ; running_mean/var updated with `momentum` (unbiased variance),
+ *   num_batches_tracked += 1 (int64, may be NULL).
+ * bn_apply_lrelu: out = lrelu(y*scale + shift).
+ * bn_lrelu_bwd_reduce: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat with dz = gout * lrelu'(y*scale+shift).
+ * bn_lrelu_bwd_apply: gy = scale * (dz - sums0/M - xhat*sums1/M) ; dgamma = sums1, dbeta = sums0 (written once).
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                     long long count, float* scale_shift, float* mean_invstd, int C, void* stream);
+int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long long nvox, int C, float slope,
+                        void* stream);
+int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
+                             float* sums, long long nvox, int C, float slope, void* stream);
+int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
+                            const float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
+                            float slope, void* stream);
+
+/* gz = gout * (out > 0 ? 1 : slope)   — aten::leaky_relu_backward on the saved in-place output (bf16 tensors) */
+int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Trilinear / bilinear resize with align_corners=True on NCDHW float32 tensors, replaces utils.upscale /
+ * utils.interpolate_3D / utils.upscale_2d (utils/images.py:9-26,83-105):
+ *   out = resize(x) [+ noise_amp * noise]          noise may be NULL (networks_3d.py:395-402)
+ * and its adjoint (aten::upsample_trilinear3d_backward) as a gather over the input grid.
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_upsample_linear_fwd(const float* x, float* out, const float* noise, float noise_amp, int NC,
+                             int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
+int hpvg_upsample_linear_bwd(const float* gout, float* gx, int NC, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                             void* stream);
+
+/* out = tanh(a + b)  (b may be NULL) — torch.tanh(block(x) + x_up), torch.tanh(decoder(z))
+ * (networks_3d.py:377,404).  bwd: g = gout * (1 - out^2). */
+int hpvg_tanh_add_fwd(const float* a, const float* b, float* out, long long numel, void* stream);
+int hpvg_tanh_bwd(const float* gout, const float* out, float* g, long long numel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * VAE head: reparameterize (networks_3d.py:29-35) on NDHWC_BF16 mu/logvar with NCDHW float32 eps:
+ *   z = eps * exp(0.5*logvar) + mu  (NDHWC_BF16) ;  bwd: gmu = gz, glogvar = gz * eps * 0.5 * exp(0.5*logvar)
+ * kl_criterion (modules/losses.py:7-9) on NCDHW float32: out[0] = mean(-0.5*(1 + logvar - mu^2 - exp(logvar)))
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_reparam_fwd(const void* mu, const void* logvar, const float* eps, void* z, int N, int C, long long spatial,
+                     void* stream);
+int hpvg_reparam_bwd(const void* gz, const void* logvar, const float* eps, void* gmu, void* glogvar, int N, int C,
+                     long long spatial, void* stream);
+int hpvg_kl_fwd(const float* mu, const float* logvar, float* out, long long numel, void* stream);
+int hpvg_kl_bwd(const float* gout, const float* mu, const float* logvar, float* gmu, float* glogvar, long long numel,
+                void* stream);
+
+/* WGAN-GP penalty (modules/utils.py:18): out[0] = lambda * mean_{n,voxel} (||g[n,:,voxel]||_2 - 1)^2 over the
+ * channel axis of an NCDHW float32 gradient; bwd: gg = gout * lambda * 2(||g||-1)/(N*S) * g/||g||. */
+int hpvg_gp_penalty_fwd(const float* g, float* out, int N, int C, long long spatial, float lambda, void* stream);
+int hpvg_gp_penalty_bwd(const float* gout, const float* g, float* gg, int N, int C, long long spatial, float lambda,
+                        void* stream);
+
+/* layout/dtype conversion between the two formats (differentiable by its own inverse) */
+int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, int N, int C, long long spatial,
+                        void* stream);
+
+/* out = alpha*a + (1-alpha)*b on float32 (the GP interpolates, modules/utils.py:9) */
+int hpvg_lerp(const float* a, const float* b, float* out, float alpha, long long numel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Spectral normalisation, one power iteration (nn.utils.spectral_norm as used by ConvBlock3DSN/2DSN,
+ * networks_3d.py:63): w_mat = w_orig viewed [Cout][K].  In place: v <- normalize(W^T u), u <- normalize(W v);
+ * sigma[0] = u^T W v.  `scratch` holds K + Cout + 4 floats.  Then w_sn = w_orig / sigma.
+ * sn_backward: gw_orig = (gw_sn - (sum(gw_sn * w_sn)) * u v^T) / sigma    (u, v constants, as in torch)
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, float* w_sn, float* scratch, int Cout,
+                       int K, int update_uv, float eps, void* stream);
+int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, const float* v, const float* sigma,
+                     float* gw_orig, float* scratch, int Cout, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPVG_H_ */
