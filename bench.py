@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — finest-scale HP-VAE-GAN training throughput (and generation frames/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl hpvg|reference] [--draws D]
+
+Workload (BASELINE.json configs[1]): train_video.py's 3-D HP-VAE-GAN on one synthetic 16-frame 64x64 clip, nfc 64,
+latent 128, vae-levels 3, sampling rates 5 3 1 -> 5 pyramid levels, finest level = 16 x 64 x 64 (a GAN level).
+A step = ONE iteration of the reference's loop at that level (train_video.py:126-202): generator 'rec' and 'rand'
+passes over the whole pyramid, four critic passes, the WGAN-GP double backward, both backward sweeps, gradient
+clipping and both Adam steps.  1 720.43 GFLOP of convolution work per step.
+
+  value : iterations/s with the clip resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : the same loop fed from pinned HOST buffers every step (H2D of the clip inside the timed region) with a
+          device->host read of the step's reconstruction loss.
+  N > 1 : batched-noise data-parallel training — one clip + its noise per GPU, replicated weights, one flat NCCL
+          all-reduce of the gradients per backward (weak scaling: value = N clip-iterations per iteration time).
+  --impl reference : the CPU arm — the oracle's restatement of the same iteration (oracle/train_ref.py, pinned to the
+          reference by tests/golden/train_*.pt) in PyTorch-CPU fp32 on all host cores.  The reference itself is a
+          Python package under /root/reference, which does not exist on the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "hp-vae-gan_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CONV_GFLOP_PER_ITER = 1720.43      # SURVEY.md App. B, config 2 finest level
+METRIC = "train_iters_per_s_finest_scale"
+UNIT = "iter/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------
+def make_opt():
+    from oracle import port            # Opt is only the argparse-namespace stand-in (no oracle compute on this path)
+    o = port.Opt(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
+    o.scale_idx = o.stop_scale
+    o.Noise_Amps = [1.0] + [0.07] * (o.stop_scale - 1)      # survey-observed amplitudes; the finest one is computed at iteration 0
+    s0, t0 = port.scale_size(0, o), port.time_depth(0, o)
+    o.Z_init_size = [1, o.latent_dim, t0, s0, s0]
+    o.batch_size = 1
+    return o
+
+
+def level_shape(o, idx):
+    from oracle import port
+    s = port.scale_size(idx, o)
+    return (1, 3, port.time_depth(idx, o), s, s)
+
+
+def workload_name(o):
+    return ("configs[1]: train_video.py 3D HP-VAE-GAN, synthetic 16-frame 64x64 clip, vae-levels 3, nfc 64, rates 5 3 1, "
+            "finest level %d of %d (GAN), batch 1 per GPU" % (o.scale_idx, o.stop_scale))
+
+
+def synthetic_clip(o, seed):
+    g = torch.Generator().manual_seed(seed)
+    real = torch.rand(level_shape(o, o.scale_idx), generator=g) * 2 - 1
+    real_zero = torch.rand(level_shape(o, 0), generator=g) * 2 - 1
+    return real, real_zero
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port on the host cores)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_iteration_timer(o, state_g, state_d, budget_s, steps, warmup):
+    """time `steps` iterations (after `warmup`) of the oracle's restatement of the same iteration; stops early when the
+    budget is exhausted.  Returns (seconds per iteration, iterations timed, cores)."""
+    from oracle import train_ref
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    sd_g = {k: v.detach().clone().float().cpu() for k, v in state_g.items()}
+    sd_d = {k: v.detach().clone().float().cpu() for k, v in state_d.items()}
+    oc = make_opt()
+    tr = train_ref.ScaleTrainer(oc, sd_g, sd_d)
+    real, real_zero = synthetic_clip(oc, 0)
+    torch.manual_seed(0)
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        tr.iteration(real, real_zero)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.iteration(real, real_zero)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return sum(times) / len(times), len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    o = make_opt()
+    sg, sd = fresh_states(o)
+    warm = max(1, min(args.warmup, 1))
+    sec, done, cores = cpu_iteration_timer(o, sg, sd, budget_s=240.0, steps=args.steps, warmup=warm)
+    val = 1.0 / sec
+    sample = "%d full iteration(s) of the same workload after %d warm-up (oracle/train_ref.py, PyTorch-CPU fp32, %d threads)" % (done, warm, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(o)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def fresh_states(o):
+    """default-initialised generator / critic state_dicts for the workload (seed 0), built on the CPU with torch modules
+    of the drop-in package (construction only: no kernel runs here)"""
+    from modules import networks_3d
+    torch.manual_seed(0)
+    g = networks_3d.GeneratorHPVAEGAN(o)
+    for _ in range(o.scale_idx):
+        g.init_next_stage()
+    d = networks_3d.WDiscriminator3D(o)
+    return g.state_dict(), d.state_dict()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_hpvg(args):
+    import torch.distributed as dist
+    from hpvg import lib, train
+    from modules import networks_3d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl hpvg needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    o = make_opt()
+    sg, sd = fresh_states(o)                       # identical on every rank (seed 0): replicated weights
+    G = networks_3d.GeneratorHPVAEGAN(o)
+    for _ in range(o.scale_idx):
+        G.init_next_stage()
+    G.load_state_dict(sg)
+    D = networks_3d.WDiscriminator3D(o)
+    D.load_state_dict(sd)
+    G.to(dev)
+    D.to(dev)
+    trainer = train.ScaleTrainer(o, G, D, distributed=distributed)
+    real_h, real_zero_h = synthetic_clip(o, rank)  # one clip per rank
+    real_h, real_zero_h = real_h.pin_memory(), real_zero_h.pin_memory()
+    real, real_zero = real_h.to(dev), real_zero_h.to(dev)
+    torch.manual_seed(1 + rank)                    # per-rank noise; the GP alpha comes from the CPU generator below
+    cpu_gen_state = torch.random.get_rng_state()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident():
+        trainer.iteration(real, real_zero)
+
+    last = {}
+
+    def step_e2e():
+        r = real_h.to(dev, non_blocking=True)
+        rz = real_zero_h.to(dev, non_blocking=True)
+        out = trainer.iteration(r, rz)
+        last["rec_loss"] = out["rec_loss"].item()          # device -> host read of the step's result
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        step_resident()
+    torch.cuda.reset_peak_memory_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    peak_mb = torch.cuda.max_memory_allocated() / 2**20
+
+    # roofline leg: the same steps again with CUDA events around every convolution launch (on the launching stream)
+    prof_steps = min(args.steps, 3)
+    lib.profile_enable(True)
+    ms_prof = timed(step_resident, prof_steps)
+    lib.profile_enable(False)
+    rows = lib.profile_dump()
+
+    # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
+    draws_rank = max(1, args.draws // world)
+    train.generate(G, o, 2, dev)
+    frames = [0]
+
+    def gen_all():
+        frames[0], _ = train.generate(G, o, draws_rank, dev)
+    ms_gen = timed(gen_all, 1)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if not peak_tf:
+            peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        by_kind = {}
+        for r in rows:
+            k = by_kind.setdefault(r["kind"], {"launches": 0, "ms": 0.0, "flops": 0.0})
+            k["launches"] += r["launches"]; k["ms"] += r["ms"]; k["flops"] += r["work"] * r["launches"]
+        # dominant kernel = the tcgen05 implicit-GEMM convolution (fprop / dgrad form) at the finest level's 64->64 shape
+        top = max((r for r in rows if r["kind"] == "conv_tc"), key=lambda r: r["ms"], default=None)
+        roofline = None
+        if top is not None:
+            per_launch_ms = top["ms"] / top["launches"]
+            achieved = top["work"] / (per_launch_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, 64->64 @ 16x64x64)",
+                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                        "flops_per_launch": top["work"], "us_per_launch": per_launch_ms * 1e3, "launches_timed": top["launches"],
+                        "peak_source": peak_src,
+                        "share_of_step": top["ms"] / prof_steps / (ms_prof / prof_steps),
+                        "by_kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in by_kind.items()},
+                        "by_kernel_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None) for k, v in by_kind.items()},
+                        "ms_per_step_with_events": ms_prof / prof_steps}
+        value = world * args.steps / (ms * 1e-3)
+        e2e = world * args.steps / (ms_e2e * 1e-3)
+        bi = (real_h.numel() + real_zero_h.numel()) * 4
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat NCCL grad all-reduce)" % world if distributed else "single GPU",
+                           "l2": "no explicit flush: one iteration touches %.0f MB of activations (peak allocated), above the 126 MB L2" % peak_mb,
+                           "conv_gflop_per_iter": CONV_GFLOP_PER_ITER},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "model_tflops": value * CONV_GFLOP_PER_ITER / 1e3 / world,
+                "generation": {"metric": "generated_frames_per_s", "value": world * frames[0] / (ms_gen * 1e-3), "unit": "frames/s",
+                               "draws": draws_rank * world, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
+                               "ms_per_draw": ms_gen / draws_rank}}
+        if distributed:
+            line["allreduce_bytes_per_step"] = trainer.allreduce_bytes // max(1, trainer.iterations)
+        if world == 1 and not args.no_cpu_baseline:
+            torch.random.set_rng_state(cpu_gen_state)
+            sec, done, cores = cpu_iteration_timer(o, sg, sd, budget_s=30.0, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d full iteration(s) of the same workload after 1 warm-up (oracle/train_ref.py, PyTorch-CPU fp32)" % done}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
+    ap.add_argument("--draws", type=int, default=64, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_hpvg(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace hpvg {
 
@@ -18,6 +22,37 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv_backend() { return g_backend.load(std::memory_order_relaxed); }
+
+// ---- optional per-launch device timing (bench.py's roofline leg): CUDA events around selected kernels, on the stream
+// they are launched on.  Off by default; never used under stream capture.
+struct ProfRecord {
+  int kind;
+  double work;
+  cudaEvent_t start, stop;
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof;
+
+bool profiling() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+void* prof_begin(int kind, double work, cudaStream_t st) {
+  if (!profiling()) return nullptr;
+  ProfRecord r;
+  r.kind = kind;
+  r.work = work;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return nullptr;
+  cudaEventRecord(r.start, st);
+  ProfRecord* out = new ProfRecord(r);
+  return out;
+}
+void prof_end(void* h, cudaStream_t st) {
+  if (!h) return;
+  ProfRecord* r = reinterpret_cast<ProfRecord*>(h);
+  cudaEventRecord(r->stop, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
 
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
@@ -81,5 +116,37 @@ int hpvg_set_conv_backend(int backend) {
 }
 int hpvg_get_conv_backend(void) { return hpvg::g_backend.load(); }
 long long hpvg_launch_count(void) { return hpvg::g_launches.load(); }
+
+int hpvg_profile_enable(int on) {
+  hpvg::g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int hpvg_profile_dump(double* rows, int max_rows) {
+  using namespace hpvg;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::pair<int, double>, std::pair<long long, double>> agg;
+  for (ProfRecord& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+      auto& a = agg[std::make_pair(r.kind, r.work)];
+      a.first += 1;
+      a.second += ms;
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  g_prof.clear();
+  int n = 0;
+  for (auto& kv : agg) {
+    if (n >= max_rows) break;
+    rows[4 * n + 0] = kv.first.first;
+    rows[4 * n + 1] = kv.first.second;
+    rows[4 * n + 2] = (double)kv.second.first;
+    rows[4 * n + 3] = kv.second.second;
+    ++n;
+  }
+  return n;
+}
 
 }  // extern "C"

@@ -19,6 +19,9 @@ namespace hpvg {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int conv_backend();
+// per-launch device timing for bench.py (hpvg_profile_enable): returns an opaque handle or nullptr when off
+void* prof_begin(int kind, double work, cudaStream_t st);
+void prof_end(void* handle, cudaStream_t st);
 
 #define HPVG_CHECK_ARG(cond, ...)                 \
   do {                                            \

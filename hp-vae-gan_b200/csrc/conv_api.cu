@@ -60,10 +60,19 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
               x_fmt, y_fmt, w_packed);
     return -1;
   }
-  if (tc_ok && backend != HPVG_BACKEND_DIRECT) return conv_tc(x, w_packed, bias, y, g, act, lrelu_slope, stats, mask_src, st);
+  const double flops = 2.0 * g.N * g.Do * g.Ho * g.Wo * (double)g.Cin * g.Cout * g.taps;
+  if (tc_ok && backend != HPVG_BACKEND_DIRECT) {
+    void* ph = prof_begin(HPVG_PROF_CONV_TC, flops, st);
+    int rc = conv_tc(x, w_packed, bias, y, g, act, lrelu_slope, stats, mask_src, st);
+    prof_end(ph, st);
+    return rc;
+  }
   HPVG_CHECK_ARG(w_f32 != nullptr, "conv_forward: the CUDA-core kernel needs the float32 weights");
   HPVG_CHECK_ARG(mask_src == nullptr || y_fmt == HPVG_FMT_NDHWC_BF16, "conv_forward: mask_src requires an NDHWC_BF16 output");
-  return conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
+  void* ph = prof_begin(HPVG_PROF_CONV_DIRECT, flops, st);
+  int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
+  prof_end(ph, st);
+  return rc;
 }
 
 size_t hpvg_conv_wgrad_workspace(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int gy_fmt) {
@@ -86,10 +95,16 @@ int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float*
     return -1;
   }
   int rc;
-  if (tc_ok && backend != HPVG_BACKEND_DIRECT)
+  const double flops = 2.0 * g.N * g.Do * g.Ho * g.Wo * (double)g.Cin * g.Cout * g.taps;
+  if (tc_ok && backend != HPVG_BACKEND_DIRECT) {
+    void* ph = prof_begin(HPVG_PROF_WGRAD_TC, flops, st);
     rc = wgrad_tc(x, gy, dw, g, workspace, workspace_bytes, st);
-  else
+    prof_end(ph, st);
+  } else {
+    void* ph = prof_begin(HPVG_PROF_WGRAD_DIRECT, flops, st);
     rc = wgrad_direct(x, x_fmt, gy, gy_fmt, dw, g, st);
+    prof_end(ph, st);
+  }
   if (rc) return rc;
   if (dbias) return hpvg_channel_sum(gy, gy_fmt, dbias, N, Cout, (long long)g.Do * g.Ho * g.Wo, stream);
   return 0;

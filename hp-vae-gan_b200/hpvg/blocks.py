@@ -233,10 +233,10 @@ def make_family(dims):
                 mu_w, logvar_w = self.encode.run(as5d(video).contiguous())
                 mu5, logvar5 = ops.ToThin.apply(mu_w), ops.ToThin.apply(logvar_w)
                 if self.training:
-                    eps = torch.zeros_like(mu5).normal_()          # same draw as reparameterize (reference :31-32)
+                    eps = images.generate_noise(ref=mu5)           # same draw as reparameterize (reference :31-32)
                     z = ops.Reparam.apply(mu_w, logvar_w, eps)
                 else:
-                    z = ops.ToWide.apply(torch.zeros_like(mu5).normal_())
+                    z = ops.ToWide.apply(images.generate_noise(ref=mu5))
                 mu, logvar = like_input(mu5, dims), like_input(logvar5, dims)
             else:
                 _check_device(noise_init)

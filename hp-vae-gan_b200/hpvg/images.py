@@ -63,12 +63,16 @@ def interpolate_3D(video, size):
     return resize(video, size)
 
 
+def draw_normal(shape, dtype, device):
+    """the single place where the networks draw N(0,1) numbers: zeros(shape).normal_(0, 1) on `device`, i.e. the same
+    generator consumption as the reference's zeros_like(ref).normal_() calls (tests replace this hook to inject noise)"""
+    return torch.zeros(tuple(shape), dtype=dtype, device=device).normal_(0, 1)
+
+
 def generate_noise(ref=None, size=None, device=None):
-    """N(0,1) noise with the reference's RNG consumption: zeros_like(ref).normal_() or zeros(size).to(device).normal_()"""
+    """N(0,1) noise shaped like `ref` (or `size`), reference utils/images.py:39-49"""
     if ref is not None:
-        noise = torch.zeros_like(ref)
-    elif size is not None:
-        noise = torch.zeros(*size).to(device)
-    else:
-        raise Exception("ref or size must be applied")
-    return noise.normal_(0, 1)
+        return draw_normal(ref.shape, ref.dtype, ref.device)
+    if size is not None:
+        return draw_normal(size, torch.float32, device)
+    raise Exception("ref or size must be applied")

@@ -19,6 +19,8 @@ PROTOTYPES = {
     "hpvg_set_conv_backend": (c_int, [c_int]),
     "hpvg_get_conv_backend": (c_int, []),
     "hpvg_launch_count": (c_longlong, []),
+    "hpvg_profile_enable": (c_int, [c_int]),
+    "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "hpvg_conv_wgrad_workspace": (c_size_t, [c_int] * 10),
@@ -93,3 +95,18 @@ def set_conv_backend(backend):
 
 def get_conv_backend():
     return int(load().hpvg_get_conv_backend())
+
+
+PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct"}
+
+
+def profile_enable(on):
+    call("hpvg_profile_enable", int(bool(on)))
+
+
+def profile_dump(max_rows=256):
+    """-> list of {kind, work (FLOPs per launch), launches, ms} aggregated over the launches recorded since the last dump"""
+    buf = (ctypes.c_double * (4 * max_rows))()
+    n = load().hpvg_profile_dump(ctypes.cast(buf, c_void_p), max_rows)
+    return [{"kind": PROF_KINDS.get(int(buf[4 * i]), str(int(buf[4 * i]))), "work": buf[4 * i + 1], "launches": int(buf[4 * i + 2]),
+             "ms": buf[4 * i + 3]} for i in range(n)]

@@ -1,0 +1,178 @@
+"""One pyramid scale of the reference's training loop, as a callable object over the drop-in modules.
+
+The reference's train scripts run unchanged on top of the drop-in `modules` package; this file restates the body of
+their per-scale loop (train_video.py:44-88 optimizer set-up, :111-202 one iteration; train_image.py is the same
+loop on 4-D tensors) so that bench.py, the parity tests and the multi-GPU mode can step it without the CLI, dataset
+and logging layers.  Hyper-parameters are read from the same `opt` fields the scripts use.
+
+Multi-GPU ("batched-noise data-parallel training", BASELINE.json config 5): one process per GPU, one clip + its
+noise per rank, replicated weights.  After each backward the parameter gradients that exist on this rank are
+averaged over ranks with ONE flat-bucket NCCL all-reduce: the critic's after errD_total.backward(),
+the generator's after total_loss.backward() and before clip_grad_norm_, so every rank clips with the same norm and
+takes the same Adam step.  BatchNorm statistics stay per rank, as under the reference's nn.DataParallel.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import images
+
+
+def _train_defaults(opt):
+    for k, v in dict(lr_g=5e-4, lr_d=5e-4, beta1=0.5, lambda_grad=0.1, rec_weight=10.0, kl_weight=1.0, disc_loss_weight=1.0,
+                     lr_scale=0.2, train_depth=1, grad_clip=5.0, noise_amp_init=0.1, batch_size=1, train_all=False,
+                     const_amp=False).items():
+        if not hasattr(opt, k):
+            setattr(opt, k, v)
+
+
+def generator_param_groups(opt, netG):
+    """train_video.py:57-86 — which generator blocks the optimizer owns at scale opt.scale_idx and their learning rates"""
+    groups = []
+    body = netG.body
+
+    def vae_groups():
+        lr = opt.lr_g * (opt.lr_scale ** opt.scale_idx)
+        return [{"params": netG.encode.parameters(), "lr": lr}, {"params": netG.decoder.parameters(), "lr": lr}]
+
+    def body_groups(blocks):
+        blocks = list(blocks)
+        return [{"params": b.parameters(), "lr": opt.lr_g * (opt.lr_scale ** (len(blocks) - 1 - i))} for i, b in enumerate(blocks)]
+
+    if not opt.train_all:
+        if opt.vae_levels < opt.scale_idx + 1:
+            depth = min(opt.train_depth, len(body) - opt.vae_levels + 1)
+            groups += body_groups(body[-depth:])
+        else:
+            groups += vae_groups()
+            groups += body_groups(body[-opt.train_depth:])
+    elif len(body) < opt.train_depth:
+        groups += vae_groups()
+        groups += body_groups(body)
+    else:
+        groups += body_groups(body[-opt.train_depth:])
+    return groups
+
+
+class GradBucket:
+    """flat fp32 bucket for the per-backward gradient all-reduce (average over ranks)"""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.flat = None
+
+    def average(self, params):
+        import torch.distributed as dist
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return 0
+        n = sum(g.numel() for g in grads)
+        if self.flat is None or self.flat.numel() != n or self.flat.device != grads[0].device:
+            self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+        views, off = [], 0
+        for g in grads:
+            views.append(self.flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(views, grads)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(dist.get_world_size(self.group))
+        torch._foreach_copy_(grads, views)
+        return n * 4
+
+
+class ScaleTrainer:
+    """state of one `train(opt, netG)` call of the reference: optimizers and the iteration body"""
+
+    def __init__(self, opt, netG, netD=None, distributed=False, dims=3):
+        _train_defaults(opt)
+        self.opt, self.netG, self.netD, self.dims = opt, netG, netD, dims
+        self.gan = opt.vae_levels < opt.scale_idx + 1
+        if self.gan and netD is None:
+            raise ValueError("scale %d is a GAN scale (vae_levels=%d): a discriminator is required" % (opt.scale_idx, opt.vae_levels))
+        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999))
+        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999)) if self.gan else None
+        self.distributed = distributed
+        self.bucketG, self.bucketD = GradBucket(), GradBucket()
+        self.allreduce_bytes = 0
+        self.iterations = 0
+
+    # train_video.py:126 — drawn every iteration, also at VAE scales where it is unused (keeps the RNG stream aligned)
+    def _noise_init(self, device):
+        return images.generate_noise(size=self.opt.Z_init_size, device=device)
+
+    def calc_noise_amp(self, real, real_zero):
+        """train_video.py:131-145 (iteration 0 of a scale)"""
+        opt = self.opt
+        if opt.const_amp:
+            opt.Noise_Amps.append(1)
+            return
+        with torch.no_grad():
+            if opt.scale_idx == 0:
+                opt.noise_amp = 1
+                opt.Noise_Amps.append(opt.noise_amp)
+            else:
+                opt.Noise_Amps.append(0)
+                z_rec, _, _ = self.netG(real_zero, opt.Noise_Amps, mode="rec")
+                mse = F.mse_loss(real, z_rec)
+                if self.distributed:
+                    import torch.distributed as dist
+                    dist.all_reduce(mse, op=dist.ReduceOp.SUM)
+                    mse /= dist.get_world_size()
+                opt.noise_amp = opt.noise_amp_init * torch.sqrt(mse).item() / opt.batch_size
+                opt.Noise_Amps[-1] = opt.noise_amp
+
+    def iteration(self, real, real_zero):
+        """train_video.py:126-202; returns the loss tensors of this iteration (no host sync inside)"""
+        from modules.losses import kl_criterion
+        from modules.utils import calc_gradient_penalty
+        opt, G, D = self.opt, self.netG, self.netD
+        noise_init = self._noise_init(real.device)
+        if self.iterations == 0 and len(opt.Noise_Amps) < opt.scale_idx + 1:
+            self.calc_noise_amp(real, real_zero)
+        out = {}
+        generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
+        if not self.gan:
+            rec_vae_loss = F.mse_loss(generated, real) + F.mse_loss(generated_vae, real_zero)
+            kl_loss = kl_criterion(mu, logvar)
+            total_loss = opt.rec_weight * rec_vae_loss + opt.kl_weight * kl_loss
+            out.update(rec_vae_loss=rec_vae_loss.detach(), kl_loss=kl_loss.detach())
+        else:
+            D.zero_grad()
+            errD_real = -D(real).mean()
+            fake, _ = G(noise_init, opt.Noise_Amps, noise_init=noise_init, mode="rand")
+            errD_fake = D(fake.detach()).mean()
+            gradient_penalty = calc_gradient_penalty(D, real, fake, opt.lambda_grad, real.device)
+            errD_total = errD_real + errD_fake + gradient_penalty
+            errD_total.backward()
+            if self.distributed:
+                self.allreduce_bytes += self.bucketD.average(list(D.parameters()))
+            self.optimizerD.step()
+
+            rec_loss = F.mse_loss(generated, real)
+            errG = -D(fake).mean() * opt.disc_loss_weight
+            total_loss = opt.rec_weight * rec_loss + errG
+            out.update(rec_loss=rec_loss.detach(), errG=errG.detach(), errD_real=errD_real.detach(), errD_fake=errD_fake.detach(),
+                       gradient_penalty=gradient_penalty.detach())
+        G.zero_grad()
+        total_loss.backward()
+        if self.distributed:
+            self.allreduce_bytes += self.bucketG.average(list(G.parameters()))
+        torch.nn.utils.clip_grad_norm_(G.parameters(), opt.grad_clip)
+        self.optimizerG.step()
+        out['total_loss'] = total_loss.detach()
+        self.iterations += 1
+        return out
+
+
+@torch.no_grad()
+def generate(netG, opt, n_samples, device, batch=1):
+    """the reference's sampling path (train_video.py:226-235): fresh z per draw, G(z, amps, noise_init=z, mode='rand').
+    batch=1 keeps BatchNorm statistics per sample, which makes the result independent of how draws are sharded over
+    GPUs.  Returns the number of generated frames and the last sample."""
+    frames, fake = 0, None
+    size = list(opt.Z_init_size)
+    for i in range(0, n_samples, batch):
+        size[0] = min(batch, n_samples - i)
+        z = images.generate_noise(size=size, device=device)
+        fake, _ = netG(z, opt.Noise_Amps, noise_init=z, mode="rand")
+        frames += fake.shape[0] * (fake.shape[2] if fake.dim() == 5 else 1)
+    return frames, fake

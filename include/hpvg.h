@@ -41,6 +41,18 @@ int hpvg_get_conv_backend(void);
 /* number of kernels this library has launched since load (all threads) — bench.py's `gpu_launches` */
 long long hpvg_launch_count(void);
 
+/* Per-launch device timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline
+ * measurement; adds two event records per launch, so it is off by default and must not be used under stream capture).
+ * hpvg_profile_dump waits for the recorded events, aggregates them by (kind, work) and clears the log; it writes up to
+ * max_rows rows of 4 doubles {kind, work per launch, launches, total milliseconds} and returns the row count.
+ * kind: HPVG_PROF_*; work: algorithmic FLOPs of the launch for the convolution kernels. */
+#define HPVG_PROF_CONV_TC 0
+#define HPVG_PROF_WGRAD_TC 1
+#define HPVG_PROF_CONV_DIRECT 2
+#define HPVG_PROF_WGRAD_DIRECT 3
+int hpvg_profile_enable(int on);
+int hpvg_profile_dump(double* rows, int max_rows);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Convolution, 3x3x3 (KD == 3) or 3x3 (KD == 1), stride 1, zero padding `pad` in {0,1,2} on every filtered axis.
  * Replaces nn.Conv3d / nn.Conv2d forward inside ConvBlock3D / ConvBlock3DSN / the tail convs

@@ -1,0 +1,289 @@
+"""Per-layer GPU parity: every layer type of the path in isolation (forward tensor, input gradient, parameter
+gradients) against the CPU oracle's fp32 arithmetic on identical inputs, through the reference's module interface.
+
+Tolerances (north_star): relative 2e-2 for layers with bf16 operands (every 64/128-channel activation is stored in
+bf16), 1e-3 or tighter for the fp32 kernels (resize, tanh, KL, gradient penalty, spectral norm).
+At BASELINE.json's full size (16 x 64 x 64, 64 channels) the oracle would take too long per case, so the kernels are
+checked there through size-independent properties: the adjoint identities <conv(x), g> = <x, dgrad(g)> and
+<wgrad(x, g), w'> = <conv_{w'}(x), g>, and BatchNorm's zero-mean / unit-variance output statistics.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+F32_TOL = 1e-3
+EMU_FWD_TOL = 5e-4     # one layer vs the oracle with bf16 storage emulation: what is left is fp32 summation order
+EMU_BWD_TOL = 3e-3
+
+
+def _fill_module(m, seed):
+    sd = m.state_dict()
+    port.det_fill(sd, seed)
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def _leafs(sd):
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(('running_mean', 'running_var', 'weight_u', 'weight_v')):
+            v.requires_grad_(True)
+    return sd
+
+
+def _compare_grads(module, sd, prefix=''):
+    worst = 0.0
+    big = max(v.grad.norm().item() for v in sd.values() if v.is_floating_point() and v.grad is not None)
+    for k, p in module.named_parameters():
+        ref = sd[prefix + k].grad
+        assert p.grad is not None and ref is not None, k
+        d = (p.grad.detach().cpu().double() - ref.double()).norm().item()
+        # a conv bias in front of BatchNorm has a mathematically zero gradient: absolute floor
+        assert d <= BF16_TOL * ref.double().norm().item() + 2e-3 * big, (k, d, ref.norm().item())
+        worst = max(worst, d / (ref.double().norm().item() + 2e-3 * big))
+    return worst
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(64, 64, (1, 6, 20, 24)), (3, 64, (2, 5, 17, 19)), (128, 64, (1, 4, 16, 16)),
+                                            (64, 64, (1, 3, 33, 9))])
+def test_convblock3d_layer(cin, cout, shape):
+    """ConvBlock3D = Conv3d + BatchNorm3d(train) + LeakyReLU (reference modules/networks_3d.py:48-56)"""
+    from modules import networks_3d
+    m = networks_3d.ConvBlock3D(cin, cout, 3, 1, 1)
+    sd = _leafs(_fill_module(m, 5))
+    m.cuda()
+    n, d, h, w = shape
+    x = port.det_tensor((n, cin, d, h, w), 1)
+    g = port.det_tensor((n, cout, d, h, w), 2)
+    if cin >= 64:      # what the preceding layer hands over is a bf16 tensor: give both sides the same values
+        x = x.bfloat16().float()
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = port.conv_block(sd, '', x_ref, 1)
+    y_ref.backward(g)
+    x_gpu = x.cuda().requires_grad_(True)
+    y = m(x_gpu)
+    assert y.shape == y_ref.shape and y.dtype == torch.float32
+    assert rel_err(y, y_ref) < BF16_TOL
+    y.backward(g.cuda())
+    assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
+    _compare_grads(m, sd)
+    for k in ('norm.running_mean', 'norm.running_var'):
+        assert rel_err(dict(m.named_buffers())[k], sd[k]) < 1e-3, k
+    assert int(m.norm.num_batches_tracked.item()) == 1
+    # the same layer against the oracle's bf16 storage emulation: tight
+    sd2 = _leafs({k: v.detach().clone() for k, v in _fill_module(networks_3d.ConvBlock3D(cin, cout, 3, 1, 1), 5).items()})
+    x_emu = x.clone().requires_grad_(True)
+    with port.storage('bf16'):
+        y_emu = port.conv_block(sd2, '', x_emu, 1)
+        y_emu.backward(g.bfloat16().float())
+    assert rel_err(y, y_emu) < EMU_FWD_TOL
+    if cin >= 64:
+        assert rel_err(x_gpu.grad, x_emu.grad.bfloat16().float()) < EMU_BWD_TOL
+    assert rel_err(m.conv.weight.grad, sd2['conv.weight'].grad) < EMU_BWD_TOL
+    assert rel_err(m.norm.weight.grad, sd2['norm.weight'].grad) < EMU_BWD_TOL
+
+
+@pytest.mark.parametrize("cin,shape", [(64, (1, 5, 18, 20)), (3, (1, 4, 15, 13))])
+def test_convblock3dsn_layer(cin, shape):
+    """ConvBlock3DSN = spectral-norm Conv3d + LeakyReLU (reference modules/networks_3d.py:59-70)"""
+    from modules import networks_3d
+    m = networks_3d.ConvBlock3DSN(cin, 64, 3, 1, 1)
+    sd = _leafs(_fill_module(m, 6))
+    m.cuda()
+    n, d, h, w = shape
+    x = port.det_tensor((n, cin, d, h, w), 3)
+    g = port.det_tensor((n, 64, d, h, w), 4)
+    if cin >= 64:
+        x = x.bfloat16().float()
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = port.conv_block_sn(sd, '', x_ref, 1)
+    y_ref.backward(g)
+    x_gpu = x.cuda().requires_grad_(True)
+    y = m(x_gpu)
+    assert rel_err(y, y_ref) < BF16_TOL
+    y.backward(g.cuda())
+    assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
+    _compare_grads(m, sd)
+    bufs = dict(m.named_buffers())
+    assert rel_err(bufs['conv.weight_u'], sd['conv.weight_u']) < 1e-4
+    assert rel_err(bufs['conv.weight_v'], sd['conv.weight_v']) < 1e-4
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_convblock2d_and_bare_heads(dims):
+    """ConvBlock2D (networks_2d.py:53-61) and the bn=False, act=None form used by the mu / logvar heads"""
+    from modules import networks_2d, networks_3d
+    nets = networks_2d if dims == 2 else networks_3d
+    cls = nets.ConvBlock2D if dims == 2 else nets.ConvBlock3D
+    sp = (22, 26) if dims == 2 else (4, 12, 14)
+    for bn, act, cout in ((True, 'lrelu', 64), (False, None, 128)):
+        m = cls(64, cout, 3, 1, 1, bn=bn, act=act)
+        sd = _leafs(_fill_module(m, 8))
+        m.cuda()
+        x = port.det_tensor((2, 64) + sp, 5).bfloat16().float()
+        g = port.det_tensor((2, cout) + sp, 6)
+        x_ref = x.clone().requires_grad_(True)
+        y_ref = port.conv_block(sd, '', x_ref, 1)
+        y_ref.backward(g)
+        x_gpu = x.cuda().requires_grad_(True)
+        y = m(x_gpu)
+        assert y.shape == y_ref.shape
+        assert rel_err(y, y_ref) < BF16_TOL
+        y.backward(g.cuda())
+        assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
+        _compare_grads(m, sd)
+
+
+@pytest.mark.parametrize("cout,pad", [(3, 1), (1, 1), (3, 0)])
+def test_tail_conv_layer(cout, pad):
+    """the bare tail convolutions 64 -> nc_im / 64 -> 1 (networks_3d.py:175,341,362; pad 0 in GeneratorSG :290)"""
+    from hpvg import ops
+    w = port.det_tensor((cout, 64, 3, 3, 3), 7, scale=0.05)
+    b = port.det_tensor((cout,), 8, scale=0.05)
+    x = port.det_tensor((1, 64, 5, 14, 15), 9).bfloat16().float()
+    x_ref, w_ref, b_ref = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = F.conv3d(x_ref, w_ref, b_ref, padding=pad)
+    g = port.det_tensor(tuple(y_ref.shape), 10)
+    y_ref.backward(g)
+    xw = ops.ToWide.apply(x.cuda().requires_grad_(True))
+    xw.retain_grad()
+    wg, bg = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.conv(xw, wg, bg, pad, False)
+    assert rel_err(y, y_ref) < 1e-3          # bf16 input, fp32 weights, fp32 accumulation and output
+    y.backward(g.cuda())
+    assert rel_err(wg.grad, w_ref.grad) < BF16_TOL
+    assert rel_err(bg.grad, b_ref.grad) < 1e-4
+    assert rel_err(ops.convert_raw(xw.grad, False), x_ref.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("in_size,out_size", [((4, 12, 12), (4, 15, 15)), ((6, 54, 54), (16, 64, 64)), ((1, 33, 33), (1, 41, 41)),
+                                              ((5, 20, 18), (3, 9, 31))])
+def test_resize_matches_interpolate(in_size, out_size):
+    """utils.upscale / interpolate_3D: trilinear, align_corners=True, fused '+ amp * noise' (utils/images.py:22-26,83-93)"""
+    from hpvg import images
+    x = port.det_tensor((2, 3) + in_size, 11)
+    noise = port.det_tensor((2, 3) + out_size, 12)
+    g = port.det_tensor((2, 3) + out_size, 13)
+    x_ref = x.clone().requires_grad_(True)
+    y_ref = port.resize(x_ref, out_size) + 0.37 * noise
+    y_ref.backward(g)
+    x_gpu = x.cuda().requires_grad_(True)
+    y = images.resize(x_gpu, out_size, noise=noise.cuda(), amp=0.37)
+    assert rel_err(y, y_ref) < 1e-5
+    y.backward(g.cuda())
+    assert rel_err(x_gpu.grad, x_ref.grad) < 1e-5
+    assert rel_err(images.resize(x.cuda(), out_size), port.resize(x, out_size)) < 1e-5
+
+
+def test_vae_head_kl_and_tanh():
+    """reparameterize (networks_3d.py:29-35), kl_criterion (losses.py:7-9), tanh(a + b) (networks_3d.py:377,404)"""
+    from hpvg import ops
+    from modules.losses import kl_criterion
+    from modules import networks_3d
+    mu = port.det_tensor((1, 128, 4, 9, 10), 14, scale=0.7).bfloat16().float()
+    logvar = port.det_tensor((1, 128, 4, 9, 10), 15, scale=1.5).bfloat16().float()
+    eps = port.det_tensor((1, 128, 4, 9, 10), 16, scale=2.0)
+    g = port.det_tensor((1, 128, 4, 9, 10), 17)
+    mr, lr = mu.clone().requires_grad_(True), logvar.clone().requires_grad_(True)
+    z_ref = eps.mul(lr.mul(0.5).exp()).add(mr)
+    z_ref.backward(g.bfloat16().float())
+    mg, lg = mu.cuda().requires_grad_(True), logvar.cuda().requires_grad_(True)
+    z = ops.ToThin.apply(ops.Reparam.apply(ops.ToWide.apply(mg), ops.ToWide.apply(lg), eps.cuda()))
+    assert rel_err(z, z_ref) < 4e-3           # one bf16 rounding of the result
+    z.backward(g.cuda())
+    assert rel_err(mg.grad, mr.grad) < 4e-3 and rel_err(lg.grad, lr.grad) < 4e-3
+    # the module-level function of the reference API draws its own eps: compare in distribution only
+    z2 = networks_3d.reparameterize(mu.cuda(), logvar.cuda(), True)
+    assert z2.shape == mu.shape and abs(((z2.cpu() - mu) / logvar.mul(0.5).exp()).std().item() - 1.0) < 0.05
+
+    mr, lr = mu.clone().requires_grad_(True), logvar.clone().requires_grad_(True)
+    kl_ref = port.kl_criterion(mr, lr)
+    kl_ref.backward()
+    mg, lg = mu.cuda().requires_grad_(True), logvar.cuda().requires_grad_(True)
+    kl = kl_criterion(mg, lg)
+    assert abs(kl.item() - kl_ref.item()) < 1e-5 * abs(kl_ref.item())
+    kl.backward()
+    assert rel_err(mg.grad, mr.grad) < 1e-5 and rel_err(lg.grad, lr.grad) < 1e-5
+
+    a, b = port.det_tensor((2, 3, 5, 11, 7), 18, scale=2.0), port.det_tensor((2, 3, 5, 11, 7), 19)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    t_ref = torch.tanh(ar + br)
+    gg = port.det_tensor((2, 3, 5, 11, 7), 20)
+    t_ref.backward(gg)
+    ag, bg = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    t = ops.TanhAdd.apply(ag, bg)
+    assert rel_err(t, t_ref) < 1e-5
+    t.backward(gg.cuda())
+    assert rel_err(ag.grad, ar.grad) < 1e-4 and rel_err(bg.grad, br.grad) < 1e-4
+
+
+def test_gradient_penalty_reduction():
+    """the penalty term itself (modules/utils.py:18): lambda * mean((||g||_2 over channels - 1)^2), forward and backward"""
+    from hpvg import ops
+    g = port.det_tensor((2, 3, 4, 10, 9), 21, scale=1.3)
+    gr = g.clone().requires_grad_(True)
+    p_ref = ((gr.norm(2, dim=1) - 1) ** 2).mean() * 0.1
+    p_ref.backward()
+    gg = g.cuda().requires_grad_(True)
+    p = ops.GpPenalty.apply(gg, 0.1)
+    assert abs(p.item() - p_ref.item()) < 1e-5 * abs(p_ref.item())
+    p.backward()
+    assert rel_err(gg.grad, gr.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full BASELINE size (config 2 finest scale: N=1, 64 channels, 16 x 64 x 64): size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def _wide_randn(shape, seed):
+    gen = torch.Generator(device='cuda').manual_seed(seed)
+    return torch.randn(shape, device='cuda', generator=gen).to(torch.bfloat16)
+
+
+def _dot(a, b):
+    return (a.double() * b.double()).sum().item()
+
+
+@pytest.mark.parametrize("cin,cout,vol", [(64, 64, (16, 64, 64)), (128, 64, (4, 32, 32)), (64, 128, (4, 32, 32)), (64, 64, (6, 54, 54))])
+def test_full_size_conv_adjoint_identities(cin, cout, vol):
+    from hpvg import ops
+    d, h, w = vol
+    x = _wide_randn((1, d, h, w, cin), 1)
+    g = _wide_randn((1, d, h, w, cout), 2)
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    wt = (torch.randn((cout, cin, 3, 3, 3), device='cuda', generator=gen) * 0.02).bfloat16().float()
+    w2 = (torch.randn((cout, cin, 3, 3, 3), device='cuda', generator=gen) * 0.02).bfloat16().float()
+    y = ops.conv_raw(x, wt, None, 1, False, True)
+    gx = ops.conv_raw(g, wt, None, 1, True, True)
+    lhs, rhs = _dot(y, g), _dot(x, gx)
+    scale = (y.double().norm() * g.double().norm()).item()
+    assert abs(lhs - rhs) < 2e-3 * scale, (lhs, rhs, scale)          # both sides carry one bf16 output rounding
+    dw, db = ops.wgrad_raw(x, g, 1, tuple(wt.shape), want_bias=True)
+    y2 = ops.conv_raw(x, w2, None, 1, False, True)
+    lhs, rhs = _dot(dw, w2), _dot(y2, g)
+    scale = (y2.double().norm() * g.double().norm()).item()
+    assert abs(lhs - rhs) < 2e-3 * scale, (lhs, rhs, scale)
+    assert rel_err(db, g.float().sum((0, 1, 2, 3))) < 1e-4
+    # linearity in the weights (exact up to output rounding): conv(x, w) + conv(x, w2) = conv(x, w + w2)
+    y12 = ops.conv_raw(x, (wt + w2).bfloat16().float(), None, 1, False, True)
+    assert rel_err(y.float() + y2.float(), y12.float()) < 1e-2
+
+
+def test_full_size_batchnorm_statistics():
+    from modules import networks_3d
+    torch.manual_seed(0)
+    m = networks_3d.ConvBlock3D(64, 64, 3, 1, 1)
+    m.cuda()
+    x = _wide_randn((1, 16, 64, 64, 64), 4)
+    from hpvg import ops
+    stats = torch.zeros(128, device='cuda')
+    y = ops.conv_raw(x, m.conv.weight.detach(), m.conv.bias.detach(), 1, False, True, stats=stats)
+    yf = y.float().view(-1, 64)
+    assert rel_err(stats[:64], yf.sum(0)) < 1e-4 and rel_err(stats[64:], (yf * yf).sum(0)) < 1e-4
+    out = m.run(x).float().view(-1, 64)
+    # LeakyReLU(0.2) of a zero-mean unit-variance channel: compare with the same transform of the normalised conv output
+    ref = F.leaky_relu((yf - yf.mean(0)) / torch.sqrt(yf.var(0, unbiased=False) + 1e-5) * m.norm.weight.detach() + m.norm.bias.detach(), 0.2)
+    assert rel_err(out, ref) < 5e-3

@@ -1,0 +1,69 @@
+"""End-of-scale criterion of north_star: after a fixed number of training iterations on identical weights, data and
+random draws, the reconstruction loss of the CUDA path must agree with the reference's within 1 %.
+
+The golden fixtures (tests/golden/train_*.pt) hold the per-iteration losses of the UNMODIFIED reference modules
+stepping the loop of train_video.py:111-202 (Adam on generator and critic, WGAN-GP, gradient clipping).
+"""
+import pytest
+import torch
+
+from helpers import state_d_from, state_from, train_opt_from
+
+pytestmark = pytest.mark.gpu
+
+REC_TOL = 1e-2        # north_star: end-of-scale reconstruction loss within 1 %
+
+
+class DrawQueue:
+    def __init__(self):
+        self.tensors = []
+
+    def __call__(self, shape, dtype, device):
+        t = self.tensors.pop(0)
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device=device, dtype=dtype)
+
+
+@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide"])
+def test_reconstruction_loss_after_k_iterations(golden, monkeypatch, name):
+    from hpvg import images, train
+    from modules import networks_3d
+    fx = golden(name)
+    opt = train_opt_from(fx)
+    g = networks_3d.GeneratorHPVAEGAN(opt)
+    for _ in range(fx['stages']):
+        g.init_next_stage()
+    g.load_state_dict(state_from(fx), strict=True)
+    g.cuda()
+    d = None
+    if 'state_d' in fx:
+        d = networks_3d.WDiscriminator3D(opt)
+        d.load_state_dict(state_d_from(fx), strict=True)
+        d.cuda()
+    tr = train.ScaleTrainer(opt, g, d)
+    q = DrawQueue()
+    monkeypatch.setattr(images, "draw_normal", q)
+    alphas = []
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: torch.full((1, 1), alphas.pop(0)))
+    real, real_zero = fx['real'].cuda(), fx['real_zero'].cuda()
+    rec_key = 'rec_loss' if d is not None else 'rec_vae_loss'
+    history = []
+    for it in range(fx['iters']):
+        dr = fx['draws'][it]
+        q.tensors = [dr['noise_init']] + ([dr['eps_amp']] if 'eps_amp' in dr else []) + [dr['eps']]
+        if d is not None:
+            q.tensors += [dr['noises'][lvl] for lvl in sorted(dr['noises'])]
+            alphas.append(dr['alpha'])
+        out = tr.iteration(real, real_zero)
+        assert not q.tensors and not alphas, "the CUDA path draws in a different order than the reference"
+        history.append({k: v.item() for k, v in out.items()})
+    ref = fx['losses']
+    for it in range(fx['iters']):
+        assert abs(history[it][rec_key] - ref[it][rec_key]) <= REC_TOL * abs(ref[it][rec_key]), (it, history[it], ref[it])
+    assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) <= REC_TOL * abs(fx['noise_amps_after'][-1])
+    if d is not None:
+        # the critic's losses are differences of near-equal means: compare on the scale of the penalty term
+        scale = max(abs(ref[-1]['gradient_penalty']), 1e-3)
+        assert abs(history[-1]['gradient_penalty'] - ref[-1]['gradient_penalty']) <= 0.1 * scale
+    else:
+        assert abs(history[-1]['kl_loss'] - ref[-1]['kl_loss']) <= 5e-2 * abs(ref[-1]['kl_loss'])

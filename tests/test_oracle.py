@@ -1,0 +1,144 @@
+"""The CPU oracle (oracle/port.py) against the golden fixtures recorded from the unmodified reference."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import opt_from, rel_err, state_from, with_grad
+from oracle import port
+
+TOL = 2e-5
+
+
+def _check_grads(sd, golden_grads, tol):
+    """per-parameter gradient check; gradients that are mathematically zero (conv bias in front of BatchNorm) are
+    compared on an absolute scale tied to the largest gradient of the network"""
+    def gnorm(g):
+        return g['norm'] if isinstance(g, dict) else g.double().norm().item()
+    floor = 1e-6 * (1.0 + max(gnorm(g) for g in golden_grads.values()))
+    checked = 0
+    for k, g in golden_grads.items():
+        mine = sd[k].grad
+        assert mine is not None, k
+        if isinstance(g, dict):
+            assert abs(mine.double().norm().item() - g['norm']) <= tol * g['norm'] + floor, k
+            d = (mine.flatten()[:64].double() - g['head'].double()).norm().item()
+            assert d <= 50 * tol * g['head'].double().norm().item() + floor, k
+        else:
+            d = (mine.double() - g.double()).norm().item()
+            assert d <= tol * g.double().norm().item() + floor, (k, d)
+        checked += 1
+    assert checked > 0
+
+
+@pytest.mark.parametrize("name", ["hp3d_tiny", "hp3d_tiny_vae", "hp2d_tiny", "hp3d_wide"])
+def test_generator_matches_reference(golden, name):
+    fx = golden(name)
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    rec = fx['rec']
+    gen, gen_vae, (mu, logvar) = port.generator(sd, opt, fx['real_zero'], fx['amps'], mode='rec', eps=rec['eps'])
+    assert rel_err(gen, rec['gen']) < TOL
+    assert rel_err(gen_vae, rec['gen_vae']) < TOL
+    assert rel_err(mu, rec['mu']) < TOL and rel_err(logvar, rec['logvar']) < TOL
+    kl = port.kl_criterion(mu, logvar)
+    assert abs(kl.item() - rec['kl']) < TOL * max(1.0, abs(rec['kl']))
+    loss = 10.0 * (F.mse_loss(gen, fx['real']) + F.mse_loss(gen_vae, fx['real_zero'])) + kl
+    assert abs(loss.item() - rec['loss']) < TOL * abs(rec['loss'])
+    loss.backward()
+    _check_grads(sd, rec['grads'], 5e-4)
+    for k, b in rec['buffers'].items():
+        assert rel_err(sd[k].float(), b.float()) < TOL, k
+    with torch.no_grad():
+        fake, fake_vae = port.generator(sd, opt, None, fx['amps'], noise_init=fx['rand']['z'], mode='rand', noises=fx['rand']['noises'])
+    assert rel_err(fake, fx['rand']['fake']) < TOL
+    assert rel_err(fake_vae, fx['rand']['fake_vae']) < TOL
+    for k, b in fx['rand']['buffers'].items():
+        assert rel_err(sd[k].float(), b.float()) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["d3d_tiny", "d2d_tiny", "d3d_wide", "d2d_wide"])
+def test_discriminator_and_gradient_penalty_match_reference(golden, name):
+    fx = golden(name)
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    out_real = port.discriminator(sd, opt, fx['real'])
+    out_fake = port.discriminator(sd, opt, fx['fake'])
+    assert rel_err(out_real, fx['out_real']) < TOL and rel_err(out_fake, fx['out_fake']) < TOL
+    gp = port.gradient_penalty(sd, opt, fx['real'], fx['fake'], fx['lambda'], alpha=fx['alpha'])
+    assert abs(gp.item() - fx['gp']) < 1e-4 * abs(fx['gp'])
+    (-out_real.mean() + out_fake.mean() + gp).backward()
+    _check_grads(sd, fx['grads'], 2e-3)
+    for k, b in fx['buffers'].items():
+        assert rel_err(sd[k], b) < TOL, k
+
+
+def test_generator_sg_matches_reference(golden):
+    fx = golden("sg3d_tiny")
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    out = port.generator_sg(sd, opt, fx['z'], fx['amps'], mode='rec')
+    assert rel_err(out, fx['rec']['out']) < TOL
+    loss = F.mse_loss(out, fx['rec']['target'])
+    assert abs(loss.item() - fx['rec']['loss']) < TOL
+    loss.backward()
+    _check_grads(sd, fx['rec']['grads'], 5e-4)
+    with torch.no_grad():
+        fake = port.generator_sg(sd, opt, fx['z'], fx['amps'], mode='rand', noises=fx['rand']['noises'])
+    assert rel_err(fake, fx['rand']['fake']) < TOL
+
+
+def test_scale_schedule(golden):
+    fx = golden("hp3d_tiny")
+    opt = opt_from(fx)
+    assert [(port.scale_size(i, opt), port.time_depth(i, opt)) for i in range(fx['stages'] + 1)] == fx['sizes']
+    # the schedules quoted in SURVEY.md App. A
+    o = port.Opt(img_size=64, sampling_rates=[5, 3, 1])
+    assert [(port.scale_size(i, o), port.time_depth(i, o)) for i in range(5)] == [(32, 4), (39, 4), (46, 6), (54, 6), (64, 16)]
+    o = port.Opt(img_size=64)
+    assert [(port.scale_size(i, o), port.time_depth(i, o)) for i in range(5)] == [(32, 4), (39, 4), (46, 5), (54, 7), (64, 13)]
+
+
+@pytest.mark.parametrize("name,bound", [("hp3d_tiny", 0.45), ("hp2d_tiny", 0.45), ("hp3d_wide", 0.10)])
+def test_bf16_storage_emulation_stays_close_to_fp32(golden, name, bound):
+    """oracle.port.storage('bf16') — the precision model of the CUDA path — against the fp32 reference fixtures: outputs
+    within 3e-2, parameter gradients within the bound the GPU tests (tests/test_gpu_modules.py REF_GRAD_TOL) allow."""
+    fx = golden(name)
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    rec = fx['rec']
+    with port.storage('bf16'):
+        gen, gen_vae, (mu, logvar) = port.generator(sd, opt, fx['real_zero'], fx['amps'], mode='rec', eps=rec['eps'])
+        loss = 10.0 * (F.mse_loss(gen, fx['real']) + F.mse_loss(gen_vae, fx['real_zero'])) + port.kl_criterion(mu, logvar)
+        loss.backward()
+    assert rel_err(gen, rec['gen']) < 3e-2 and rel_err(gen_vae, rec['gen_vae']) < 3e-2
+    assert abs(loss.item() - rec['loss']) < 2e-3 * abs(rec['loss'])
+    big = max((g['norm'] if isinstance(g, dict) else g.double().norm().item()) for g in rec['grads'].values())
+    for k, g in rec['grads'].items():
+        mine = sd[k].grad.double()
+        if isinstance(g, dict):
+            assert abs(mine.norm().item() - g['norm']) <= bound * g['norm'] + 2e-3 * big, k
+        else:
+            assert (mine - g.double()).norm().item() <= bound * g.double().norm().item() + 2e-3 * big, k
+
+
+@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide"])
+def test_training_loop_matches_reference(golden, name):
+    """oracle/train_ref.py (optimizer groups + iteration body of train_video.py:44-202) against the losses recorded from
+    the unmodified reference modules stepping the same loop on the same draws"""
+    from helpers import state_d_from, train_opt_from
+    from oracle import train_ref
+    fx = golden(name)
+    opt = train_opt_from(fx)
+    sd_g = state_from(fx)
+    sd_d = state_d_from(fx) if 'state_d' in fx else None
+    tr = train_ref.ScaleTrainer(opt, sd_g, sd_d)
+    for it in range(fx['iters']):
+        dr = fx['draws'][it]
+        out = tr.iteration(fx['real'], fx['real_zero'], noise_init=dr['noise_init'], eps=dr['eps'], noises=dr.get('noises'),
+                           alpha=dr.get('alpha'), eps_amp=dr.get('eps_amp'))
+        for k, v in fx['losses'][it].items():
+            assert abs(out[k].item() - v) <= 2e-3 * abs(v) + 2e-5, (it, k, out[k].item(), v)
+    assert len(opt.Noise_Amps) == len(fx['noise_amps_after'])
+    assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) < 1e-4 * abs(fx['noise_amps_after'][-1])
+    key = ('body.%d.tail.weight' % (fx['stages'] - 1)) if fx['stages'] > 0 else 'decoder.tail.weight'
+    assert rel_err(sd_g[key], fx['final_tail_weight']) < 1e-3
