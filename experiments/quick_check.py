@@ -25,7 +25,8 @@ def check_conv(n, cin, cout, d, h, w, pad, x_wide, y_wide, act=None, backend=lib
     b = torch.randn(cout, device=dev) if not transposed else None
     xq = wide(x) if x_wide else x
     xr = thin(xq) if x_wide else x
-    wr = wt.to(torch.bfloat16).float() if (x_wide and y_wide and backend != lib.BACKEND_DIRECT and cin % 64 == 0 and cout % 64 == 0) else wt
+    tc = x_wide and backend != lib.BACKEND_DIRECT and ((y_wide and cin % 64 == 0 and cout % 64 == 0) or (not y_wide and cin == 64 and cout <= 16 and act is None))
+    wr = wt.to(torch.bfloat16).float() if tc else wt
     stats = torch.zeros(2 * cout, device=dev) if y_wide else None
     y = ops.conv_raw(xq, wt, b, pad, transposed, y_wide, act_slope=act, stats=stats)
     torch.cuda.synchronize()
@@ -84,6 +85,13 @@ if which in ("all", "tc"):
     check_conv(1, 64, 64, 7, 20, 21, 0, True, True, tag="[tc]")
     check_conv(1, 64, 64, 5, 20, 21, 2, True, True, tag="[tc]")
     check_conv(1, 64, 64, 4, 16, 16, 1, True, True, transposed=True, tag="[tc]")
+if which in ("all", "thin"):
+    check_conv(1, 64, 3, 4, 16, 8, 1, True, False, tag="[tc-thin]")
+    check_conv(2, 64, 3, 3, 10, 7, 1, True, False, tag="[tc-thin]")
+    check_conv(1, 64, 1, 6, 54, 54, 1, True, False, tag="[tc-thin]")
+    check_conv(1, 64, 3, 16, 64, 64, 1, True, False, tag="[tc-thin]")
+    check_conv(1, 64, 3, 7, 20, 21, 0, True, False, tag="[tc-thin]")
+    check_conv(1, 64, 3, 4, 9, 11, 1, True, False, transposed=True, tag="[tc-thin]")
 if which in ("all", "wtc"):
     check_wgrad(1, 64, 64, 4, 16, 8, 1, True, True)
     check_wgrad(1, 64, 64, 4, 32, 32, 1, True, True)

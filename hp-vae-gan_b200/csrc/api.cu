@@ -54,6 +54,9 @@ void prof_end(void* h, cudaStream_t st) {
   delete r;
 }
 
+static std::atomic<long long*> g_dbg{nullptr};
+long long* debug_clock_buffer() { return g_dbg.load(std::memory_order_relaxed); }
+
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   static std::atomic<int> state{0};
@@ -116,6 +119,11 @@ int hpvg_set_conv_backend(int backend) {
 }
 int hpvg_get_conv_backend(void) { return hpvg::g_backend.load(); }
 long long hpvg_launch_count(void) { return hpvg::g_launches.load(); }
+
+int hpvg_debug_set_clock_buffer(long long* device_buffer) {
+  hpvg::g_dbg.store(device_buffer);
+  return 0;
+}
 
 int hpvg_profile_enable(int on) {
   hpvg::g_prof_on.store(on ? 1 : 0);

@@ -7,8 +7,8 @@ int conv_direct(const void* x, int x_fmt, const float* w, const float* bias, voi
                 int act, float slope, float* stats, const void* mask_src, cudaStream_t st);
 int wgrad_direct(const void* x, int x_fmt, const void* gy, int gy_fmt, float* dw, const ConvGeom& g, cudaStream_t st);
 bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_packed);
-int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
-            const void* mask_src, cudaStream_t st);
+int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
+            float* stats, const void* mask_src, cudaStream_t st);
 bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
@@ -54,7 +54,8 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
   HPVG_CHECK_ARG(act == HPVG_ACT_NONE || act == HPVG_ACT_LRELU, "conv_forward: unknown activation %d", act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int backend = conv_backend();
-  const bool tc_ok = conv_tc_supported(x_fmt, y_fmt, g, w_packed);
+  const bool tc_ok = conv_tc_supported(x_fmt, y_fmt, g, w_packed) &&
+                     (y_fmt == HPVG_FMT_NDHWC_BF16 || (act == HPVG_ACT_NONE && !stats && !mask_src));
   if (backend == HPVG_BACKEND_TCGEN05 && !tc_ok) {
     set_error("conv_forward: tcgen05 backend required but shape/format unsupported (Cin=%d Cout=%d fmt %d->%d packed=%p)", Cin, Cout,
               x_fmt, y_fmt, w_packed);
@@ -63,7 +64,7 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
   const double flops = 2.0 * g.N * g.Do * g.Ho * g.Wo * (double)g.Cin * g.Cout * g.taps;
   if (tc_ok && backend != HPVG_BACKEND_DIRECT) {
     void* ph = prof_begin(HPVG_PROF_CONV_TC, flops, st);
-    int rc = conv_tc(x, w_packed, bias, y, g, act, lrelu_slope, stats, mask_src, st);
+    int rc = conv_tc(x, w_packed, bias, y, y_fmt, g, act, lrelu_slope, stats, mask_src, st);
     prof_end(ph, st);
     return rc;
   }

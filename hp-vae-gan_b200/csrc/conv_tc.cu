@@ -18,6 +18,7 @@
 //    (TMEM -> registers -> bias / LeakyReLU / LeakyReLU'-mask -> bf16 -> swizzled smem -> TMA store with hardware
 //    clipping at the tensor edge, plus per-channel sum / sum-of-squares for BatchNorm).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hpvg {
 
@@ -26,23 +27,37 @@ constexpr int SLAB_H = BH + 2, SLAB_W = BW + 2;     // 18 x 10 halo
 constexpr int SLAB_ROWS = SLAB_H * SLAB_W;          // 180 voxel rows of 128 B
 constexpr int SLAB_BYTES = SLAB_ROWS * 128;         // 23040
 constexpr int SLAB_STRIDE = 23 * 1024;              // keep every slab 1024-aligned
-constexpr int BTILE_BYTES = 64 * 128;               // one tap: 64 output channels x 64 input channels bf16
 constexpr int STG_BYTES = 128 * 128;                // one output tile: 128 voxels x 64 channels bf16
-constexpr int TC_THREADS = 192;
+constexpr int MAX_COUT = 256;
+constexpr int NEPI_WIDE = 8;                        // epilogue warps, wide (bf16 NDHWC) output: 2 per TMEM lane quadrant
+constexpr int NEPI_THIN = 4;                        // epilogue warps, thin (fp32 NCDHW, Cout <= 16) output
+constexpr int NMMA = 1;                             // MMA-issuing warps: one elected thread each, accumulators a % NMMA == index
 
-template <int KCHUNKS, int NACC>
+// KCHUNKS: input channels / 64.  NACC: output d-slices (accumulators) per unit.  NGRP: accumulator groups per unit;
+// the 27 weight taps are streamed once per group, so the epilogue of group i overlaps the MMAs of group i+1.
+// NOUT: MMA N = output channels per accumulator: 64 (wide output) or 16 (thin output, Cout <= 16 zero-padded).
+template <int KCHUNKS, int NACC, int NGRP, int NOUT>
 struct TcCfg {
+  static constexpr bool THIN = NOUT < 64;
   static constexpr int NSLOTS = NACC + 2;                       // d-slices resident per unit (3-D, pad 1)
   static constexpr int NSLAB = NSLOTS * KCHUNKS;
-  static constexpr int NB = (KCHUNKS == 1) ? 4 : 3;             // weight ring depth
-  static constexpr int NSTG = (KCHUNKS == 1) ? 2 : 1;           // output staging buffers
-  static constexpr int TMEM_COLS = (NACC * 64 <= 32) ? 32 : (NACC * 64 <= 64 ? 64 : (NACC * 64 <= 128 ? 128 : (NACC * 64 <= 256 ? 256 : 512)));
+  static constexpr int BTILE_BYTES = NOUT * 128;                // one tap: NOUT output channels x 64 input channels bf16
+  static constexpr int NB = THIN ? 8 : ((KCHUNKS == 1) ? 6 : 3);   // weight ring depth
+  static constexpr int NSTG = THIN ? 0 : ((KCHUNKS == 1) ? 2 : 1); // output staging buffers
+  static constexpr int NEPI = THIN ? NEPI_THIN : NEPI_WIDE;
+  static constexpr int THREADS = 32 * (1 + NMMA) + 32 * NEPI;
+  static constexpr int EPI_WARP0 = 1 + NMMA;
+  static constexpr int ACC_COLS = NACC * NOUT;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static constexpr int OFF_SLAB = 0;
   static constexpr int OFF_B = OFF_SLAB + NSLAB * SLAB_STRIDE;
   static constexpr int OFF_STG = OFF_B + NB * BTILE_BYTES;
-  static constexpr int OFF_BAR = OFF_STG + NSTG * STG_BYTES;
+  static constexpr int OFF_BIAS = OFF_STG + NSTG * STG_BYTES;          // float[MAX_COUT]
+  static constexpr int OFF_BAR = OFF_BIAS + MAX_COUT * 4;
   static constexpr int NBARS = NSLAB + 2 * NB + 3;
   static constexpr int SMEM_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
+  static_assert(NACC % NGRP == 0, "groups must divide the accumulators");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct TcParams {
@@ -54,13 +69,17 @@ struct TcParams {
   const float* bias;
   float* stats;
   const __nv_bfloat16* mask_src;
+  float* y_thin;    // NOUT == 16: float32 NCDHW output
+  long long* dbg;   // optional per-CTA phase clocks (development aid, hpvg_debug_set_clock_buffer)
 };
 
-template <int KCHUNKS, int NACC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT>
+__global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const TcParams p) {
-  using Cfg = TcCfg<KCHUNKS, NACC>;
+  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT>;
+  constexpr int GACC = NACC / NGRP;            // accumulators per group
+  constexpr int NEPI_THREADS = 32 * Cfg::NEPI;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -86,23 +105,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     for (int i = 0; i < Cfg::NSLAB; ++i) mbar_init(bar_slab_full(i), 1);
     for (int i = 0; i < Cfg::NB; ++i) {
       mbar_init(bar_b_full(i), 1);
-      mbar_init(bar_b_empty(i), 1);
+      mbar_init(bar_b_empty(i), NMMA);
     }
-    mbar_init(bar_acc_full, 1);
-    mbar_init(bar_acc_empty, 128);
-    mbar_init(bar_slabs_free, 1);
+    mbar_init(bar_acc_full, NMMA);
+    mbar_init(bar_acc_empty, NEPI_THREADS);
+    mbar_init(bar_slabs_free, NMMA);
     mbar_fence_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_y);
+    if (!Cfg::THIN) tma_prefetch_desc(&tmap_y);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  float* bias_s = reinterpret_cast<float*>(sgen + Cfg::OFF_BIAS);
+  for (int i = threadIdx.x; i < MAX_COUT; i += Cfg::THREADS) bias_s[i] = (p.bias && i < g.Cout) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int nslots = NACC + g.KD - 1;   // d-slices a unit touches
 
   // unit -> coordinates
   auto decode = [&](long long u, int& nb, int& n, int& d0, int& h0, int& w0) {
@@ -118,21 +137,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t bstage = 0, bphase = 0;
       int it = 0;
       for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
         int nb, n, d0, h0, w0;
         decode(u, nb, n, d0, h0, w0);
         if (it > 0) mbar_wait(bar_slabs_free, (uint32_t)((it - 1) & 1));
-        for (int j = 0; j < nslots; ++j) {
+#pragma unroll
+        for (int j = 0; j < NACC + KDT - 1; ++j) {
           const int d = d0 + j - g.pad_d;
           if (d < 0 || d >= g.Di) continue;
           // slice needed only if some valid accumulator reads it
           bool needed = false;
+#pragma unroll
           for (int a = 0; a < NACC; ++a) {
             const int kd = j - a;
-            if (kd >= 0 && kd < g.KD && d0 + a < g.Do) needed = true;
+            if (kd >= 0 && kd < KDT && d0 + a < g.Do) needed = true;
           }
           if (!needed) continue;
 #pragma unroll
@@ -142,162 +163,261 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tma_load_5d(s_slab + si * SLAB_STRIDE, &tmap_x, bar_slab_full(si), kc * 64, w0 - g.pad, h0 - g.pad, d, n);
           }
         }
-        for (int t = 0; t < g.taps; ++t) {
+#pragma unroll 1
+        for (int grp = 0; grp < NGRP; ++grp) {
+#pragma unroll 1
+          for (int t = 0; t < KDT * 9; ++t) {
 #pragma unroll
-          for (int kc = 0; kc < KCHUNKS; ++kc) {
-            mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
-            mbar_expect_tx(bar_b_full(bstage), BTILE_BYTES);
-            tma_load_2d(s_b + bstage * BTILE_BYTES, &tmap_w, bar_b_full(bstage), kc * 64, t * g.Cout + nb * 64);
-            if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+            for (int kc = 0; kc < KCHUNKS; ++kc) {
+              mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
+              mbar_expect_tx(bar_b_full(bstage), Cfg::BTILE_BYTES);
+              tma_load_2d(s_b + bstage * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), kc * 64, t * p.nblocks * NOUT + nb * NOUT);
+              if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+            }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 0, 0);
-    uint32_t bstage = 0, bphase = 0;
-    int it = 0;
-    for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
-      int nb, n, d0, h0, w0;
-      decode(u, nb, n, d0, h0, w0);
-      if (it > 0) {
-        mbar_wait(bar_acc_empty, (uint32_t)((it - 1) & 1));
-        tc_fence_after();
-      }
-      uint32_t touched = 0, slab_ready = 0;
-      for (int t = 0; t < g.taps; ++t) {
-        const int kd = t / 9, kh = (t % 9) / 3, kw = t % 3;
-#pragma unroll
-        for (int kc = 0; kc < KCHUNKS; ++kc) {
-          mbar_wait(bar_b_full(bstage), bphase);
+  } else if (warp <= NMMA) {
+    // ===================== MMA issuers: ONE elected thread per warp runs the whole loop =====================
+    // Measured on B200 (experiments/bench_kernels.py clk): with both operands in shared memory the loop is bound by
+    // the operand reads, (128 x 16 A + N x 16 B) x 2 B at 128 B/clk = 48 clk per MMA at N = 64 and 36 clk at N = 16,
+    // not by issue — a second issuing warp (NMMA = 2, accumulators a % NMMA) or removing the weight waits changes
+    // nothing.  That caps an N = 64 layer at 32/48 = 67 % of the tensor peak with this (SS) operand form.
+    const int mma_id = warp - 1;
+    // A tcgen05.mma of this shape occupies the tensor pipe for M*N/256 = 32 cycles (N = 64); the issuing thread must
+    // stay below that per MMA, so descriptors are formed by adding constants to precomputed 64-bit bases, every inner
+    // loop is unrolled and the region is guarded by elect.sync (a lane-id test makes ptxas broadcast each descriptor
+    // through a loop: the first version of this kernel spent ~125 cycles per MMA on issue alone).
+    if (elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(128, NOUT, 0, 0);
+      const uint64_t a_base = umma_desc(s_slab, 16, SLAB_W * 128, 2);
+      const uint64_t b_base = umma_desc(s_b, 16, 1024, 2);
+      uint32_t bstage = 0, bphase = 0;
+      int it = 0;
+      long long t_start = clock64(), t_bwait = 0, t_swait = 0;
+      for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+        int nb, n, d0, h0, w0;
+        decode(u, nb, n, d0, h0, w0);
+        if (it > 0) {
+          mbar_wait(bar_acc_empty, (uint32_t)((it - 1) & 1));
           tc_fence_after();
-          const uint32_t b_addr = s_b + bstage * BTILE_BYTES;
+        }
+        uint32_t touched = 0, waited = 0;
 #pragma unroll
-          for (int a = 0; a < NACC; ++a) {
-            if (d0 + a >= g.Do) continue;
-            const int slot = a + kd;
-            const int d = d0 + slot - g.pad_d;
-            if (d < 0 || d >= g.Di) continue;
-            const int si = slot * KCHUNKS + kc;
-            if (!((slab_ready >> si) & 1u)) {
-              mbar_wait(bar_slab_full(si), (uint32_t)(it & 1));
-              tc_fence_after();
-              slab_ready |= 1u << si;
+        for (int grp = 0; grp < NGRP; ++grp) {
+#pragma unroll
+          for (int kd = 0; kd < KDT; ++kd) {
+            // accumulators of this group that kd feeds
+            uint32_t amask = 0;
+#pragma unroll
+            for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
+              const int d = d0 + a + kd - g.pad_d;
+              if (a % NMMA == mma_id && d0 + a < g.Do && d >= 0 && d < g.Di) amask |= 1u << a;
             }
-            if (lane == 0) {
-              const uint32_t a_addr = s_slab + si * SLAB_STRIDE + (kh * SLAB_W + kw) * 128;
+            if (amask == 0) {
+              // nothing to do for this kd: the producer still streams its 9 weight taps, hand the slots back
+#pragma unroll 1
+              for (int q = 0; q < 9 * KCHUNKS; ++q) {
+                mbar_wait(bar_b_full(bstage), bphase);
+                umma_commit(bar_b_empty(bstage));
+                if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+              }
+              continue;
+            }
+            if (p.dbg) t_swait -= clock64();
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = umma_desc(a_addr + ks * 32, 16, SLAB_W * 128, 2);
-                const uint64_t bd = umma_desc(b_addr + ks * 32, 16, 1024, 2);
-                umma_bf16(tmem_base + a * 64, ad, bd, IDESC, (uint32_t)(((touched >> a) & 1u) | (ks > 0)));
+            for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
+              if (!((amask >> a) & 1u)) continue;
+              const int slot = a + kd;
+              if ((waited >> slot) & 1u) continue;
+              waited |= 1u << slot;
+#pragma unroll
+              for (int kc = 0; kc < KCHUNKS; ++kc) mbar_wait(bar_slab_full(slot * KCHUNKS + kc), (uint32_t)(it & 1));
+            }
+            if (p.dbg) t_swait += clock64();
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int kh = q / 3, kw = q % 3;
+#pragma unroll
+              for (int kc = 0; kc < KCHUNKS; ++kc) {
+                if (p.dbg) t_bwait -= clock64();
+                mbar_wait(bar_b_full(bstage), bphase);
+                if (p.dbg) t_bwait += clock64();
+                tc_fence_after();
+                const uint64_t bd = b_base + (uint64_t)((bstage * Cfg::BTILE_BYTES) >> 4);
+#pragma unroll
+                for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
+                  if (!((amask >> a) & 1u)) continue;
+                  const uint64_t ad = a_base + (uint64_t)((((a + kd) * KCHUNKS + kc) * SLAB_STRIDE + (kh * SLAB_W + kw) * 128) >> 4);
+                  const uint32_t tacc = tmem_base + a * NOUT;
+                  umma_bf16(tacc, ad, bd, IDESC, (touched >> a) & 1u);
+                  umma_bf16_acc(tacc, ad + 2, bd + 2, IDESC);
+                  umma_bf16_acc(tacc, ad + 4, bd + 4, IDESC);
+                  umma_bf16_acc(tacc, ad + 6, bd + 6, IDESC);
+                }
+                touched |= amask;
+                umma_commit(bar_b_empty(bstage));
+                if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
               }
             }
-            touched |= 1u << a;
           }
-          __syncwarp();
-          if (lane == 0) umma_commit(bar_b_empty(bstage));
-          if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+          umma_commit(bar_acc_full);      // group `grp` of this unit is complete when everything issued so far is
         }
-      }
-      if (lane == 0) {
-        umma_commit(bar_acc_full);
         umma_commit(bar_slabs_free);
       }
-      __syncwarp();
+      if (p.dbg && mma_id == 0) {
+        p.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;   // MMA issue loop, all units
+        p.dbg[blockIdx.x * 8 + 1] = t_bwait;               // waiting for weight tiles
+        p.dbg[blockIdx.x * 8 + 2] = t_swait;               // waiting for input slabs
+      }
     }
-  } else {
-    // ===================== epilogue (128 threads) =====================
+    __syncwarp();
+  } else if (!Cfg::THIN) {
+    // ===================== epilogue, wide output (8 warps: TMEM lane quadrant = warp & 3, column half = (warp - 2) / 4) ==========
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int ch = (warp - Cfg::EPI_WARP0) >> 2;   // which 32 of the 64 accumulator columns
     const int m = q * 32 + lane;             // accumulator row = brick voxel (hh = m / 8, ww = m % 8)
-    const int et = threadIdx.x - 64;         // 0..127 index inside the epilogue group
+    const int et = threadIdx.x - 32 * Cfg::EPI_WARP0;   // 0..255 index inside the epilogue group
     int it = 0;
     int stg = 0;
+    uint32_t full_phase = 0;
+    long long t_start = clock64(), t_accwait = 0;
     for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
       int nb, n, d0, h0, w0;
       decode(u, nb, n, d0, h0, w0);
-      mbar_wait(bar_acc_full, (uint32_t)(it & 1));
-      tc_fence_after();
       const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
       const bool row_ok = (oh < g.Ho) && (ow < g.Wo);
-      for (int a = 0; a < NACC; ++a) {
-        const int od = d0 + a;
-        if (od >= g.Do) break;
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64;
-        tmem_ld32(taddr, r);
-        tmem_ld32(taddr + 32, r + 32);
-        tmem_ld_wait();
-        float v[64];
+      float st_s = 0.f, st_s2 = 0.f;     // BatchNorm sums of this unit: channel (et & 63), rows of quarter (et >> 6)
+#pragma unroll 1
+      for (int grp = 0; grp < NGRP; ++grp) {
+        long long tq = clock64();
+        mbar_wait(bar_acc_full, full_phase);
+        full_phase ^= 1u;
+        t_accwait += clock64() - tq;
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
+          const int od = d0 + a;
+          if (od >= g.Do) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + ch * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nb * 64 + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] += __ldg(p.bias + nb * 64 + j);
-        }
-        if (p.mask_src && row_ok) {
-          const uint4* mp = reinterpret_cast<const uint4*>(
-              p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 mv = __ldg(mp + c);
-            float2 f;
-            f = unpack_bf16x2(mv.x); v[8 * c + 0] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 1] *= f.y > 0.f ? 1.f : p.slope;
-            f = unpack_bf16x2(mv.y); v[8 * c + 2] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 3] *= f.y > 0.f ? 1.f : p.slope;
-            f = unpack_bf16x2(mv.z); v[8 * c + 4] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 5] *= f.y > 0.f ? 1.f : p.slope;
-            f = unpack_bf16x2(mv.w); v[8 * c + 6] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 7] *= f.y > 0.f ? 1.f : p.slope;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bq = b4[j];
+              v[4 * j + 0] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+            }
           }
-        }
-        if (p.act == HPVG_ACT_LRELU) {
+          if (p.mask_src && row_ok) {
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64 + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-        }
-        if (!row_ok) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = 0.f;
-        }
-        // staging buffer must be free: the thread that issued its last TMA store waits for the read to finish
-        if (et == 0) tma_store_wait_read<Cfg::NSTG - 1>();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const uint32_t sdst = s_stg + stg * STG_BYTES + m * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = sdst + ((uint32_t)(c ^ (m & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[8 * c + 0], v[8 * c + 1])),
-                       "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
-                       "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7]))
-                       : "memory");
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          tma_store_5d(&tmap_y, s_stg + stg * STG_BYTES, nb * 64, w0, h0, od, n);
-          tma_store_commit();
-        }
-        if (p.stats) {
-          // column sums over the staged (bf16-rounded, invalid rows zeroed) tile: thread = channel, 64 rows each
-          const int c = et & 63, half = et >> 6;
-          const uint8_t* tile = sgen + Cfg::OFF_STG + stg * STG_BYTES;
-          float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < 64; ++rr) {
-            const int row = half * 64 + rr;
-            const __nv_bfloat16 bv =
-                *reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((c >> 3) ^ (row & 7)) << 4) + (c & 7) * 2);
-            const float f = bf2f(bv);
-            s += f;
-            s2 = fmaf(f, f, s2);
+            for (int c = 0; c < 4; ++c) {
+              uint4 mv = __ldg(mp + c);
+              float2 f;
+              f = unpack_bf16x2(mv.x); v[8 * c + 0] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 1] *= f.y > 0.f ? 1.f : p.slope;
+              f = unpack_bf16x2(mv.y); v[8 * c + 2] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 3] *= f.y > 0.f ? 1.f : p.slope;
+              f = unpack_bf16x2(mv.z); v[8 * c + 4] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 5] *= f.y > 0.f ? 1.f : p.slope;
+              f = unpack_bf16x2(mv.w); v[8 * c + 6] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 7] *= f.y > 0.f ? 1.f : p.slope;
+            }
           }
-          atomicAdd(p.stats + nb * 64 + c, s);
-          atomicAdd(p.stats + g.Cout + nb * 64 + c, s2);
+          if (p.act == HPVG_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+          }
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          // staging buffer must be free: the thread that issued its last TMA store waits for the read to finish
+          if (et == 0) tma_store_wait_read<Cfg::NSTG - 1>();
+          asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+          const uint32_t sdst = s_stg + stg * STG_BYTES + m * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = sdst + ((uint32_t)((ch * 4 + c) ^ (m & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[8 * c + 0], v[8 * c + 1])),
+                         "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
+                         "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7]))
+                         : "memory");
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+          if (et == 0) {
+            tma_store_5d(&tmap_y, s_stg + stg * STG_BYTES, nb * 64, w0, h0, od, n);
+            tma_store_commit();
+          }
+          if (p.stats) {
+            // column sums over the staged (bf16-rounded, invalid rows zeroed) tile: thread = channel, 32 rows each
+            const int c = et & 63, quarter = et >> 6;
+            const uint8_t* tile = sgen + Cfg::OFF_STG + stg * STG_BYTES;
+#pragma unroll 16
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = quarter * 32 + rr;
+              const __nv_bfloat16 bv =
+                  *reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((c >> 3) ^ (row & 7)) << 4) + (c & 7) * 2);
+              const float f = bf2f(bv);
+              st_s += f;
+              st_s2 = fmaf(f, f, st_s2);
+            }
+          }
+          stg = (stg + 1 == Cfg::NSTG) ? 0 : stg + 1;
         }
-        stg = (stg + 1 == Cfg::NSTG) ? 0 : stg + 1;
+      }
+      if (p.stats) {
+        atomicAdd(p.stats + nb * 64 + (et & 63), st_s);
+        atomicAdd(p.stats + g.Cout + nb * 64 + (et & 63), st_s2);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty);
     }
     if (et == 0) tma_store_wait_all<0>();
+    if (p.dbg && et == 0) {
+      p.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;   // epilogue warps, all units
+      p.dbg[blockIdx.x * 8 + 4] = t_accwait;             // of which waiting for the accumulators
+    }
+  } else {
+    // ===================== epilogue, thin output: float32 NCDHW, Cout <= 16, bias only =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int it = 0;
+    uint32_t full_phase = 0;
+    const size_t out_sp = (size_t)g.Do * g.Ho * g.Wo;
+    for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+      int nb, n, d0, h0, w0;
+      decode(u, nb, n, d0, h0, w0);
+      const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
+      const bool row_ok = (oh < g.Ho) && (ow < g.Wo);
+#pragma unroll 1
+      for (int grp = 0; grp < NGRP; ++grp) {
+        mbar_wait(bar_acc_full, full_phase);
+        full_phase ^= 1u;
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
+          const int od = d0 + a;
+          if (od >= g.Do) break;
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * NOUT, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* yp = p.y_thin + (size_t)n * g.Cout * out_sp + ((size_t)od * g.Ho + oh) * g.Wo + ow;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (c < g.Cout) yp[(size_t)c * out_sp] = __uint_as_float(r[c]) + bias_s[c];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty);
+    }
   }
 
   tc_fence_before();
@@ -305,12 +425,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int KCHUNKS, int NACC>
+template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<KCHUNKS, NACC>;
+  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return -2;
@@ -321,21 +442,29 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   p.units_d = (int)cdiv(g.Do, NACC);
   p.units_h = (int)cdiv(g.Ho, BH);
   p.units_w = (int)cdiv(g.Wo, BW);
-  p.nblocks = g.Cout / 64;
+  p.nblocks = NOUT == 64 ? g.Cout / 64 : 1;
   p.num_units = (long long)p.nblocks * g.N * p.units_d * p.units_h * p.units_w;
   const int grid = (int)min((long long)num_sms(), p.num_units);
-  conv_tc_kernel<KCHUNKS, NACC><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
+  conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
   HPVG_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
 }
 
+// wide -> wide (Cout multiple of 64) or wide -> thin (Cout <= 16, packed weights zero-padded to 16 rows per tap)
 bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_packed) {
-  return x_fmt == HPVG_FMT_NDHWC_BF16 && y_fmt == HPVG_FMT_NDHWC_BF16 && w_packed != nullptr && (g.Cin == 64 || g.Cin == 128) &&
-         (g.Cout % 64 == 0) && g.Cout >= 64 && g.Wi <= 65535 && g.Hi <= 65535;
+  if (x_fmt != HPVG_FMT_NDHWC_BF16 || w_packed == nullptr || !(g.Cin == 64 || g.Cin == 128) || g.Wi > 65535 || g.Hi > 65535) return false;
+  if (y_fmt == HPVG_FMT_NDHWC_BF16) return (g.Cout % 64 == 0) && g.Cout >= 64 && g.Cout <= MAX_COUT;
+  return g.Cout <= 16 && g.Cin == 64;
 }
 
-int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
-            const void* mask_src, cudaStream_t st) {
+int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
+            float* stats, const void* mask_src, cudaStream_t st) {
+  const bool thin = y_fmt == HPVG_FMT_NCDHW_F32;
+  if (thin && (act != HPVG_ACT_NONE || stats || mask_src)) {
+    set_error("conv_tc: the thin-output kernel supports bias only (no activation, statistics or mask)");
+    return -1;
+  }
+  const int nout = thin ? 16 : 64;
   CUtensorMap mx, mw, my;
   {
     uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.Di, (uint64_t)g.N};
@@ -343,14 +472,17 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, con
     if (int rc = make_tmap_bf16(&mx, x, 5, dims, box)) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)g.Cin, (uint64_t)g.taps * g.Cout};
-    uint32_t box[2] = {64, 64};
+    const int rows_per_tap = thin ? 16 : g.Cout;
+    uint64_t dims[2] = {(uint64_t)g.Cin, (uint64_t)g.taps * rows_per_tap};
+    uint32_t box[2] = {64, (uint32_t)nout};
     if (int rc = make_tmap_bf16(&mw, w_packed, 2, dims, box)) return rc;
   }
-  {
+  if (!thin) {
     uint64_t dims[5] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)g.N};
     uint32_t box[5] = {64, BW, BH, 1, 1};
     if (int rc = make_tmap_bf16(&my, y, 5, dims, box)) return rc;
+  } else {
+    my = mx;
   }
   TcParams p;
   p.g = g;
@@ -359,8 +491,19 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, con
   p.bias = bias;
   p.stats = stats;
   p.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask_src);
-  if (g.Cin == 64) return launch_tc<1, 4>(mx, mw, my, p, st);
-  return launch_tc<2, 2>(mx, mw, my, p, st);
+  p.y_thin = thin ? reinterpret_cast<float*>(y) : nullptr;
+  p.dbg = debug_clock_buffer();
+  if (thin) {
+    if (g.KD == 3) return launch_tc<1, 4, 3, 1, 16>(mx, mw, my, p, st);
+    return launch_tc<1, 4, 1, 1, 16>(mx, mw, my, p, st);
+  }
+  static const int ngrp = getenv("HPVG_TC_NGRP") ? atoi(getenv("HPVG_TC_NGRP")) : 1;   // tuning knob (development aid)
+  if (g.KD == 3) {
+    if (g.Cin == 64) return ngrp == 2 ? launch_tc<1, 4, 3, 2, 64>(mx, mw, my, p, st) : launch_tc<1, 4, 3, 1, 64>(mx, mw, my, p, st);
+    return launch_tc<2, 2, 3, 2, 64>(mx, mw, my, p, st);
+  }
+  if (g.Cin == 64) return launch_tc<1, 4, 1, 2, 64>(mx, mw, my, p, st);
+  return launch_tc<2, 2, 1, 2, 64>(mx, mw, my, p, st);
 }
 
 }  // namespace hpvg

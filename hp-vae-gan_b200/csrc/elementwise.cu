@@ -464,14 +464,15 @@ __global__ void __launch_bounds__(256) channel_sum_ncdhw_kernel(const float* __r
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int transposed,
-                                    const float* __restrict__ sigma) {
+                                    const float* __restrict__ sigma, int rows_per_tap) {
   const float inv = sigma ? 1.f / sigma[0] : 1.f;
-  const long long total = (long long)taps * Cout * Cin;
+  const long long total = (long long)taps * rows_per_tap * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin);
-    const int co = (int)((i / Cin) % Cout);
-    const int t = (int)(i / ((long long)Cin * Cout));
-    const float v = transposed ? w[((size_t)ci * Cout + co) * taps + (taps - 1 - t)] : w[((size_t)co * Cin + ci) * taps + t];
+    const int co = (int)((i / Cin) % rows_per_tap);
+    const int t = (int)(i / ((long long)Cin * rows_per_tap));
+    float v = 0.f;
+    if (co < Cout) v = transposed ? w[((size_t)ci * Cout + co) * taps + (taps - 1 - t)] : w[((size_t)co * Cin + ci) * taps + t];
     out[i] = f2bf(v * inv);
   }
 }
@@ -734,10 +735,11 @@ int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long
 }
 
 int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed, const float* inv_scale_of,
-                      void* stream) {
-  const long long total = (long long)taps * Cout * Cin;
+                      int rows_per_tap, void* stream) {
+  HPVG_CHECK_ARG(rows_per_tap >= Cout, "pack_weights: rows_per_tap (%d) < Cout (%d)", rows_per_tap, Cout);
+  const long long total = (long long)taps * rows_per_tap * Cin;
   pack_weights_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(w_f32, reinterpret_cast<__nv_bfloat16*>(w_packed), Cout, Cin, taps,
-                                                                     transposed, inv_scale_of);
+                                                                     transposed, inv_scale_of, rows_per_tap);
   HPVG_CHECK_LAUNCH("pack_weights");
   return 0;
 }

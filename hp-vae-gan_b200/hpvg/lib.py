@@ -19,6 +19,7 @@ PROTOTYPES = {
     "hpvg_set_conv_backend": (c_int, [c_int]),
     "hpvg_get_conv_backend": (c_int, []),
     "hpvg_launch_count": (c_longlong, []),
+    "hpvg_debug_set_clock_buffer": (c_int, [c_void_p]),
     "hpvg_profile_enable": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -26,7 +27,7 @@ PROTOTYPES = {
     "hpvg_conv_wgrad_workspace": (c_size_t, [c_int] * 10),
     "hpvg_conv_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "hpvg_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hpvg_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "hpvg_channel_sum": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_longlong, c_void_p]),
     "hpvg_bn_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_longlong,
                                  c_void_p, c_void_p, c_int, c_void_p]),

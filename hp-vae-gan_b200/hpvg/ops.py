@@ -81,13 +81,23 @@ def _kd_of(weight):
     return 3 if weight.dim() == 5 else 1
 
 
-def _tc_eligible(cin, cout, x_wide, y_wide):
-    return x_wide and y_wide and cin in (64, 128) and cout % 64 == 0 and lib.get_conv_backend() != lib.BACKEND_DIRECT
+THIN_ROWS = 16   # rows per tap of the packed weights of the thin-output tcgen05 kernel (Cout <= 16, zero padded)
 
 
-def pack_weights(w, cout, cin, taps, transposed, sigma=None):
-    out = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
-    lib.call("hpvg_pack_weights", _ptr(w), _ptr(out), cout, cin, taps, int(transposed), _ptr(sigma), _stream())
+def _tc_eligible(cin, cout, x_wide, y_wide, plain=True):
+    """which convolutions run on the tcgen05 kernels: wide -> wide with Cin in {64,128} and Cout a multiple of 64, and
+    wide -> thin with Cin == 64 and Cout <= 16 (bias only: `plain`)"""
+    if not x_wide or lib.get_conv_backend() == lib.BACKEND_DIRECT:
+        return False
+    if y_wide:
+        return cin in (64, 128) and cout % 64 == 0
+    return plain and cin == 64 and cout <= THIN_ROWS
+
+
+def pack_weights(w, cout, cin, taps, transposed, sigma=None, rows=None):
+    rows = cout if rows is None else rows
+    out = torch.empty((taps, rows, cin), dtype=torch.bfloat16, device=w.device)
+    lib.call("hpvg_pack_weights", _ptr(w), _ptr(out), cout, cin, taps, int(transposed), _ptr(sigma), rows, _stream())
     return out
 
 
@@ -112,8 +122,8 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
     do, ho, wo = d + 2 * pad_d - (kd - 1), h + 2 * pad - 2, wd + 2 * pad - 2
     y = _empty(n, cout, do, ho, wo, out_wide, x.device)
     packed = None
-    if _tc_eligible(cin, cout, is_wide(x), out_wide):
-        packed = pack_weights(w, cout, cin, taps, transposed)
+    if _tc_eligible(cin, cout, is_wide(x), out_wide, plain=act_slope is None and stats is None and mask_src is None):
+        packed = pack_weights(w, cout, cin, taps, transposed, rows=None if out_wide else THIN_ROWS)
     if bias is not None:
         bias = bias.contiguous()
     lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,

@@ -50,6 +50,8 @@ long long hpvg_launch_count(void);
 #define HPVG_PROF_WGRAD_TC 1
 #define HPVG_PROF_CONV_DIRECT 2
 #define HPVG_PROF_WGRAD_DIRECT 3
+/* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
+int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
 int hpvg_profile_dump(double* rows, int max_rows);
 
@@ -64,8 +66,8 @@ int hpvg_profile_dump(double* rows, int max_rows);
  *                      (the data gradient of a forward conv with padding p is this call with pad = 2 - p)
  * Output extent per filtered axis = input extent + 2*pad - 2.  D is not filtered when KD == 1.
  * `w_f32` is the float32 master weight in PyTorch layout; `w_packed` (may be NULL) is the bf16 image produced by
- * hpvg_pack_weights for the same `transposed` flag, required for the tcgen05 path (Cin, Cout multiples of 64 and
- * both tensors NDHWC_BF16).  `bias` may be NULL.  `stats` (may be NULL) is a float32 [2*Cout] accumulator that
+ * hpvg_pack_weights for the same `transposed` flag, required for the tcgen05 path (NDHWC_BF16 input with Cin in
+ * {64, 128}; NDHWC_BF16 output with Cout a multiple of 64, or NCDHW_F32 output with Cout <= 16 and Cin == 64, bias only).  `bias` may be NULL.  `stats` (may be NULL) is a float32 [2*Cout] accumulator that
  * receives += per-channel sum and sum of squares of the *stored* output (BatchNorm batch statistics,
  * aten::native_batch_norm's reduction, fused into the conv epilogue); the caller zeroes it.
  * `mask_src` (may be NULL; NDHWC_BF16, same extents as y) multiplies the result by the LeakyReLU derivative of that
@@ -85,11 +87,12 @@ int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float*
                     int N, int Cin, int Cout, int D, int H, int W, int KD, int pad,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* float32 [Cout][Cin][taps] (transposed == 0) or [Cin][Cout][taps] (transposed == 1) -> bf16 [taps][Cout][Cin]
- * K-major tiles for the tcgen05 kernels; `scale_ptr` (may be NULL) points to a device float whose reciprocal
- * multiplies every weight (spectral normalisation: W / sigma). */
+/* float32 [Cout][Cin][taps] (transposed == 0) or [Cin][Cout][taps] (transposed == 1) -> bf16 [taps][rows_per_tap][Cin]
+ * K-major tiles for the tcgen05 kernels (rows >= Cout are zero).  rows_per_tap = Cout for wide outputs, 16 for the
+ * thin-output kernel (Cout <= 16).  `inv_scale_of` (may be NULL) points to a device float whose reciprocal multiplies
+ * every weight (spectral normalisation: W / sigma). */
 int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed,
-                      const float* inv_scale_of, void* stream);
+                      const float* inv_scale_of, int rows_per_tap, void* stream);
 
 /* per-channel sum of a tensor: out[c] = sum_{n,o} t[n,c,o]   (bias gradient) */
 int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long spatial, void* stream);

@@ -71,9 +71,9 @@ def store_grad(t):
 
 
 def mma_weight(w):
-    """weights of the tcgen05 layers (Cin in {64,128}, Cout multiple of 64) are fed to the tensor core in bf16; the
-    master weight and its gradient stay fp32 (straight-through)"""
-    if _STORAGE[-1] == 'bf16' and w.shape[1] in (64, 128) and w.shape[0] % 64 == 0:
+    """weights of the tcgen05 layers (Cin in {64,128} with Cout a multiple of 64, and the 64 -> nc_im / 64 -> 1 tails)
+    are fed to the tensor core in bf16; the master weight and its gradient stay fp32 (straight-through)"""
+    if _STORAGE[-1] == 'bf16' and ((w.shape[1] in (64, 128) and w.shape[0] % 64 == 0) or (w.shape[1] == 64 and w.shape[0] <= 16)):
         return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()
     return w
 
@@ -185,7 +185,7 @@ def stage(sd, opt, prefix, x, pad, tail_pad):
     h = conv_block(sd, prefix + 'head.', x, pad)
     for i in range(opt.num_layer):
         h = conv_block(sd, '%sblock%d.' % (prefix, i), h, pad)
-    return conv(h, sd[prefix + 'tail.weight'], sd[prefix + 'tail.bias'], tail_pad)
+    return conv(h, mma_weight(sd[prefix + 'tail.weight']), sd[prefix + 'tail.bias'], tail_pad)
 
 
 def num_body(sd):
@@ -235,7 +235,7 @@ def discriminator(sd, opt, x):
     h = conv_block_sn(sd, 'head.', x, _half(opt))
     for i in range(opt.num_layer):
         h = conv_block_sn(sd, 'body.block%d.' % i, h, _half(opt))
-    return conv(h, sd['tail.weight'], sd['tail.bias'], 1)
+    return conv(h, mma_weight(sd['tail.weight']), sd['tail.bias'], 1)
 
 
 def gradient_penalty(sd_d, opt, real, fake, lam, alpha=None):

@@ -153,7 +153,7 @@ def test_tail_conv_layer(cout, pad):
     xw.retain_grad()
     wg, bg = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
     y = ops.conv(xw, wg, bg, pad, False)
-    assert rel_err(y, y_ref) < 1e-3          # bf16 input, fp32 weights, fp32 accumulation and output
+    assert rel_err(y, y_ref) < 5e-3          # bf16 input and weights (tcgen05), fp32 accumulation and output
     y.backward(g.cuda())
     assert rel_err(wg.grad, w_ref.grad) < BF16_TOL
     assert rel_err(bg.grad, b_ref.grad) < 1e-4
