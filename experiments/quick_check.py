@@ -85,6 +85,20 @@ if which in ("all", "tc"):
     check_conv(1, 64, 64, 7, 20, 21, 0, True, True, tag="[tc]")
     check_conv(1, 64, 64, 5, 20, 21, 2, True, True, tag="[tc]")
     check_conv(1, 64, 64, 4, 16, 16, 1, True, True, transposed=True, tag="[tc]")
+if which in ("all", "narrow"):
+    check_conv(1, 3, 64, 4, 9, 11, 1, False, True, act=0.2, tag="[expand]")
+    check_conv(2, 3, 64, 5, 17, 40, 1, False, True, tag="[expand]")
+    check_conv(1, 1, 64, 4, 9, 11, 1, False, True, transposed=True, tag="[expand]")
+    check_conv(1, 3, 64, 7, 20, 21, 0, False, True, tag="[expand]")
+    check_conv(1, 3, 64, 16, 64, 64, 1, False, True, tag="[expand]")
+    check_wgrad(1, 3, 64, 4, 9, 11, 1, False, True)
+    check_wgrad(2, 3, 64, 5, 17, 40, 1, False, True)
+    check_wgrad(1, 3, 64, 7, 20, 21, 0, False, True)
+    check_wgrad(1, 3, 64, 16, 64, 64, 1, False, True)
+    check_wgrad(1, 64, 1, 4, 9, 11, 1, True, False)
+    check_wgrad(2, 64, 3, 5, 17, 40, 1, True, False)
+    check_wgrad(1, 64, 3, 7, 20, 21, 0, True, False)
+    check_wgrad(1, 64, 3, 16, 64, 64, 1, True, False)
 if which in ("all", "thin"):
     check_conv(1, 64, 3, 4, 16, 8, 1, True, False, tag="[tc-thin]")
     check_conv(2, 64, 3, 3, 10, 7, 1, True, False, tag="[tc-thin]")

@@ -9,6 +9,13 @@ int wgrad_direct(const void* x, int x_fmt, const void* gy, int gy_fmt, float* dw
 bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_packed);
 int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
             float* stats, const void* mask_src, cudaStream_t st);
+bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* mask_src);
+int expand_conv(const void* x, const float* w, const float* bias, void* y, const ConvGeom& g, int transposed, int act, float slope,
+                float* stats, cudaStream_t st);
+bool narrow_wgrad_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
+size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g);
+int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbias_wide, const ConvGeom& g, void* workspace,
+                 size_t ws_bytes, cudaStream_t st);
 bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
@@ -70,6 +77,12 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
   }
   HPVG_CHECK_ARG(w_f32 != nullptr, "conv_forward: the CUDA-core kernel needs the float32 weights");
   HPVG_CHECK_ARG(mask_src == nullptr || y_fmt == HPVG_FMT_NDHWC_BF16, "conv_forward: mask_src requires an NDHWC_BF16 output");
+  if (backend != HPVG_BACKEND_DIRECT && expand_conv_supported(x_fmt, y_fmt, g, mask_src)) {
+    void* ph = prof_begin(HPVG_PROF_CONV_EXPAND, flops, st);
+    int rc = expand_conv(x, w_f32, bias, y, g, transposed, act, lrelu_slope, stats, st);
+    prof_end(ph, st);
+    return rc;
+  }
   void* ph = prof_begin(HPVG_PROF_CONV_DIRECT, flops, st);
   int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
   prof_end(ph, st);
@@ -80,6 +93,7 @@ size_t hpvg_conv_wgrad_workspace(int N, int Cin, int Cout, int D, int H, int W, 
   ConvGeom g;
   if (make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_wgrad_workspace")) return 0;
   if (wgrad_tc_supported(x_fmt, gy_fmt, g)) return wgrad_tc_workspace(g);
+  if (narrow_wgrad_supported(x_fmt, gy_fmt, g)) return narrow_wgrad_workspace(x_fmt, g);
   return 0;
 }
 
@@ -101,6 +115,13 @@ int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float*
     void* ph = prof_begin(HPVG_PROF_WGRAD_TC, flops, st);
     rc = wgrad_tc(x, gy, dw, g, workspace, workspace_bytes, st);
     prof_end(ph, st);
+  } else if (backend != HPVG_BACKEND_DIRECT && narrow_wgrad_supported(x_fmt, gy_fmt, g)) {
+    void* ph = prof_begin(HPVG_PROF_WGRAD_NARROW, flops, st);
+    const bool head = x_fmt == HPVG_FMT_NCDHW_F32;
+    rc = narrow_wgrad(x, x_fmt, gy, dw, head ? dbias : nullptr, g, workspace, workspace_bytes, st);
+    prof_end(ph, st);
+    if (rc) return rc;
+    if (head) return 0;      // the bias gradient (channel sum of the wide gy) was produced by the same kernel
   } else {
     void* ph = prof_begin(HPVG_PROF_WGRAD_DIRECT, flops, st);
     rc = wgrad_direct(x, x_fmt, gy, gy_fmt, dw, g, st);

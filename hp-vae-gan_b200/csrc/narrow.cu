@@ -1,0 +1,404 @@
+// CUDA-core kernels for the narrow ends of the networks, where one side of the convolution has <= 4 channels (the
+// 3-channel video / image, the 1-channel critic map) and the other side has 64:
+//
+//   expand_conv_kernel   thin (float32 NCDHW, Cin <= 4) -> wide (bf16 NDHWC, Cout = 64): the head convolutions
+//                        (modules/networks_3d.py:51,63 with in_channel = nc_im) and the data gradient of the tails
+//   outer_corr_kernel    weight gradients of both narrow layer types (aten::convolution_backward grad_weight):
+//                          head  dw[co][ci][t] = sum_v gy[v][co] * x[ci][v + t - pad]      (x thin, gy wide)
+//                          tail  dw[c][ci][t]  = sum_u x[u][ci]  * gy[c][u - t + pad]      (x wide, gy thin)
+//                        both are   OUT[k][j][t] = sum_p WIDE[p][k] * THIN[j][p + s_t]   with k < 64, j <= 4
+//
+// K = 27 * 3 = 81 per output is far below a tensor-core tile and the 64-channel side is read exactly once, so these are
+// FMA / HBM bound; the kernels stage a halo tile of the thin tensor and the filter in shared memory and keep
+// 24-128 accumulators per thread.  (The wide -> thin direction runs on tcgen05: conv_tc.cu, NOUT = 16.)
+#include "common.cuh"
+
+namespace hpvg {
+
+constexpr int EX_TH = 8, EX_TW = 32;             // output tile of the expand kernel: 1 x 8 x 32 voxels, 2 per thread
+constexpr int EX_HW = EX_TW + 2, EX_HH = EX_TH + 2;
+
+// ---------------------------------------------------------------------------------------------------------------
+// thin -> wide convolution, Cout == 64
+// ---------------------------------------------------------------------------------------------------------------
+template <int KDT>
+__global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, ConvGeom g,
+                                                          int transposed, int act, float slope, float* __restrict__ stats) {
+  extern __shared__ float sm[];
+  constexpr int TAPS = KDT * 9;
+  float* ws = sm;                                   // [TAPS][Cin][64]
+  float* xs = sm + TAPS * g.Cin * 64;               // [Cin][KDT][EX_HH][EX_HW]
+  const int tiles_w = (g.Wo + EX_TW - 1) / EX_TW, tiles_h = (g.Ho + EX_TH - 1) / EX_TH;
+  int b = blockIdx.x;
+  const int w0 = (b % tiles_w) * EX_TW;
+  b /= tiles_w;
+  const int h0 = (b % tiles_h) * EX_TH;
+  b /= tiles_h;
+  const int od = b % g.Do;
+  const int n = b / g.Do;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < TAPS * g.Cin * 64; i += 128) {
+    const int co = i & 63, ci = (i >> 6) % g.Cin, t = i / (64 * g.Cin);
+    ws[i] = transposed ? w[((size_t)ci * 64 + co) * TAPS + (TAPS - 1 - t)] : w[((size_t)co * g.Cin + ci) * TAPS + t];
+  }
+  const size_t in_sp = (size_t)g.Di * g.Hi * g.Wi;
+  for (int i = tid; i < g.Cin * KDT * EX_HH * EX_HW; i += 128) {
+    const int ww = i % EX_HW, hh = (i / EX_HW) % EX_HH, kd = (i / (EX_HW * EX_HH)) % KDT, ci = i / (EX_HW * EX_HH * KDT);
+    const int id = od + kd - g.pad_d, ih = h0 + hh - g.pad, iw = w0 + ww - g.pad;
+    float v = 0.f;
+    if (id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi)
+      v = __ldg(x + ((size_t)n * g.Cin + ci) * in_sp + ((size_t)id * g.Hi + ih) * g.Wi + iw);
+    xs[i] = v;
+  }
+  __syncthreads();
+
+  const int ty = tid >> 4, tx = tid & 15;          // output row ty, output columns 2*tx and 2*tx + 1 of the tile
+  float acc0[64], acc1[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc0[j] = acc1[j] = 0.f;
+  // the (ci, kd, kh) loops stay rolled: the body (48 LDS.128 + 384 FFMA) is already long enough to pipeline, and a
+  // fully unrolled kernel (27x larger) stalled on instruction fetch (ncu: stall_no_inst was the top reason)
+#pragma unroll 1
+  for (int ci = 0; ci < g.Cin; ++ci) {
+#pragma unroll 1
+    for (int kd = 0; kd < KDT; ++kd) {
+#pragma unroll 1
+      for (int kh = 0; kh < 3; ++kh) {
+        const float* xr = xs + ((ci * KDT + kd) * EX_HH + ty + kh) * EX_HW + 2 * tx;
+        const float2 xa = *reinterpret_cast<const float2*>(xr), xb = *reinterpret_cast<const float2*>(xr + 2);
+        const float xv[4] = {xa.x, xa.y, xb.x, xb.y};
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4* w4 = reinterpret_cast<const float4*>(ws + (((kd * 3 + kh) * 3 + kw) * g.Cin + ci) * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 q = w4[j];
+            acc0[4 * j + 0] = fmaf(xv[kw], q.x, acc0[4 * j + 0]);
+            acc0[4 * j + 1] = fmaf(xv[kw], q.y, acc0[4 * j + 1]);
+            acc0[4 * j + 2] = fmaf(xv[kw], q.z, acc0[4 * j + 2]);
+            acc0[4 * j + 3] = fmaf(xv[kw], q.w, acc0[4 * j + 3]);
+            acc1[4 * j + 0] = fmaf(xv[kw + 1], q.x, acc1[4 * j + 0]);
+            acc1[4 * j + 1] = fmaf(xv[kw + 1], q.y, acc1[4 * j + 1]);
+            acc1[4 * j + 2] = fmaf(xv[kw + 1], q.z, acc1[4 * j + 2]);
+            acc1[4 * j + 3] = fmaf(xv[kw + 1], q.w, acc1[4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  // epilogue: bias, activation, bf16 rounding, store, BatchNorm sums of the stored values
+  const int oh = h0 + ty, ow = w0 + 2 * tx;
+  const bool ok0 = oh < g.Ho && ow < g.Wo, ok1 = oh < g.Ho && ow + 1 < g.Wo;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float bv = bias ? __ldg(bias + j) : 0.f;
+    float a = acc0[j] + bv, c = acc1[j] + bv;
+    if (act == HPVG_ACT_LRELU) {
+      a = a > 0.f ? a : a * slope;
+      c = c > 0.f ? c : c * slope;
+    }
+    acc0[j] = ok0 ? bf2f(f2bf(a)) : 0.f;
+    acc1[j] = ok1 ? bf2f(f2bf(c)) : 0.f;
+  }
+  __nv_bfloat16* yp = y + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 64;
+  if (ok0) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      uint4 q;
+      q.x = pack_bf16x2(acc0[j + 0], acc0[j + 1]); q.y = pack_bf16x2(acc0[j + 2], acc0[j + 3]);
+      q.z = pack_bf16x2(acc0[j + 4], acc0[j + 5]); q.w = pack_bf16x2(acc0[j + 6], acc0[j + 7]);
+      *reinterpret_cast<uint4*>(yp + j) = q;
+    }
+  }
+  if (ok1) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      uint4 q;
+      q.x = pack_bf16x2(acc1[j + 0], acc1[j + 1]); q.y = pack_bf16x2(acc1[j + 2], acc1[j + 3]);
+      q.z = pack_bf16x2(acc1[j + 4], acc1[j + 5]); q.w = pack_bf16x2(acc1[j + 6], acc1[j + 7]);
+      *reinterpret_cast<uint4*>(yp + 64 + j) = q;
+    }
+  }
+  if (stats) {
+    __syncthreads();                 // the filter stage is dead: reuse it for the block reduction [2][64]
+    float* red = sm;
+    if (tid < 128) red[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const float s = warp_sum(acc0[j] + acc1[j]);
+      const float s2 = warp_sum(acc0[j] * acc0[j] + acc1[j] * acc1[j]);
+      if ((tid & 31) == 0) {
+        atomicAdd(red + j, s);
+        atomicAdd(red + 64 + j, s2);
+      }
+    }
+    __syncthreads();
+    if (tid < 128) atomicAdd(stats + tid, red[tid]);
+  }
+}
+
+bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* mask_src) {
+  return x_fmt == HPVG_FMT_NCDHW_F32 && y_fmt == HPVG_FMT_NDHWC_BF16 && g.Cin <= 4 && g.Cout == 64 && mask_src == nullptr;
+}
+
+int expand_conv(const void* x, const float* w, const float* bias, void* y, const ConvGeom& g, int transposed, int act, float slope,
+                float* stats, cudaStream_t st) {
+  const int tiles_w = (int)cdiv(g.Wo, EX_TW), tiles_h = (int)cdiv(g.Ho, EX_TH);
+  const long long blocks = (long long)g.N * g.Do * tiles_h * tiles_w;
+  const size_t smem = ((size_t)g.taps * g.Cin * 64 + (size_t)g.Cin * g.KD * EX_HH * EX_HW) * sizeof(float);
+  if (g.KD == 3)
+    expand_conv_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                                              g, transposed, act, slope, stats);
+  else
+    expand_conv_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+                                                              g, transposed, act, slope, stats);
+  HPVG_CHECK_LAUNCH("expand_conv_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// OUT[k][j][t] = sum_p WIDE[p][k] * THIN[j][p + s_t]        k < 64 (bf16 NDHWC), j < J <= 4 (float32 NCDHW)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int OC_TH = 8, OC_TW = 32;               // tile of WIDE voxels per block iteration: 1 x 8 x 32
+constexpr int OC_HH = OC_TH + 2, OC_HW = OC_TW + 2;
+constexpr int OC_ONES = OC_TH * OC_HW + OC_TW;     // a run of 1.0f long enough for every voxel base offset
+constexpr int OC_THREADS = 256;
+
+struct OuterCorrParams {
+  const __nv_bfloat16* wide;   // [N][Dw][Hw][Ww][64]
+  const float* thin;           // [N][J][Dt][Ht][Wt]
+  float* partial;              // [grid][NC][4][256] per-block partial sums (thread-major: coalesced), reduced by a second kernel
+  int N, J, KD, taps;
+  int Dw, Hw, Ww, Dt, Ht, Wt;
+  int sign, shift;             // THIN coordinate = p + sign * (tap offset) + shift   on every filtered axis
+  int shift_d;                 // the same for the depth axis (0 when KD == 1)
+  int want_sum;                // also produce sum_p WIDE[p][k] (bias gradient of a head layer) in the spare slot of slice 15
+  long long tiles;
+  int tiles_h, tiles_w;
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// thread = (kq = tid & 15 -> channels 4kq..4kq+3 of WIDE, sl = tid >> 4 -> (j, t) combinations sl, sl+16, ...); NC = combinations
+// per thread.  Unused slots point at offset 0 and are dropped by the reduction; with want_sum the last slot of slice 15
+// points into a run of ones, so that it accumulates the plain channel sum.
+template <int KDT, int NC>
+__global__ void __launch_bounds__(OC_THREADS, 2) outer_corr_kernel(const OuterCorrParams p) {
+  extern __shared__ __align__(16) uint8_t osm[];
+  constexpr int TAPS = KDT * 9;
+  constexpr int WT_BYTES = OC_TH * OC_TW * 128;
+  float* th = reinterpret_cast<float*>(osm + WT_BYTES);                 // [J][KDT][OC_HH][OC_HW] then OC_ONES ones
+  const int th_elems = p.J * KDT * OC_HH * OC_HW;
+  const int tid = threadIdx.x;
+  const int kq = tid & 15, sl = tid >> 4;
+  const int ncomb = TAPS * p.J;
+  uint32_t off[NC];                                                      // byte offsets into the THIN halo tile
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = sl + 16 * i;
+    off[i] = 0;
+    if (c < ncomb) {
+      const int j = c / TAPS, t = c % TAPS;
+      const int kd = t / 9, kh = (t % 9) / 3, kw = t % 3;
+      const int dd = (KDT == 3) ? (p.sign * kd + (p.sign > 0 ? 0 : 2)) : 0;
+      const int hh = p.sign * kh + (p.sign > 0 ? 0 : 2);
+      const int ww = p.sign * kw + (p.sign > 0 ? 0 : 2);
+      off[i] = 4u * (uint32_t)(((j * KDT + dd) * OC_HH + hh) * OC_HW + ww);
+    } else if (p.want_sum && sl == 15 && i == NC - 1) {
+      off[i] = 4u * (uint32_t)th_elems;
+    }
+  }
+  float acc[NC][4];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int i = tid; i < OC_ONES; i += OC_THREADS) th[th_elems + i] = 1.0f;
+
+  const uint32_t s_wt = smem_u32(osm) + 8u * kq, s_th = smem_u32(th);
+  const size_t thin_sp = (size_t)p.Dt * p.Ht * p.Wt;
+  for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    long long b = tile;
+    const int w0 = (int)(b % p.tiles_w) * OC_TW;
+    b /= p.tiles_w;
+    const int h0 = (int)(b % p.tiles_h) * OC_TH;
+    b /= p.tiles_h;
+    const int d0 = (int)(b % p.Dw);
+    const int n = (int)(b / p.Dw);
+    __syncthreads();
+    // WIDE tile: 256 voxels x 128 B, zero outside the tensor
+    for (int i = tid; i < OC_TH * OC_TW * 8; i += OC_THREADS) {
+      const int chunk = i & 7, vox = i >> 3;
+      const int hh = vox / OC_TW, ww = vox % OC_TW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (h0 + hh < p.Hw && w0 + ww < p.Ww)
+        v = __ldg(reinterpret_cast<const uint4*>(p.wide + ((((size_t)n * p.Dw + d0) * p.Hw + h0 + hh) * p.Ww + w0 + ww) * 64) + chunk);
+      reinterpret_cast<uint4*>(osm)[i] = v;
+    }
+    // THIN halo tile: origin chosen so that voxel (hh, ww) with tap offset k in {0,1,2} reads [hh + k'][ww + k'], k' >= 0
+    const int od = d0 + p.shift_d - (KDT == 3 ? (p.sign > 0 ? 0 : 2) : 0);
+    const int oh = h0 + p.shift - (p.sign > 0 ? 0 : 2), ow = w0 + p.shift - (p.sign > 0 ? 0 : 2);
+    for (int i = tid; i < th_elems; i += OC_THREADS) {
+      const int ww = i % OC_HW, hh = (i / OC_HW) % OC_HH, dd = (i / (OC_HW * OC_HH)) % KDT, j = i / (OC_HW * OC_HH * KDT);
+      const int id = od + dd, ih = oh + hh, iw = ow + ww;
+      float v = 0.f;
+      if (id >= 0 && id < p.Dt && ih >= 0 && ih < p.Ht && iw >= 0 && iw < p.Wt)
+        v = __ldg(p.thin + ((size_t)n * p.J + j) * thin_sp + ((size_t)id * p.Ht + ih) * p.Wt + iw);
+      th[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int hh = 0; hh < OC_TH; ++hh) {
+      uint32_t a_wt = s_wt + (uint32_t)(hh * OC_TW) * 128u;
+      uint32_t a_th = s_th + 4u * (uint32_t)(hh * OC_HW);
+#pragma unroll 4
+      for (int ww = 0; ww < OC_TW; ++ww, a_wt += 128u, a_th += 4u) {
+        const uint2 raw = lds_u64(a_wt);
+        const float2 a = unpack_bf16x2(raw.x), c = unpack_bf16x2(raw.y);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const float t = lds_f32(a_th + off[i]);
+          acc[i][0] = fmaf(a.x, t, acc[i][0]);
+          acc[i][1] = fmaf(a.y, t, acc[i][1]);
+          acc[i][2] = fmaf(c.x, t, acc[i][2]);
+          acc[i][3] = fmaf(c.y, t, acc[i][3]);
+        }
+      }
+    }
+  }
+  float* dst = p.partial + (size_t)blockIdx.x * (NC * 4 * OC_THREADS) + tid;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[(i * 4 + e) * OC_THREADS] = acc[i][e];
+}
+
+// dw[...] = sum over blocks of the partials; one thread per (slot i, element e, thread id) of the first kernel
+__global__ void outer_corr_reduce_kernel(const float* __restrict__ partial, int blocks, int nc, int taps, int J, int wide_is_gy,
+                                         float* __restrict__ dw, float* __restrict__ wide_sum) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nc * 4 * OC_THREADS) return;
+  const int tid = idx % OC_THREADS, e = (idx / OC_THREADS) & 3, i = idx / (4 * OC_THREADS);
+  const int kq = tid & 15, sl = tid >> 4;
+  const int c = sl + 16 * i, k = 4 * kq + e;
+  const int ncomb = taps * J;
+  const bool is_sum = wide_sum != nullptr && sl == 15 && i == nc - 1 && c >= ncomb;
+  if (c >= ncomb && !is_sum) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * (nc * 4 * OC_THREADS) + idx];
+  if (is_sum) {
+    wide_sum[k] = s;
+    return;
+  }
+  const int j = c / taps, t = c % taps;
+  if (wide_is_gy)
+    dw[((size_t)k * J + j) * taps + t] = s;
+  else
+    dw[((size_t)j * 64 + k) * taps + t] = s;
+}
+
+bool narrow_wgrad_supported(int x_fmt, int gy_fmt, const ConvGeom& g) {
+  if (x_fmt == HPVG_FMT_NCDHW_F32 && gy_fmt == HPVG_FMT_NDHWC_BF16) return g.Cin <= 4 && g.Cout == 64;
+  if (x_fmt == HPVG_FMT_NDHWC_BF16 && gy_fmt == HPVG_FMT_NCDHW_F32) return g.Cin == 64 && g.Cout <= 4;
+  return false;
+}
+
+static int oc_slots(const ConvGeom& g, bool head, bool want_sum) {
+  const int ncomb = g.taps * (head ? g.Cin : g.Cout);
+  int need = (int)cdiv(ncomb, 16);
+  if (want_sum && 15 + 16 * (need - 1) < ncomb) need += 1;      // slice 15 has no spare slot: add one
+  return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 6 ? 6 : 7));
+}
+static int oc_grid(const ConvGeom& g, bool head) {
+  const long long tiles = head ? (long long)g.N * g.Do * cdiv(g.Ho, OC_TH) * cdiv(g.Wo, OC_TW)
+                               : (long long)g.N * g.Di * cdiv(g.Hi, OC_TH) * cdiv(g.Wi, OC_TW);
+  return (int)min(tiles, (long long)num_sms() * 2);
+}
+
+size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g) {
+  const bool head = x_fmt == HPVG_FMT_NCDHW_F32;
+  return (size_t)oc_grid(g, head) * 7 * 4 * OC_THREADS * sizeof(float);
+}
+
+template <int KDT, int NC>
+static void oc_launch(const OuterCorrParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(outer_corr_kernel<KDT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done = true;
+  }
+  outer_corr_kernel<KDT, NC><<<grid, OC_THREADS, smem, st>>>(p);
+}
+
+// Two launches: per-block partial sums into `workspace` (deterministic, no atomics), then a fixed-order reduction into
+// dw (and dbias_wide = channel sum of the wide gy for a head layer).
+int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbias_wide, const ConvGeom& g, void* workspace,
+                 size_t ws_bytes, cudaStream_t st) {
+  OuterCorrParams p;
+  const bool head = x_fmt == HPVG_FMT_NCDHW_F32;
+  p.N = g.N;
+  p.KD = g.KD;
+  p.taps = g.taps;
+  if (head) {   // WIDE = gy over output voxels, THIN = x at v + t - pad
+    p.wide = reinterpret_cast<const __nv_bfloat16*>(gy);
+    p.thin = reinterpret_cast<const float*>(x);
+    p.J = g.Cin;
+    p.Dw = g.Do; p.Hw = g.Ho; p.Ww = g.Wo;
+    p.Dt = g.Di; p.Ht = g.Hi; p.Wt = g.Wi;
+    p.sign = 1;
+    p.shift = -g.pad;
+    p.shift_d = -g.pad_d;
+  } else {      // WIDE = x over input voxels, THIN = gy at u - t + pad
+    p.wide = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.thin = reinterpret_cast<const float*>(gy);
+    p.J = g.Cout;
+    p.Dw = g.Di; p.Hw = g.Hi; p.Ww = g.Wi;
+    p.Dt = g.Do; p.Ht = g.Ho; p.Wt = g.Wo;
+    p.sign = -1;
+    p.shift = g.pad;
+    p.shift_d = g.pad_d;
+  }
+  p.want_sum = (head && dbias_wide) ? 1 : 0;
+  p.tiles_h = (int)cdiv(p.Hw, OC_TH);
+  p.tiles_w = (int)cdiv(p.Ww, OC_TW);
+  p.tiles = (long long)p.N * p.Dw * p.tiles_h * p.tiles_w;
+  const int nc = oc_slots(g, head, p.want_sum != 0);
+  const int grid = oc_grid(g, head);
+  const size_t need = (size_t)grid * nc * 4 * OC_THREADS * sizeof(float);
+  if (workspace == nullptr || ws_bytes < need) {
+    set_error("narrow_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return -1;
+  }
+  p.partial = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)OC_TH * OC_TW * 128 + ((size_t)p.J * g.KD * OC_HH * OC_HW + OC_ONES) * sizeof(float);
+  if (g.KD == 3) {
+    if (nc == 2) oc_launch<3, 2>(p, grid, smem, st);
+    else if (nc == 4) oc_launch<3, 4>(p, grid, smem, st);
+    else if (nc == 6) oc_launch<3, 6>(p, grid, smem, st);
+    else oc_launch<3, 7>(p, grid, smem, st);
+  } else {
+    if (nc == 2) oc_launch<1, 2>(p, grid, smem, st);
+    else if (nc == 4) oc_launch<1, 4>(p, grid, smem, st);
+    else if (nc == 6) oc_launch<1, 6>(p, grid, smem, st);
+    else oc_launch<1, 7>(p, grid, smem, st);
+  }
+  HPVG_CHECK_LAUNCH("outer_corr_kernel");
+  const int total = nc * 4 * OC_THREADS;
+  outer_corr_reduce_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, grid, nc, g.taps, p.J, head ? 1 : 0, dw,
+                                                                      p.want_sum ? dbias_wide : nullptr);
+  HPVG_CHECK_LAUNCH("outer_corr_reduce_kernel");
+  return 0;
+}
+
+}  // namespace hpvg

@@ -50,6 +50,8 @@ long long hpvg_launch_count(void);
 #define HPVG_PROF_WGRAD_TC 1
 #define HPVG_PROF_CONV_DIRECT 2
 #define HPVG_PROF_WGRAD_DIRECT 3
+#define HPVG_PROF_CONV_EXPAND 4
+#define HPVG_PROF_WGRAD_NARROW 5
 /* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
 int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
