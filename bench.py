@@ -209,7 +209,8 @@ def run_hpvg(args):
     D.load_state_dict(sd)
     G.to(dev)
     D.to(dev)
-    trainer = train.ScaleTrainer(o, G, D, distributed=distributed)
+    use_graph = not args.no_graph
+    trainer = train.ScaleTrainer(o, G, D, distributed=distributed, capturable=use_graph)
     real_h, real_zero_h = synthetic_clip(o, rank)  # one clip per rank
     real_h, real_zero_h = real_h.pin_memory(), real_zero_h.pin_memory()
     real, real_zero = real_h.to(dev), real_zero_h.to(dev)
@@ -234,35 +235,54 @@ def run_hpvg(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    def step_resident():
-        trainer.iteration(real, real_zero)
-
     last = {}
-
-    def step_e2e():
-        r = real_h.to(dev, non_blocking=True)
-        rz = real_zero_h.to(dev, non_blocking=True)
-        out = trainer.iteration(r, rz)
-        last["rec_loss"] = out["rec_loss"].item()          # device -> host read of the step's result
-
     W = max(3, args.warmup)
-    for _ in range(W):
-        step_resident()
+    if use_graph:
+        # the whole iteration (every libhpvg kernel, autograd glue, clipping, both Adam steps, the all-reduces) is
+        # recorded once into a CUDA graph after W eager warm-up iterations and replayed per step
+        c0 = lib.launch_count()
+        trainer.capture(real, real_zero, warmup=W)
+        launches_per_iter = (lib.launch_count() - c0) // (W + 1)
+
+        def step_resident():
+            trainer.replay()
+
+        def step_e2e():
+            out = trainer.replay(real_h, real_zero_h)          # H2D of the clip into the graph's input buffers
+            last["rec_loss"] = out["rec_loss"].item()          # device -> host read of the step's result
+        for _ in range(2):
+            step_resident()
+    else:
+        launches_per_iter = None
+
+        def step_resident():
+            trainer.iteration(real, real_zero)
+
+        def step_e2e():
+            r = real_h.to(dev, non_blocking=True)
+            rz = real_zero_h.to(dev, non_blocking=True)
+            out = trainer.iteration(r, rz)
+            last["rec_loss"] = out["rec_loss"].item()
+        for _ in range(W):
+            step_resident()
     torch.cuda.reset_peak_memory_stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = lib.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = lib.launch_count() - n0
+    launches = lib.launch_count() - n0 if not use_graph else launches_per_iter * args.steps
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     peak_mb = torch.cuda.max_memory_allocated() / 2**20
 
     # roofline leg: the same steps again with CUDA events around every convolution launch (on the launching stream)
     prof_steps = min(args.steps, 3)
+
+    def step_eager():
+        trainer.iteration(real, real_zero)
     lib.profile_enable(True)
-    ms_prof = timed(step_resident, prof_steps)
+    ms_prof = timed(step_eager, prof_steps)
     lib.profile_enable(False)
     rows = lib.profile_dump()
 
@@ -303,7 +323,8 @@ def run_hpvg(args):
                         "share_of_step": top["ms"] / prof_steps / (ms_prof / prof_steps),
                         "by_kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in by_kind.items()},
                         "by_kernel_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None) for k, v in by_kind.items()},
-                        "ms_per_step_with_events": ms_prof / prof_steps}
+                        "ms_per_step_with_events": ms_prof / prof_steps,
+                        "note": "per-launch CUDA events need eager launches: this leg runs the same iteration un-graphed"}
         value = world * args.steps / (ms * 1e-3)
         e2e = world * args.steps / (ms_e2e * 1e-3)
         bi = (real_h.numel() + real_zero_h.numel()) * 4
@@ -312,7 +333,9 @@ def run_hpvg(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat NCCL grad all-reduce)" % world if distributed else "single GPU",
                            "l2": "no explicit flush: one iteration touches %.0f MB of activations (peak allocated), above the 126 MB L2" % peak_mb,
-                           "conv_gflop_per_iter": CONV_GFLOP_PER_ITER},
+                           "conv_gflop_per_iter": CONV_GFLOP_PER_ITER,
+                           "launch": ("one CUDA graph replay per iteration (%d libhpvg kernels recorded)" % launches_per_iter) if use_graph
+                           else "eager launches"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops": value * CONV_GFLOP_PER_ITER / 1e3 / world,
@@ -340,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
     ap.add_argument("--draws", type=int, default=64, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -430,7 +430,9 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, flo
     dst[i] = bf2f(src[(n * S + s) * C + c]);
   }
 }
-__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, float alpha, long long n) {
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                            const float* __restrict__ alpha_ptr, long long n) {
+  const float alpha = __ldg(alpha_ptr);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = alpha * a[i] + (1.f - alpha) * b[i];
 }
@@ -711,7 +713,8 @@ int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, in
   return 0;
 }
 
-int hpvg_lerp(const float* a, const float* b, float* out, float alpha, long long numel, void* stream) {
+int hpvg_lerp(const float* a, const float* b, float* out, const float* alpha, long long numel, void* stream) {
+  HPVG_CHECK_ARG(alpha != nullptr, "lerp: alpha must point to a device float");
   lerp_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(a, b, out, alpha, numel);
   HPVG_CHECK_LAUNCH("lerp");
   return 0;

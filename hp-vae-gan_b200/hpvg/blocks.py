@@ -232,12 +232,12 @@ def make_family(dims):
                 _check_device(video)
                 mu_w, logvar_w = self.encode.run(as5d(video).contiguous())
                 mu5, logvar5 = ops.ToThin.apply(mu_w), ops.ToThin.apply(logvar_w)
+                mu, logvar = like_input(mu5, dims), like_input(logvar5, dims)
                 if self.training:
-                    eps = images.generate_noise(ref=mu5)           # same draw as reparameterize (reference :31-32)
+                    eps = as5d(images.generate_noise(ref=mu))      # same draw as reparameterize (reference :31-32)
                     z = ops.Reparam.apply(mu_w, logvar_w, eps)
                 else:
-                    z = ops.ToWide.apply(images.generate_noise(ref=mu5))
-                mu, logvar = like_input(mu5, dims), like_input(logvar5, dims)
+                    z = ops.ToWide.apply(as5d(images.generate_noise(ref=mu)))
             else:
                 _check_device(noise_init)
                 z = ops.ToWide.apply(as5d(noise_init).contiguous())
@@ -264,7 +264,7 @@ def make_family(dims):
                 x_up = images.resize(x5, size)
                 # 3-D adds noise only from the first GAN level on; 2-D adds it at every level (networks_2d.py:261-263)
                 if mode == 'rand' and (dims == 2 or opt.vae_levels <= idx + 1):
-                    noise = images.generate_noise(ref=x_up)
+                    noise = as5d(images.generate_noise(ref=like_input(x_up, dims)))
                     x_in = images.resize(x5, size, noise=noise, amp=float(noise_amp[idx + 1]))
                 else:
                     x_in = x_up

@@ -470,12 +470,42 @@ class ToThin(Function):
         return ToWide.apply(g.contiguous())
 
 
+class _GpAlpha:
+    """The WGAN-GP mixing coefficient: ONE scalar per call drawn from torch's CPU generator (reference modules/utils.py:5),
+    handed to the kernels through a device float.  In eager mode every call draws; under CUDA-graph capture/replay
+    (hpvg.train.ScaleTrainer.capture) the owner sets `external` and calls draw() itself before each replay, so the captured
+    lerp kernel reads a fresh value."""
+    external = False
+    tensors = {}
+
+    @classmethod
+    def tensor(cls, device):
+        key = (device.type, device.index)
+        t = cls.tensors.get(key)
+        if t is None:
+            t = cls.tensors[key] = torch.zeros(1, dtype=torch.float32, device=device)
+        return t
+
+    @classmethod
+    def draw(cls, device):
+        t = cls.tensor(device)
+        t.fill_(float(torch.rand(1, 1)))     # scalar travels as a kernel argument: no host buffer to race with
+        return t
+
+
+def gp_alpha(device):
+    device = torch.device(device) if not isinstance(device, torch.device) else device
+    if device.index is None:
+        device = torch.device(device.type, torch.cuda.current_device())
+    return _GpAlpha.tensor(device) if _GpAlpha.external else _GpAlpha.draw(device)
+
+
 def lerp(a, b, alpha):
-    """alpha*a + (1-alpha)*b on thin tensors, no autograd (the GP interpolates are a detached leaf)."""
-    _require_cuda(a, b)
+    """alpha*a + (1-alpha)*b on thin tensors, no autograd (the GP interpolates are a detached leaf); alpha is a device float"""
+    _require_cuda(a, b, alpha)
     a, b = a.detach().contiguous(), b.detach().contiguous()
     out = torch.empty_like(a)
-    lib.call("hpvg_lerp", _ptr(a), _ptr(b), _ptr(out), float(alpha), a.numel(), _stream())
+    lib.call("hpvg_lerp", _ptr(a), _ptr(b), _ptr(out), _ptr(alpha), a.numel(), _stream())
     return out
 
 

@@ -14,7 +14,7 @@ takes the same Adam step.  BatchNorm statistics stay per rank, as under the refe
 import torch
 import torch.nn.functional as F
 
-from . import images
+from . import images, ops
 
 
 def _train_defaults(opt):
@@ -82,18 +82,24 @@ class GradBucket:
 class ScaleTrainer:
     """state of one `train(opt, netG)` call of the reference: optimizers and the iteration body"""
 
-    def __init__(self, opt, netG, netD=None, distributed=False, dims=3):
+    def __init__(self, opt, netG, netD=None, distributed=False, dims=3, capturable=False):
+        """capturable=True builds the Adam optimizers with device-side step counters (torch's `capturable` flag: same
+        arithmetic), which capture() needs to record the whole iteration into one CUDA graph."""
         _train_defaults(opt)
         self.opt, self.netG, self.netD, self.dims = opt, netG, netD, dims
         self.gan = opt.vae_levels < opt.scale_idx + 1
         if self.gan and netD is None:
             raise ValueError("scale %d is a GAN scale (vae_levels=%d): a discriminator is required" % (opt.scale_idx, opt.vae_levels))
-        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999))
-        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999)) if self.gan else None
+        self.capturable = capturable
+        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999),
+                                           capturable=capturable)
+        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999),
+                                           capturable=capturable) if self.gan else None
         self.distributed = distributed
         self.bucketG, self.bucketD = GradBucket(), GradBucket()
         self.allreduce_bytes = 0
         self.iterations = 0
+        self.graph = None
 
     # train_video.py:126 — drawn every iteration, also at VAE scales where it is unused (keeps the RNG stream aligned)
     def _noise_init(self, device):
@@ -161,6 +167,48 @@ class ScaleTrainer:
         out['total_loss'] = total_loss.detach()
         self.iterations += 1
         return out
+
+
+    # -----------------------------------------------------------------------------------------------------------
+    # whole-iteration CUDA graph: shapes are static within a scale, so the ~1 200 kernel launches of one
+    # iteration (libhpvg kernels, autograd glue, clipping, both Adam steps, the NCCL all-reduces in the multi-GPU
+    # mode) are recorded once and replayed with a single launch.  Same kernels, same arithmetic as iteration().
+    # -----------------------------------------------------------------------------------------------------------
+    def capture(self, real, real_zero, warmup=3):
+        """Record one iteration on static copies of (real, real_zero).  Runs `warmup` eager iterations first (the first
+        one computes this scale's noise amplitude on the host, which must happen before recording)."""
+        if not self.capturable:
+            raise RuntimeError("ScaleTrainer(capturable=True) is required to capture the iteration into a CUDA graph")
+        self.static_real, self.static_real_zero = real.clone(), real_zero.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.iteration(self.static_real, self.static_real_zero)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        ops._GpAlpha.external = True
+        try:
+            with torch.cuda.graph(self.graph):
+                self.static_out = self.iteration(self.static_real, self.static_real_zero)
+        finally:
+            ops._GpAlpha.external = False
+        self.iterations -= 1          # the recording pass executed nothing
+        return self.static_out
+
+    def replay(self, real=None, real_zero=None):
+        """one iteration through the recorded graph; new data (device or pinned host tensors) is copied into the static
+        input buffers on the current stream first"""
+        if real is not None:
+            self.static_real.copy_(real, non_blocking=True)
+        if real_zero is not None:
+            self.static_real_zero.copy_(real_zero, non_blocking=True)
+        if self.gan:
+            ops._GpAlpha.draw(self.static_real.device)     # the reference's per-iteration CPU draw of the GP alpha
+        self.graph.replay()
+        self.iterations += 1
+        return self.static_out
 
 
 @torch.no_grad()

@@ -10,10 +10,10 @@ def calc_gradient_penalty(netD, real_data, fake_data, LAMBDA, device):
     detached leaf, critic gradient w.r.t. them with create_graph=True, channel-axis L2 norm per voxel.
     The first-order sweep asks only for d/d(interpolates); the double backward is composed of the same
     fprop/dgrad/wgrad kernels by hpvg.ops."""
-    alpha = float(torch.rand(1, 1).item())          # same CPU-generator draw as the reference (:5)
+    alpha = _ops.gp_alpha(real_data.device)         # same CPU-generator draw as the reference (:5), as a device float
     interpolates = _ops.lerp(real_data, fake_data, alpha).requires_grad_(True)
     disc_interpolates = netD(interpolates)
-    ones = torch.ones(disc_interpolates.size()).to(device)
+    ones = torch.ones(disc_interpolates.size(), device=disc_interpolates.device)
     with _ops.input_grad_only():
         gradients = torch.autograd.grad(outputs=disc_interpolates, inputs=interpolates, grad_outputs=ones,
                                         create_graph=True, retain_graph=True, only_inputs=True)[0]

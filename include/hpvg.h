@@ -162,8 +162,9 @@ int hpvg_gp_penalty_bwd(const float* gout, const float* g, float* gg, int N, int
 int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, int N, int C, long long spatial,
                         void* stream);
 
-/* out = alpha*a + (1-alpha)*b on float32 (the GP interpolates, modules/utils.py:9) */
-int hpvg_lerp(const float* a, const float* b, float* out, float alpha, long long numel, void* stream);
+/* out = alpha*a + (1-alpha)*b on float32 (the GP interpolates, modules/utils.py:9); alpha is read from device memory
+ * so that a captured CUDA graph sees a fresh value at every replay */
+int hpvg_lerp(const float* a, const float* b, float* out, const float* alpha, long long numel, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Spectral normalisation, one power iteration (nn.utils.spectral_norm as used by ConvBlock3DSN/2DSN,

@@ -17,6 +17,14 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2
+# Input gradients that pass through a LeakyReLU whose pre-activation is stored in bf16: the derivative (0.2 | 1) is read
+# from the sign of the STORED value, so it differs from the fp32 reference wherever rounding moved a pre-activation across
+# zero (about 0.3 % of the elements for a BatchNorm output with |mean| ~ std; each such element is off by 0.8 |g|, i.e.
+# sqrt(0.003) * 0.8 = 4e-2 in relative L2; the weight gradient of the layer consumes the same masked tensor).  Forward
+# tensors and the gradients of activation-free layers meet BF16_TOL; for gradients behind a LeakyReLU the bar against fp32 is
+# LRELU_GRAD_TOL, and the bar against the oracle's bf16 storage emulation — which
+# stores the same values and therefore reads the same signs — is EMU_BWD_TOL.
+LRELU_GRAD_TOL = 5e-2
 F32_TOL = 1e-3
 EMU_FWD_TOL = 5e-4     # one layer vs the oracle with bf16 storage emulation: what is left is fp32 summation order
 EMU_BWD_TOL = 3e-3
@@ -35,7 +43,19 @@ def _leafs(sd):
     return sd
 
 
-def _compare_grads(module, sd, prefix=''):
+def _run_block(m, x_gpu):
+    """a block as the networks chain it: 64/128-channel inputs arrive as bf16 NDHWC tensors from the previous block (the
+    module's own forward(), which takes float32 NCDHW, is the reference-API entry used for 3-channel inputs)"""
+    from hpvg import ops
+    if x_gpu.shape[1] >= 64:
+        x5 = x_gpu.unsqueeze(2) if x_gpu.dim() == 4 else x_gpu
+        y = ops.ToThin.apply(m.run(ops.ToWide.apply(x5)))
+        return y.squeeze(2) if x_gpu.dim() == 4 else y
+    return m(x_gpu)
+
+
+def _compare_grads(module, sd, tol=None, prefix=''):
+    tol = LRELU_GRAD_TOL if tol is None else tol
     worst = 0.0
     big = max(v.grad.norm().item() for v in sd.values() if v.is_floating_point() and v.grad is not None)
     for k, p in module.named_parameters():
@@ -43,7 +63,7 @@ def _compare_grads(module, sd, prefix=''):
         assert p.grad is not None and ref is not None, k
         d = (p.grad.detach().cpu().double() - ref.double()).norm().item()
         # a conv bias in front of BatchNorm has a mathematically zero gradient: absolute floor
-        assert d <= BF16_TOL * ref.double().norm().item() + 2e-3 * big, (k, d, ref.norm().item())
+        assert d <= tol * ref.double().norm().item() + 2e-3 * big, (k, d, ref.norm().item())
         worst = max(worst, d / (ref.double().norm().item() + 2e-3 * big))
     return worst
 
@@ -65,11 +85,11 @@ def test_convblock3d_layer(cin, cout, shape):
     y_ref = port.conv_block(sd, '', x_ref, 1)
     y_ref.backward(g)
     x_gpu = x.cuda().requires_grad_(True)
-    y = m(x_gpu)
+    y = _run_block(m, x_gpu)
     assert y.shape == y_ref.shape and y.dtype == torch.float32
     assert rel_err(y, y_ref) < BF16_TOL
     y.backward(g.cuda())
-    assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
+    assert rel_err(x_gpu.grad, x_ref.grad) < LRELU_GRAD_TOL
     _compare_grads(m, sd)
     for k in ('norm.running_mean', 'norm.running_var'):
         assert rel_err(dict(m.named_buffers())[k], sd[k]) < 1e-3, k
@@ -103,10 +123,10 @@ def test_convblock3dsn_layer(cin, shape):
     y_ref = port.conv_block_sn(sd, '', x_ref, 1)
     y_ref.backward(g)
     x_gpu = x.cuda().requires_grad_(True)
-    y = m(x_gpu)
+    y = _run_block(m, x_gpu)
     assert rel_err(y, y_ref) < BF16_TOL
     y.backward(g.cuda())
-    assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
+    assert rel_err(x_gpu.grad, x_ref.grad) < LRELU_GRAD_TOL
     _compare_grads(m, sd)
     bufs = dict(m.named_buffers())
     assert rel_err(bufs['conv.weight_u'], sd['conv.weight_u']) < 1e-4
@@ -130,12 +150,12 @@ def test_convblock2d_and_bare_heads(dims):
         y_ref = port.conv_block(sd, '', x_ref, 1)
         y_ref.backward(g)
         x_gpu = x.cuda().requires_grad_(True)
-        y = m(x_gpu)
+        y = _run_block(m, x_gpu)
         assert y.shape == y_ref.shape
         assert rel_err(y, y_ref) < BF16_TOL
         y.backward(g.cuda())
-        assert rel_err(x_gpu.grad, x_ref.grad) < BF16_TOL
-        _compare_grads(m, sd)
+        assert rel_err(x_gpu.grad, x_ref.grad) < (LRELU_GRAD_TOL if act else BF16_TOL)
+        _compare_grads(m, sd, LRELU_GRAD_TOL if act else BF16_TOL)
 
 
 @pytest.mark.parametrize("cout,pad", [(3, 1), (1, 1), (3, 0)])
