@@ -211,6 +211,14 @@ class ScaleTrainer:
         return self.static_out
 
 
+def draws_for_rank(total, world, rank):
+    """how the independent noise draws of diverse-sample generation split over ranks: contiguous, sizes differ by <= 1"""
+    base, extra = divmod(int(total), int(world))
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
 @torch.no_grad()
 def generate(netG, opt, n_samples, device, batch=1):
     """the reference's sampling path (train_video.py:226-235): fresh z per draw, G(z, amps, noise_init=z, mode='rand').

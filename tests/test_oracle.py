@@ -142,3 +142,40 @@ def test_training_loop_matches_reference(golden, name):
     assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) < 1e-4 * abs(fx['noise_amps_after'][-1])
     key = ('body.%d.tail.weight' % (fx['stages'] - 1)) if fx['stages'] > 0 else 'decoder.tail.weight'
     assert rel_err(sd_g[key], fx['final_tail_weight']) < 1e-3
+
+
+def test_numpy_primitives_match_torch():
+    """oracle/np_ops.py (independent float64 numpy definitions) against the torch CPU operators oracle/port.py calls"""
+    import numpy as np
+    from oracle import np_ops
+    x = port.det_tensor((2, 3, 4, 6, 5), 61).double()
+    w = port.det_tensor((5, 3, 3, 3, 3), 62, scale=0.3).double()
+    b = port.det_tensor((5,), 63).double()
+    for pad in (0, 1, 2):
+        assert np.allclose(np_ops.conv_nd(x.numpy(), w.numpy(), b.numpy(), pad), F.conv3d(x, w, b, padding=pad).numpy(), atol=1e-10)
+    x2, w2 = x[:, :, 0], w[:, :, 0]
+    assert np.allclose(np_ops.conv_nd(x2.numpy(), w2.numpy(), None, 1), F.conv2d(x2, w2, None, padding=1).numpy(), atol=1e-10)
+    y = F.conv3d(x, w, b, padding=1)
+    gamma, beta = port.det_tensor((5,), 64).double() + 1.5, port.det_tensor((5,), 65).double()
+    sd = {'weight': gamma, 'bias': beta, 'running_mean': torch.zeros(5).double(), 'running_var': torch.ones(5).double(),
+          'num_batches_tracked': torch.zeros((), dtype=torch.int64)}
+    out_t = port.batch_norm_train(sd, '', y)
+    out_n, mean, var_unbiased = np_ops.batch_norm_train(y.numpy(), gamma.numpy(), beta.numpy())
+    assert np.allclose(out_n, out_t.numpy(), atol=1e-9)
+    assert np.allclose(sd['running_mean'].numpy(), 0.1 * mean, atol=1e-12)
+    assert np.allclose(sd['running_var'].numpy(), 0.9 + 0.1 * var_unbiased, atol=1e-12)
+    assert np.allclose(np_ops.leaky_relu(y.numpy()), F.leaky_relu(y, 0.2).numpy())
+    for size in ((4, 8, 7), (9, 3, 11), (1, 6, 5)):
+        assert np.allclose(np_ops.resize_linear(x.numpy(), size), port.resize(x, size).numpy(), atol=1e-12)
+    assert np.allclose(np_ops.resize_linear(x2.numpy(), (9, 4)), port.resize(x2, (9, 4)).numpy(), atol=1e-12)
+    u = port.det_tensor((5,), 66).double()
+    u = u / u.norm()
+    sdw = {'weight_orig': w.clone(), 'weight_u': u.clone(), 'weight_v': torch.zeros(81).double()}
+    w_sn = port.spectral_weight(sdw, '')
+    w_np, u_np, v_np = np_ops.spectral_norm_step(w.numpy(), u.numpy())
+    assert np.allclose(w_np, w_sn.numpy(), atol=1e-10) and np.allclose(u_np, sdw['weight_u'].numpy(), atol=1e-10)
+    assert np.allclose(v_np, sdw['weight_v'].numpy(), atol=1e-10)
+    mu, lv = port.det_tensor((2, 4, 3, 3), 67).double(), port.det_tensor((2, 4, 3, 3), 68).double()
+    assert abs(np_ops.kl(mu.numpy(), lv.numpy()) - port.kl_criterion(mu, lv).item()) < 1e-12
+    g = port.det_tensor((2, 3, 2, 4, 4), 69).double()
+    assert abs(np_ops.gp_penalty(g.numpy(), 0.1) - (((g.norm(2, dim=1) - 1) ** 2).mean() * 0.1).item()) < 1e-12
