@@ -280,6 +280,9 @@ def run_hpvg(args):
     prof_steps = min(args.steps, 3)
 
     def step_eager():
+        # keep the GPU busy while the host enqueues the iteration, so that the event pairs bracket back-to-back kernels
+        # and not host launch latency (eager launching is CPU-bound on this workload)
+        torch.cuda._sleep(int(0.12 * 1.9e9))
         trainer.iteration(real, real_zero)
     lib.profile_enable(True)
     ms_prof = timed(step_eager, prof_steps)
@@ -287,12 +290,17 @@ def run_hpvg(args):
     rows = lib.profile_dump()
 
     # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
-    draws_rank = max(1, args.draws // world)
-    train.generate(G, o, 2, dev)
+    _, draws_rank = train.draws_for_rank(args.draws, world, rank)
+    draws_rank = max(1, draws_rank)
+    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph)
     frames = [0]
 
     def gen_all():
-        frames[0], _ = train.generate(G, o, draws_rank, dev)
+        n = 0
+        for _ in range(draws_rank):
+            n += sampler.frames_per_call(sampler.sample())
+        frames[0] = n
+    gen_all()
     ms_gen = timed(gen_all, 1)
 
     if rank == 0:
@@ -320,11 +328,12 @@ def run_hpvg(args):
                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                         "flops_per_launch": top["work"], "us_per_launch": per_launch_ms * 1e3, "launches_timed": top["launches"],
                         "peak_source": peak_src,
-                        "share_of_step": top["ms"] / prof_steps / (ms_prof / prof_steps),
+                        "share_of_step": (top["ms"] / prof_steps) / (ms / args.steps),
                         "by_kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in by_kind.items()},
                         "by_kernel_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None) for k, v in by_kind.items()},
-                        "ms_per_step_with_events": ms_prof / prof_steps,
-                        "note": "per-launch CUDA events need eager launches: this leg runs the same iteration un-graphed"}
+                        "note": "per-launch CUDA events need eager launches: this leg runs the same iteration un-graphed behind a "
+                                "GPU-side delay so that launches are queued ahead of the GPU; share_of_step = kernel ms per "
+                                "iteration / graph-replay ms per iteration"}
         value = world * args.steps / (ms * 1e-3)
         e2e = world * args.steps / (ms_e2e * 1e-3)
         bi = (real_h.numel() + real_zero_h.numel()) * 4
@@ -340,8 +349,9 @@ def run_hpvg(args):
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops": value * CONV_GFLOP_PER_ITER / 1e3 / world,
                 "generation": {"metric": "generated_frames_per_s", "value": world * frames[0] / (ms_gen * 1e-3), "unit": "frames/s",
-                               "draws": draws_rank * world, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
-                               "ms_per_draw": ms_gen / draws_rank}}
+                               "draws": args.draws, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
+                               "ms_per_draw": ms_gen / draws_rank,
+                               "note": "draws split over ranks, no collective; rank 0's share timed x N (equal shares)"}}
         if distributed:
             line["allreduce_bytes_per_step"] = trainer.allreduce_bytes // max(1, trainer.iterations)
         if world == 1 and not args.no_cpu_baseline:
@@ -361,7 +371,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
-    ap.add_argument("--draws", type=int, default=64, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
+    ap.add_argument("--draws", type=int, default=256, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
     args = ap.parse_args()

@@ -87,7 +87,7 @@ if which == "clk":
         print("rep", rep, "per-CTA clocks [mma loop, wait weights, wait slabs, epilogue total, epilogue wait acc]")
         for b in (0, 1, 64, 127):
             print("  cta", b, d[b, :5].tolist())
-        print("  mean", d[:128, :5].float().mean(0).tolist())
+        print("  mean", [int(v) for v in d[:128, :8].float().mean(0).tolist()])
     print("thin 64->3")
     packed_t = ops.pack_weights(w_tail, 3, 64, 27, False, rows=16)
     b3 = torch.zeros(3, device=dev)

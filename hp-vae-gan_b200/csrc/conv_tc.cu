@@ -19,6 +19,7 @@
 //    clipping at the tensor edge, plus per-channel sum / sum-of-squares for BatchNorm).
 #include "common.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace hpvg {
 
@@ -36,13 +37,19 @@ constexpr int NMMA = 1;                             // MMA-issuing warps: one el
 // KCHUNKS: input channels / 64.  NACC: output d-slices (accumulators) per unit.  NGRP: accumulator groups per unit;
 // the 27 weight taps are streamed once per group, so the epilogue of group i overlaps the MMAs of group i+1.
 // NOUT: MMA N = output channels per accumulator: 64 (wide output) or 16 (thin output, Cout <= 16 zero-padded).
-template <int KCHUNKS, int NACC, int NGRP, int NOUT>
+// STACK (3-D, Cin = 64 only): one weight-ring stage holds the three kd tiles of a (kh, kw) position, and one MMA with
+// N = 3 * NOUT multiplies a slab view with all three of them at once — the accumulators are laid out in TMEM in
+// descending slice order, so the three results land in the three accumulators that input slice feeds.  Reading the A
+// operand (128 x 16 bf16 = 4 KB at 128 B/clk) is what bounds an N = 64 MMA; stacking amortises it over 3x the work.
+template <int KCHUNKS, int NACC, int NGRP, int NOUT, bool STACK = false>
 struct TcCfg {
   static constexpr bool THIN = NOUT < 64;
   static constexpr int NSLOTS = NACC + 2;                       // d-slices resident per unit (3-D, pad 1)
   static constexpr int NSLAB = NSLOTS * KCHUNKS;
   static constexpr int BTILE_BYTES = NOUT * 128;                // one tap: NOUT output channels x 64 input channels bf16
-  static constexpr int NB = THIN ? 8 : ((KCHUNKS == 1) ? 6 : 3);   // weight ring depth
+  static constexpr int STAGE_TILES = STACK ? 3 : 1;
+  static constexpr int STAGE_BYTES = STAGE_TILES * BTILE_BYTES;
+  static constexpr int NB = STACK ? (THIN ? 4 : 2) : (THIN ? 8 : ((KCHUNKS == 1) ? 6 : 3));   // weight ring depth (stages)
   static constexpr int NSTG = THIN ? 0 : ((KCHUNKS == 1) ? 2 : 1); // output staging buffers
   static constexpr int NEPI = THIN ? NEPI_THIN : NEPI_WIDE;
   static constexpr int THREADS = 32 * (1 + NMMA) + 32 * NEPI;
@@ -51,12 +58,13 @@ struct TcCfg {
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static constexpr int OFF_SLAB = 0;
   static constexpr int OFF_B = OFF_SLAB + NSLAB * SLAB_STRIDE;
-  static constexpr int OFF_STG = OFF_B + NB * BTILE_BYTES;
+  static constexpr int OFF_STG = OFF_B + NB * STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_STG + NSTG * STG_BYTES;          // float[MAX_COUT]
   static constexpr int OFF_BAR = OFF_BIAS + MAX_COUT * 4;
   static constexpr int NBARS = NSLAB + 2 * NB + 3;
   static constexpr int SMEM_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
   static_assert(NACC % NGRP == 0, "groups must divide the accumulators");
+  static_assert(!STACK || (KCHUNKS == 1 && NGRP == 1), "kd stacking is implemented for Cin = 64, one group");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -73,11 +81,14 @@ struct TcParams {
   long long* dbg;   // optional per-CTA phase clocks (development aid, hpvg_debug_set_clock_buffer)
 };
 
-template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT>
-__global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT>::THREADS), 1)
+template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK>
+__global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const TcParams p) {
-  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT>;
+  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
+  static_assert(!STACK || KDT == 3, "kd stacking needs a 3-deep kernel");
+  // accumulator a lives at TMEM columns (NACC - 1 - a) * NOUT: descending slice order (see STACK)
+  auto acc_col = [](int a) { return (uint32_t)((NACC - 1 - a) * NOUT); };
   constexpr int GACC = NACC / NGRP;            // accumulators per group
   constexpr int NEPI_THREADS = 32 * Cfg::NEPI;
   extern __shared__ uint8_t smem_raw[];
@@ -144,6 +155,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int nb, n, d0, h0, w0;
         decode(u, nb, n, d0, h0, w0);
         if (it > 0) mbar_wait(bar_slabs_free, (uint32_t)((it - 1) & 1));
+        int q_first = 0;
+        if (STACK) {
+          // the first weight stage goes out BEFORE the slabs: it is small and L2-resident, and the first MMAs need it
+          // together with slab 0 — behind 138 KB of slab traffic it arrived ~2 us late
+          mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
+          mbar_expect_tx(bar_b_full(bstage), Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+            tma_load_2d(s_b + bstage * Cfg::STAGE_BYTES + kd * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), 0,
+                        (kd * 9 + 0) * p.nblocks * NOUT + nb * NOUT);
+          if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+          q_first = 1;
+        }
 #pragma unroll
         for (int j = 0; j < NACC + KDT - 1; ++j) {
           const int d = d0 + j - g.pad_d;
@@ -163,16 +187,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tma_load_5d(s_slab + si * SLAB_STRIDE, &tmap_x, bar_slab_full(si), kc * 64, w0 - g.pad, h0 - g.pad, d, n);
           }
         }
+        if (STACK) {
 #pragma unroll 1
-        for (int grp = 0; grp < NGRP; ++grp) {
-#pragma unroll 1
-          for (int t = 0; t < KDT * 9; ++t) {
+          for (int q = q_first; q < 9; ++q) {       // one stage = the kd = 0, 1, 2 tiles of position q = kh * 3 + kw
+            mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
+            mbar_expect_tx(bar_b_full(bstage), Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int kc = 0; kc < KCHUNKS; ++kc) {
-              mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
-              mbar_expect_tx(bar_b_full(bstage), Cfg::BTILE_BYTES);
-              tma_load_2d(s_b + bstage * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), kc * 64, t * p.nblocks * NOUT + nb * NOUT);
-              if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+            for (int kd = 0; kd < 3; ++kd)
+              tma_load_2d(s_b + bstage * Cfg::STAGE_BYTES + kd * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), 0,
+                          (kd * 9 + q) * p.nblocks * NOUT + nb * NOUT);
+            if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+          }
+        } else {
+#pragma unroll 1
+          for (int grp = 0; grp < NGRP; ++grp) {
+#pragma unroll 1
+            for (int t = 0; t < KDT * 9; ++t) {
+#pragma unroll
+              for (int kc = 0; kc < KCHUNKS; ++kc) {
+                mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
+                mbar_expect_tx(bar_b_full(bstage), Cfg::BTILE_BYTES);
+                tma_load_2d(s_b + bstage * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), kc * 64, t * p.nblocks * NOUT + nb * NOUT);
+                if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+              }
             }
           }
         }
@@ -204,6 +241,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           tc_fence_after();
         }
         uint32_t touched = 0, waited = 0;
+        if (STACK) {
+          // per input slot j, the kd range whose accumulators a = j - kd exist.  For a full unit (all NACC output slices
+          // inside the volume) the ranges are compile-time constants and only the presence of a slab (zero padding at the
+          // volume faces) is a run-time bit, so every descriptor below folds to base + constant; partial units take the
+          // same code with run-time ranges (FULL = false).
+          const int amax = min(NACC, g.Do - d0);
+          uint32_t svalid = 0;
+#pragma unroll
+          for (int j = 0; j < NACC + 2; ++j) {
+            const int d = d0 + j - g.pad_d;
+            if (d >= 0 && d < g.Di) svalid |= 1u << j;
+          }
+          auto run = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+              const int kh = q / 3, kw = q % 3;
+              if (p.dbg) t_bwait -= clock64();
+              mbar_wait(bar_b_full(bstage), bphase);
+              if (p.dbg) t_bwait += clock64();
+              tc_fence_after();
+              const uint64_t bs = b_base + (uint64_t)((bstage * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int j = 0; j < NACC + 2; ++j) {
+                  const int a_lo = j - 2 > 0 ? j - 2 : 0;
+                  const int a_hi = FULL ? (j < NACC - 1 ? j : NACC - 1) : min(j, amax - 1);
+                  const int klo = j - a_hi, n = a_hi - a_lo + 1;
+                  if (n <= 0 || !((svalid >> j) & 1u)) continue;
+                  const uint64_t ad = a_base + (uint64_t)((j * SLAB_STRIDE + (kh * SLAB_W + kw) * 128 + ks * 32) >> 4);
+                  if (q == 0 && ks == 0) {
+                    // first touch: one MMA per accumulator so that each gets its own "overwrite" flag
+                    if (p.dbg) t_swait -= clock64();
+                    mbar_wait(bar_slab_full(j), (uint32_t)(it & 1));
+                    if (p.dbg) t_swait += clock64();
+                    tc_fence_after();
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                      if (kd < klo || kd >= klo + n) continue;
+                      const int a = j - kd;
+                      umma_bf16(tmem_base + acc_col(a), ad, bs + (uint64_t)((kd * Cfg::BTILE_BYTES) >> 4), IDESC, (touched >> a) & 1u);
+                      touched |= 1u << a;
+                    }
+                  } else {
+                    const uint64_t bd = bs + (uint64_t)((klo * Cfg::BTILE_BYTES + ks * 32) >> 4);
+                    const uint32_t tacc = tmem_base + acc_col(j - klo);
+                    if (n == 3)
+                      umma_bf16_acc(tacc, ad, bd, umma_idesc_bf16(128, 3 * NOUT, 0, 0));
+                    else if (n == 2)
+                      umma_bf16_acc(tacc, ad, bd, umma_idesc_bf16(128, 2 * NOUT, 0, 0));
+                    else
+                      umma_bf16_acc(tacc, ad, bd, IDESC);
+                  }
+                }
+              }
+              umma_commit(bar_b_empty(bstage));
+              if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+            }
+          };
+          if (amax == NACC)
+            run(std::true_type{});
+          else
+            run(std::false_type{});
+          umma_commit(bar_acc_full);
+          umma_commit(bar_slabs_free);
+          continue;
+        }
 #pragma unroll
         for (int grp = 0; grp < NGRP; ++grp) {
 #pragma unroll
@@ -251,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
                   if (!((amask >> a) & 1u)) continue;
                   const uint64_t ad = a_base + (uint64_t)((((a + kd) * KCHUNKS + kc) * SLAB_STRIDE + (kh * SLAB_W + kw) * 128) >> 4);
-                  const uint32_t tacc = tmem_base + a * NOUT;
+                  const uint32_t tacc = tmem_base + acc_col(a);
                   umma_bf16(tacc, ad, bd, IDESC, (touched >> a) & 1u);
                   umma_bf16_acc(tacc, ad + 2, bd + 2, IDESC);
                   umma_bf16_acc(tacc, ad + 4, bd + 4, IDESC);
@@ -275,21 +380,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
     __syncwarp();
   } else if (!Cfg::THIN) {
-    // ===================== epilogue, wide output (8 warps: TMEM lane quadrant = warp & 3, column half = (warp - 2) / 4) ==========
-    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
-    const int ch = (warp - Cfg::EPI_WARP0) >> 2;   // which 32 of the 64 accumulator columns
-    const int m = q * 32 + lane;             // accumulator row = brick voxel (hh = m / 8, ww = m % 8)
-    const int et = threadIdx.x - 32 * Cfg::EPI_WARP0;   // 0..255 index inside the epilogue group
+    // ===================== epilogue, wide output: NEPI warps, TMEM lane quadrant = warp & 3, CPT columns per thread ==========
+    // Measured (bench_kernels.py clk): of the ~6.5 k cycles after the last MMA about half is this chain and half the
+    // drain of the final TMA stores to HBM; 16 warps x 16 columns was not faster than 8 x 32.
+    constexpr int CPT = 64 / (Cfg::NEPI / 4);                 // accumulator columns per thread (16 or 32)
+    constexpr int RPT = 128 / (NEPI_THREADS / 64);            // rows per thread in the BatchNorm-sum pass
+    const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+    const int ch = (warp - Cfg::EPI_WARP0) >> 2;              // which CPT-wide column group
+    const int m = q * 32 + lane;                              // accumulator row = brick voxel (hh = m / 8, ww = m % 8)
+    const int et = threadIdx.x - 32 * Cfg::EPI_WARP0;         // index inside the epilogue group
     int it = 0;
     int stg = 0;
     uint32_t full_phase = 0;
-    long long t_start = clock64(), t_accwait = 0;
+    long long t_start = clock64(), t_accwait = 0, t_ld = 0, t_bar = 0, t_stat = 0;
     for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
       int nb, n, d0, h0, w0;
       decode(u, nb, n, d0, h0, w0);
       const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
       const bool row_ok = (oh < g.Ho) && (ow < g.Wo);
-      float st_s = 0.f, st_s2 = 0.f;     // BatchNorm sums of this unit: channel (et & 63), rows of quarter (et >> 6)
+      const bool brick_full = (h0 + BH <= g.Ho) && (w0 + BW <= g.Wo);
+      float st_s = 0.f, st_s2 = 0.f;     // BatchNorm sums of this unit: channel (et & 63), row group (et >> 6)
 #pragma unroll 1
       for (int grp = 0; grp < NGRP; ++grp) {
         long long tq = clock64();
@@ -301,25 +411,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
           const int od = d0 + a;
           if (od >= g.Do) break;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + ch * 32, r);
+          uint32_t r[CPT];
+          if (p.dbg) t_ld -= clock64();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col(a) + ch * CPT;
+          if (CPT == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
           tmem_ld_wait();
-          float v[32];
+          if (p.dbg) t_ld += clock64();
+          float v[CPT];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < CPT; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nb * 64 + ch * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + nb * 64 + ch * CPT);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CPT / 4; ++j) {
               const float4 bq = b4[j];
               v[4 * j + 0] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
             }
           }
           if (p.mask_src && row_ok) {
             const uint4* mp = reinterpret_cast<const uint4*>(
-                p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64 + ch * 32);
+                p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64 + ch * CPT);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CPT / 8; ++c) {
               uint4 mv = __ldg(mp + c);
               float2 f;
               f = unpack_bf16x2(mv.x); v[8 * c + 0] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 1] *= f.y > 0.f ? 1.f : p.slope;
@@ -330,37 +443,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           if (p.act == HPVG_ACT_LRELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+            for (int j = 0; j < CPT; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);     // slope in (0, 1): max(x, slope * x)
           }
-          if (!row_ok) {
+          if (!brick_full && !row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int j = 0; j < CPT; ++j) v[j] = 0.f;
           }
           // staging buffer must be free: the thread that issued its last TMA store waits for the read to finish
+          if (p.dbg) t_bar -= clock64();
           if (et == 0) tma_store_wait_read<Cfg::NSTG - 1>();
           asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+          if (p.dbg) t_bar += clock64();
           const uint32_t sdst = s_stg + stg * STG_BYTES + m * 128;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t addr = sdst + ((uint32_t)((ch * 4 + c) ^ (m & 7)) << 4);
+          for (int c = 0; c < CPT / 8; ++c) {
+            const uint32_t addr = sdst + ((uint32_t)((ch * (CPT / 8) + c) ^ (m & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[8 * c + 0], v[8 * c + 1])),
                          "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
                          "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7]))
                          : "memory");
           }
           fence_proxy_async();
+          if (p.dbg) t_bar -= clock64();
           asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+          if (p.dbg) t_bar += clock64();
           if (et == 0) {
             tma_store_5d(&tmap_y, s_stg + stg * STG_BYTES, nb * 64, w0, h0, od, n);
             tma_store_commit();
           }
+          if (p.dbg) t_stat -= clock64();
           if (p.stats) {
-            // column sums over the staged (bf16-rounded, invalid rows zeroed) tile: thread = channel, 32 rows each
-            const int c = et & 63, quarter = et >> 6;
+            // column sums over the staged (bf16-rounded, invalid rows zeroed) tile: thread = channel, RPT rows each
+            const int c = et & 63, rg = et >> 6;
             const uint8_t* tile = sgen + Cfg::OFF_STG + stg * STG_BYTES;
-#pragma unroll 16
-            for (int rr = 0; rr < 32; ++rr) {
-              const int row = quarter * 32 + rr;
+#pragma unroll
+            for (int rr = 0; rr < RPT; ++rr) {
+              const int row = rg * RPT + rr;
               const __nv_bfloat16 bv =
                   *reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((c >> 3) ^ (row & 7)) << 4) + (c & 7) * 2);
               const float f = bf2f(bv);
@@ -368,6 +486,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               st_s2 = fmaf(f, f, st_s2);
             }
           }
+          if (p.dbg) t_stat += clock64();
           stg = (stg + 1 == Cfg::NSTG) ? 0 : stg + 1;
         }
       }
@@ -382,6 +501,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (p.dbg && et == 0) {
       p.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;   // epilogue warps, all units
       p.dbg[blockIdx.x * 8 + 4] = t_accwait;             // of which waiting for the accumulators
+      p.dbg[blockIdx.x * 8 + 5] = t_ld;                  // TMEM loads
+      p.dbg[blockIdx.x * 8 + 6] = t_bar;                 // staging-buffer barriers
+      p.dbg[blockIdx.x * 8 + 7] = t_stat;                // BatchNorm sums
     }
   } else {
     // ===================== epilogue, thin output: float32 NCDHW, Cout <= 16, bias only =====================
@@ -405,7 +527,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const int od = d0 + a;
           if (od >= g.Do) break;
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * NOUT, r);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col(a), r);
           tmem_ld_wait();
           if (row_ok) {
             float* yp = p.y_thin + (size_t)n * g.Cout * out_sp + ((size_t)od * g.Ho + oh) * g.Wo + ow;
@@ -425,12 +547,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT>
+template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT>;
+  using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -445,7 +567,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   p.nblocks = NOUT == 64 ? g.Cout / 64 : 1;
   p.num_units = (long long)p.nblocks * g.N * p.units_d * p.units_h * p.units_w;
   const int grid = (int)min((long long)num_sms(), p.num_units);
-  conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
+  conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
   HPVG_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
 }
@@ -493,13 +615,17 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
   p.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask_src);
   p.y_thin = thin ? reinterpret_cast<float*>(y) : nullptr;
   p.dbg = debug_clock_buffer();
+  static const int variant = getenv("HPVG_TC_VARIANT") ? atoi(getenv("HPVG_TC_VARIANT")) : 0;   // tuning knob: 1 = unstacked, 2 = two groups
   if (thin) {
-    if (g.KD == 3) return launch_tc<1, 4, 3, 1, 16>(mx, mw, my, p, st);
+    if (g.KD == 3) return variant == 1 ? launch_tc<1, 4, 3, 1, 16>(mx, mw, my, p, st) : launch_tc<1, 4, 3, 1, 16, true>(mx, mw, my, p, st);
     return launch_tc<1, 4, 1, 1, 16>(mx, mw, my, p, st);
   }
-  static const int ngrp = getenv("HPVG_TC_NGRP") ? atoi(getenv("HPVG_TC_NGRP")) : 1;   // tuning knob (development aid)
   if (g.KD == 3) {
-    if (g.Cin == 64) return ngrp == 2 ? launch_tc<1, 4, 3, 2, 64>(mx, mw, my, p, st) : launch_tc<1, 4, 3, 1, 64>(mx, mw, my, p, st);
+    if (g.Cin == 64) {
+      if (variant == 1) return launch_tc<1, 4, 3, 1, 64>(mx, mw, my, p, st);
+      if (variant == 2) return launch_tc<1, 4, 3, 2, 64>(mx, mw, my, p, st);
+      return launch_tc<1, 4, 3, 1, 64, true>(mx, mw, my, p, st);
+    }
     return launch_tc<2, 2, 3, 2, 64>(mx, mw, my, p, st);
   }
   if (g.Cin == 64) return launch_tc<1, 4, 1, 2, 64>(mx, mw, my, p, st);

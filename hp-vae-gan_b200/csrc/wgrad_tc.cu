@@ -91,7 +91,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (long long b = b_begin; b < b_end; ++b) {
         int n, od, h0, w0;
@@ -105,38 +105,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);   // A and B MN-major
-    uint32_t stage = 0, phase = 0;
-    uint32_t first = 1;
-    for (long long b = b_begin; b < b_end; ++b) {
-      int n, od, h0, w0;
-      if (!decode(b, n, od, h0, w0)) continue;
-      mbar_wait(bar_full(stage), phase);
-      tc_fence_after();
-      if (lane == 0) {
+    // one elected thread issues every MMA; descriptors are precomputed bases + compile-time constants (see conv_tc.cu:
+    // a lane-id guard makes ptxas wrap each tcgen05.mma in a descriptor-broadcast loop)
+    if (elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);   // A and B MN-major
+      uint32_t stage = 0, phase = 0;
+      uint32_t first = 1;
+      for (long long b = b_begin; b < b_end; ++b) {
+        int n, od, h0, w0;
+        if (!decode(b, n, od, h0, w0)) continue;
+        mbar_wait(bar_full(stage), phase);
+        tc_fence_after();
         const uint32_t sa = sbase + stage * WG_STAGE_BYTES;
-        const uint32_t sb = sa + WG_SLAB_STRIDE;
+        const uint64_t b_base = umma_desc(sa + WG_SLAB_STRIDE, 16, 1024, 2);
 #pragma unroll
         for (int pr = 0; pr < WG_NACC; ++pr) {
           // taps q0 = 2*pr and q1 = 2*pr+1 (q = kh*3 + kw); the last pair duplicates tap 8
           const int q0 = 2 * pr, q1 = (2 * pr + 1 <= 8) ? 2 * pr + 1 : 8;
           const int off0 = (q0 / 3) * WG_SLAB_W + (q0 % 3), off1 = (q1 / 3) * WG_SLAB_W + (q1 % 3);
           const uint32_t lbo = (uint32_t)(off1 - off0) * 128u;
+          const uint64_t a_base = umma_desc(sa + (uint32_t)off0 * 128u, lbo, WG_SLAB_W * 128, 2);
+          const uint32_t tacc = tmem_base + pr * 64;
+          // K step = 16 voxels = brick rows 2ks, 2ks+1 (8 voxels each): A advances 2 slab rows, B 2048 bytes
+          umma_bf16(tacc, a_base, b_base, IDESC, first ^ 1u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            // K step = 16 voxels = brick rows 2ks, 2ks+1 (8 voxels each)
-            const uint64_t ad = umma_desc(sa + (uint32_t)(off0 + 2 * ks * WG_SLAB_W) * 128u, lbo, WG_SLAB_W * 128, 2);
-            const uint64_t bd = umma_desc(sb + ks * 2048, 16, 1024, 2);
-            umma_bf16(tmem_base + pr * 64, ad, bd, IDESC, (uint32_t)((!first) | (ks > 0)));
-          }
+          for (int ks = 1; ks < 8; ++ks)
+            umma_bf16_acc(tacc, a_base + (uint64_t)((2 * ks * WG_SLAB_W * 128) >> 4), b_base + (uint64_t)((ks * 2048) >> 4), IDESC);
         }
         umma_commit(bar_empty(stage));
+        first = 0;
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
       }
-      first = 0;
-      __syncwarp();
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+      umma_commit(bar_acc);
     }
-    if (lane == 0) umma_commit(bar_acc);
     __syncwarp();
   } else {
     // ===================== drain: TMEM -> fp32 partial [tap][ci][co] =====================

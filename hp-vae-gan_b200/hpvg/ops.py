@@ -101,6 +101,36 @@ def pack_weights(w, cout, cin, taps, transposed, sigma=None, rows=None):
     return out
 
 
+_PACK_GEN = [0]
+
+
+def invalidate_packed_weights():
+    """Packed bf16 weight images are cached on the weight tensor, stamped with its version counter.  A CUDA-graph replay
+    updates weights without touching version counters, so whoever replays a graph that contains optimizer steps calls
+    this (hpvg.train.ScaleTrainer.replay does)."""
+    _PACK_GEN[0] += 1
+
+
+def packed_for(w, cout, cin, taps, transposed, rows):
+    """bf16 operand image of `w` for the tcgen05 kernels, repacked only when the weight changed: the same weight is used
+    by the 'rec' and 'rand' generator passes and, transposed, by their data-gradient passes within one iteration"""
+    key = (bool(transposed), rows)
+    stamp = (w._version, _PACK_GEN[0], w.data_ptr())
+    cache = getattr(w, '_hpvg_packs', None)
+    if cache is not None:
+        hit = cache.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+    packed = pack_weights(w, cout, cin, taps, transposed, rows=rows)
+    if cache is None:
+        try:
+            w._hpvg_packs = cache = {}
+        except (AttributeError, RuntimeError):
+            return packed
+    cache[key] = (stamp, packed)
+    return packed
+
+
 def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None):
     """One hpvg_conv_forward call.  `w` is the float32 weight of the *forward* convolution ([Cout_f, Cin_f, (3,)3,3]);
     transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f)."""
@@ -123,7 +153,7 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
     y = _empty(n, cout, do, ho, wo, out_wide, x.device)
     packed = None
     if _tc_eligible(cin, cout, is_wide(x), out_wide, plain=act_slope is None and stats is None and mask_src is None):
-        packed = pack_weights(w, cout, cin, taps, transposed, rows=None if out_wide else THIN_ROWS)
+        packed = packed_for(w, cout, cin, taps, transposed, cout if out_wide else THIN_ROWS)
     if bias is not None:
         bias = bias.contiguous()
     lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,

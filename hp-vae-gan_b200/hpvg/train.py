@@ -91,10 +91,10 @@ class ScaleTrainer:
         if self.gan and netD is None:
             raise ValueError("scale %d is a GAN scale (vae_levels=%d): a discriminator is required" % (opt.scale_idx, opt.vae_levels))
         self.capturable = capturable
-        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999),
-                                           capturable=capturable)
-        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999),
-                                           capturable=capturable) if self.gan else None
+        # capturable mode uses torch's fused multi-tensor Adam kernel (one launch per parameter group, same update rule)
+        extra = dict(capturable=True, fused=True) if capturable else {}
+        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999), **extra)
+        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999), **extra) if self.gan else None
         self.distributed = distributed
         self.bucketG, self.bucketD = GradBucket(), GradBucket()
         self.allreduce_bytes = 0
@@ -207,6 +207,7 @@ class ScaleTrainer:
         if self.gan:
             ops._GpAlpha.draw(self.static_real.device)     # the reference's per-iteration CPU draw of the GP alpha
         self.graph.replay()
+        ops.invalidate_packed_weights()                    # the replay stepped the optimizers behind torch's version counters
         self.iterations += 1
         return self.static_out
 
@@ -217,6 +218,43 @@ def draws_for_rank(total, world, rank):
     count = base + (1 if rank < extra else 0)
     start = rank * base + min(rank, extra)
     return start, count
+
+
+class Sampler:
+    """Diverse-sample generation (train_video.py:226-235) with the forward of one draw recorded into a CUDA graph: z is
+    drawn by torch's generator inside the graph (graph-safe Philox offsets), so every replay is a fresh sample."""
+
+    def __init__(self, netG, opt, device, batch=1, graph=True):
+        self.netG, self.opt, self.device, self.batch = netG, opt, device, batch
+        self.size = [batch] + list(opt.Z_init_size[1:])
+        self.graph = None
+        if graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):
+                    self._draw()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.static_fake = self._draw()
+
+    def _draw(self):
+        z = images.generate_noise(size=self.size, device=self.device)
+        fake, _ = self.netG(z, self.opt.Noise_Amps, noise_init=z, mode="rand")
+        return fake
+
+    @torch.no_grad()
+    def sample(self):
+        """one batch of draws; with a graph the returned tensor is the graph's output buffer (overwritten by the next call)"""
+        if self.graph is None:
+            return self._draw()
+        self.graph.replay()
+        return self.static_fake
+
+    def frames_per_call(self, fake):
+        return fake.shape[0] * (fake.shape[2] if fake.dim() == 5 else 1)
 
 
 @torch.no_grad()
