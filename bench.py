@@ -265,6 +265,15 @@ def run_hpvg(args):
             last["rec_loss"] = out["rec_loss"].item()
         for _ in range(W):
             step_resident()
+    if args.profile_one:
+        # for `ncu --profile-from-start off`: exactly one replayed (or eager) iteration between cudaProfilerStart/Stop
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiled": "one iteration", "graph": use_graph}), flush=True)
+        return
     torch.cuda.reset_peak_memory_stats()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -361,8 +370,13 @@ def run_hpvg(args):
                                     "sample": "%d full iteration(s) of the same workload after 1 warm-up (oracle/train_ref.py, PyTorch-CPU fp32)" % done}
         print(json.dumps(line), flush=True)
     if distributed:
+        # all ranks are done once rank 0 has printed; leave without tearing NCCL down: destroy_process_group() was seen
+        # to hang while CUDA graphs holding captured all-reduces are alive
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -373,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
     ap.add_argument("--draws", type=int, default=256, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
     args = ap.parse_args()
     if args.impl == "reference":
