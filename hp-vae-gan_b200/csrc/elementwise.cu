@@ -63,6 +63,74 @@ __global__ void __launch_bounds__(256) bn_apply_lrelu_kernel(const uint4* __rest
   }
 }
 
+// bn_finalize + bn_apply_lrelu in one launch: every block derives scale/shift for all channels from the sums (C <= 256
+// channels: trivial), block 0 also publishes them for the backward pass and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_finalize_apply_lrelu_kernel(const uint4* __restrict__ y, const float* __restrict__ stats,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                      long long* __restrict__ nbt, float momentum, float eps,
+                                                                      long long count, float* __restrict__ scale_shift,
+                                                                      float* __restrict__ mean_invstd, uint4* __restrict__ out,
+                                                                      long long nvec, int C, float slope) {
+  extern __shared__ float ss[];  // scale[C], shift[C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double inv = 1.0 / (double)count;
+    const double mean = (double)stats[c] * inv;
+    double var = (double)stats[C + c] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    const float sh = beta[c] - (float)mean * sc;
+    ss[c] = sc;
+    ss[C + c] = sh;
+    if (blockIdx.x == 0) {
+      scale_shift[c] = sc;
+      scale_shift[C + c] = sh;
+      mean_invstd[c] = (float)mean;
+      mean_invstd[C + c] = invstd;
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) {
+        const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+      if (c == 0 && nbt) nbt[0] += 1;
+    }
+  }
+  __syncthreads();
+  const int cvec = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) << 3;
+    uint4 v = __ldg(y + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = unpack_bf16x2(w[k]);
+      float a = fmaf(f.x, ss[c0 + 2 * k], ss[C + c0 + 2 * k]);
+      float b = fmaf(f.y, ss[c0 + 2 * k + 1], ss[C + c0 + 2 * k + 1]);
+      a = a > 0.f ? a : a * slope;
+      b = b > 0.f ? b : b * slope;
+      w[k] = pack_bf16x2(a, b);
+    }
+    out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// per-channel sums of bf16 vectors a thread produced (its 8-channel group is fixed because the grid stride is a multiple
+// of C/8): block reduction through shared memory, then one atomic per channel and block
+__device__ __forceinline__ void block_channel_sum(const float (&acc)[8], int c0, int C, float* red, float* __restrict__ out) {
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // lanes of a warp cover 32 / (C/8) rows x (C/8) channel groups: combine the rows that share a group first
+    float v = acc[k];
+    for (int o = 16; o >= (C >> 3); o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) < (C >> 3)) atomicAdd(red + c0 + k, v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, red[i]);
+}
+
 // thread = (row lane, 8-channel group); per-thread partial sums in registers, block reduction through shared memory
 __global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gout,
                                                                   const float* __restrict__ scale_shift,
@@ -123,8 +191,11 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
                                                                  const float* __restrict__ scale_shift,
                                                                  const float* __restrict__ mean_invstd, const float* __restrict__ sums,
                                                                  uint4* __restrict__ gy, float* __restrict__ dgamma,
-                                                                 float* __restrict__ dbeta, long long nvox, int C, float slope) {
-  extern __shared__ float prm[];  // scale, shift, mean, invstd, m0 = sum dz / M, m1 = sum dz*xhat / M
+                                                                 float* __restrict__ dbeta, long long nvox, int C, float slope,
+                                                                 float* __restrict__ chsum) {
+  extern __shared__ float prm[];  // scale, shift, mean, invstd, m0 = sum dz / M, m1 = sum dz*xhat / M, [C] reduction scratch
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int my_c0 = 0;
   const float invM = 1.f / (float)nvox;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     prm[i] = scale_shift[i];
@@ -159,13 +230,27 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
         res[e] = prm[c] * (dz - prm[4 * C + c] - xh * prm[5 * C + c]);
       }
       ow[k] = pack_bf16x2(res[0], res[1]);
+      if (chsum) {   // sum of the STORED (bf16) gradient: the bias gradient of the convolution in front of this BatchNorm
+        const float2 st = unpack_bf16x2(ow[k]);
+        csum[2 * k] += st.x;
+        csum[2 * k + 1] += st.y;
+      }
     }
+    my_c0 = c0;
     gy[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  if (chsum) {
+    __syncthreads();
+    block_channel_sum(csum, ((threadIdx.x % cvec) << 3), C, prm + 6 * C, chsum);
+    (void)my_c0;
   }
 }
 
 __global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict__ gout, const uint4* __restrict__ outv,
-                                                        uint4* __restrict__ gz, long long nvec, float slope) {
+                                                        uint4* __restrict__ gz, long long nvec, float slope, int C,
+                                                        float* __restrict__ chsum) {
+  extern __shared__ float red[];   // [C] when chsum
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 g = __ldg(gout + i), o = __ldg(outv + i);
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
@@ -174,9 +259,15 @@ __global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict_
     for (int k = 0; k < 4; ++k) {
       const float2 gf = unpack_bf16x2(gw[k]), of = unpack_bf16x2(ow[k]);
       r[k] = pack_bf16x2(of.x > 0.f ? gf.x : gf.x * slope, of.y > 0.f ? gf.y : gf.y * slope);
+      if (chsum) {
+        const float2 st = unpack_bf16x2(r[k]);
+        csum[2 * k] += st.x;
+        csum[2 * k + 1] += st.y;
+      }
     }
     gz[i] = make_uint4(r[0], r[1], r[2], r[3]);
   }
+  if (chsum) block_channel_sum(csum, (int)((threadIdx.x % (C >> 3)) << 3), C, red, chsum);
 }
 
 // ===============================================================================================================
@@ -584,10 +675,22 @@ int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long
   return 0;
 }
 
+int hpvg_bn_finalize_apply_lrelu(const void* y, const float* stats, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, long long* nbt, float momentum, float eps, float* scale_shift,
+                                 float* mean_invstd, void* out, long long nvox, int C, float slope, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && nvox > 0, "bn_finalize_apply_lrelu: C=%d must be a multiple of 8 (<= 256)", C);
+  const long long nvec = nvox * (C / 8);
+  bn_finalize_apply_lrelu_kernel<<<ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream)>>>(
+      reinterpret_cast<const uint4*>(y), stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, nvox, scale_shift,
+      mean_invstd, reinterpret_cast<uint4*>(out), nvec, C, slope);
+  HPVG_CHECK_LAUNCH("bn_finalize_apply_lrelu");
+  return 0;
+}
+
 int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
                              long long nvox, int C, float slope, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 256, "bn_lrelu_bwd_reduce: C=%d must be a multiple of 8 (<= 256)", C);
-  MEMSET0(sums, 2 * C * sizeof(float), ST(stream), "bn_lrelu_bwd_reduce");
+  MEMSET0(sums, 3 * C * sizeof(float), ST(stream), "bn_lrelu_bwd_reduce");   // [2C] sums + [C] bias-gradient accumulator
   const int rows = 256 / (C / 8);
   const size_t smem = (size_t)(4 * C + rows * 2 * C) * sizeof(float);
   const int blocks = (int)max(1LL, min(cdiv(nvox, rows), (long long)num_sms() * 4));
@@ -597,23 +700,27 @@ int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale
   return 0;
 }
 
-int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, const float* sums,
-                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, void* stream) {
-  HPVG_CHECK_ARG(C % 8 == 0 && C <= 1024, "bn_lrelu_bwd_apply: C=%d must be a multiple of 8", C);
+int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
+                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum, void* stream) {
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && (256 % (C / 8)) == 0, "bn_lrelu_bwd_apply: C=%d must be a multiple of 8 dividing 2048", C);
   const long long nvec = nvox * (C / 8);
-  bn_lrelu_bwd_apply_kernel<<<ew_blocks(nvec, 256), 256, 6 * C * sizeof(float), ST(stream)>>>(
+  bn_lrelu_bwd_apply_kernel<<<ew_blocks(nvec, 256), 256, 7 * C * sizeof(float), ST(stream)>>>(
       reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift, mean_invstd, sums,
-      reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope);
+      reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr);
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
   return 0;
 }
 
-int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, void* stream) {
+int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, int C, float* chsum,
+                   void* stream) {
   HPVG_CHECK_ARG(numel % 8 == 0, "lrelu_bwd: numel=%lld must be a multiple of 8", numel);
+  HPVG_CHECK_ARG(chsum == nullptr || (C % 8 == 0 && C <= 256 && (256 % (C / 8)) == 0 && numel % C == 0),
+                 "lrelu_bwd: fused channel sum needs C (=%d) a multiple of 8 dividing 2048", C);
+  if (chsum) MEMSET0(chsum, C * sizeof(float), ST(stream), "lrelu_bwd");
   const long long nvec = numel / 8;
-  lrelu_bwd_kernel<<<ew_blocks(nvec, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(gout),
-                                                                 reinterpret_cast<const uint4*>(out_saved), reinterpret_cast<uint4*>(gz),
-                                                                 nvec, slope);
+  lrelu_bwd_kernel<<<ew_blocks(nvec, 256), 256, chsum ? C * sizeof(float) : 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(gout), reinterpret_cast<const uint4*>(out_saved), reinterpret_cast<uint4*>(gz), nvec, slope, C,
+      chsum);
   HPVG_CHECK_LAUNCH("lrelu_bwd");
   return 0;
 }

@@ -284,19 +284,28 @@ __global__ void __launch_bounds__(OC_THREADS, 2) outer_corr_kernel(const OuterCo
     for (int e = 0; e < 4; ++e) dst[(i * 4 + e) * OC_THREADS] = acc[i][e];
 }
 
-// dw[...] = sum over blocks of the partials; one thread per (slot i, element e, thread id) of the first kernel
-__global__ void outer_corr_reduce_kernel(const float* __restrict__ partial, int blocks, int nc, int taps, int J, int wide_is_gy,
-                                         float* __restrict__ dw, float* __restrict__ wide_sum) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nc * 4 * OC_THREADS) return;
+// dw[...] = sum over blocks of the partials.  A block reduces 32 consecutive outputs (one 128-byte line of every partial
+// row) with 8 threads per output walking the rows 8 apart, so the ~300 dependent loads of a serial sum become ~37.
+__global__ void __launch_bounds__(256) outer_corr_reduce_kernel(const float* __restrict__ partial, int blocks, int nc, int taps, int J,
+                                                                int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int total = nc * 4 * OC_THREADS;
+  const int idx = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (idx < total)
+    for (int b = slice; b < blocks; b += 8) s += partial[(size_t)b * total + idx];
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || idx >= total) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) s += red[k][lane];
   const int tid = idx % OC_THREADS, e = (idx / OC_THREADS) & 3, i = idx / (4 * OC_THREADS);
   const int kq = tid & 15, sl = tid >> 4;
   const int c = sl + 16 * i, k = 4 * kq + e;
   const int ncomb = taps * J;
   const bool is_sum = wide_sum != nullptr && sl == 15 && i == nc - 1 && c >= ncomb;
   if (c >= ncomb && !is_sum) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * (nc * 4 * OC_THREADS) + idx];
   if (is_sum) {
     wide_sum[k] = s;
     return;
@@ -395,7 +404,7 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
   }
   HPVG_CHECK_LAUNCH("outer_corr_kernel");
   const int total = nc * 4 * OC_THREADS;
-  outer_corr_reduce_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(p.partial, grid, nc, g.taps, p.J, head ? 1 : 0, dw,
+  outer_corr_reduce_kernel<<<(unsigned)cdiv(total, 32), 256, 0, st>>>(p.partial, grid, nc, g.taps, p.J, head ? 1 : 0, dw,
                                                                       p.want_sum ? dbias_wide : nullptr);
   HPVG_CHECK_LAUNCH("outer_corr_reduce_kernel");
   return 0;

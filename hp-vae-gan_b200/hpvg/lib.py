@@ -34,8 +34,10 @@ PROTOTYPES = {
     "hpvg_bn_apply_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "hpvg_bn_lrelu_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "hpvg_bn_lrelu_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_longlong, c_int, c_float, c_void_p]),
-    "hpvg_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
+                                        c_longlong, c_int, c_float, c_int, c_void_p]),
+    "hpvg_bn_finalize_apply_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                             c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "hpvg_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p, c_void_p]),
     "hpvg_upsample_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),
     "hpvg_upsample_linear_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

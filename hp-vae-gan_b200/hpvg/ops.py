@@ -205,14 +205,21 @@ class ConvFwd(Function):
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope) if ctx.act_slope is not None else gy.contiguous()
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2] and not _input_only()
         gx = gw = gb = None
+        if ctx.act_slope is not None:
+            if want_gb and _chsum_fusable(y.shape[-1]):
+                gz, gb = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, True)    # bias gradient from the same pass
+            else:
+                gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, False)
+        else:
+            gz = gy.contiguous()
         if ctx.needs_input_grad[0]:
             gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
         if not _input_only():
             if ctx.needs_input_grad[1]:
                 gw = ConvWgrad.apply(x, gz, ctx.pad, tuple(w.shape))
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+            if want_gb and gb is None:
                 gb = ChannelSum.apply(gz)
         return gx, gw, gb, None, None, None, None
 
@@ -261,24 +268,35 @@ class ConvWgrad(Function):
         return g_x, g_gz, None, None
 
 
+def _chsum_fusable(c):
+    """channel counts for which the elementwise backward kernels can also emit per-channel sums (C/8 a power of two)"""
+    return c % 8 == 0 and c <= 256 and (256 % (c // 8)) == 0
+
+
 class LReluBwd(Function):
-    """gz = gy * lrelu'(y) with the derivative read from the saved activation output (sign(y) == sign(pre-activation))."""
+    """gz = gy * lrelu'(y) with the derivative read from the saved activation output (sign(y) == sign(pre-activation)).
+    With want_sum the kernel also returns the per-channel sum of gz (the bias gradient of the convolution in front)."""
 
     @staticmethod
-    def forward(ctx, gy, y, slope):
+    def forward(ctx, gy, y, slope, want_sum=False):
         _require_cuda(gy, y)
         if not (is_wide(gy) and is_wide(y)):
             raise TypeError("LReluBwd works on wide (bf16 NDHWC) tensors")
         gz = torch.empty_like(gy)
-        lib.call("hpvg_lrelu_bwd", _ptr(gy), _ptr(y), _ptr(gz), gy.numel(), float(slope), _stream())
-        ctx.slope = slope
+        c = gy.shape[-1]
+        gb = torch.empty((c,), dtype=torch.float32, device=gy.device) if want_sum else None
+        lib.call("hpvg_lrelu_bwd", _ptr(gy), _ptr(y), _ptr(gz), gy.numel(), float(slope), c, _ptr(gb), _stream())
+        ctx.slope, ctx.want_sum = slope, want_sum
         ctx.save_for_backward(y)
+        if want_sum:
+            ctx.mark_non_differentiable(gb)
+            return gz, gb
         return gz
 
     @staticmethod
-    def backward(ctx, ggz):
+    def backward(ctx, ggz, *unused):
         (y,) = ctx.saved_tensors
-        return LReluBwd.apply(ggz.contiguous(), y, ctx.slope), None, None
+        return LReluBwd.apply(ggz.contiguous(), y, ctx.slope, False), None, None, None
 
 
 class ChannelSum(Function):
@@ -326,24 +344,69 @@ class BnLrelu(Function):
         y, scale_shift, mean_invstd = ctx.saved_tensors
         gout = gout.contiguous()
         c, nvox = ctx.c, ctx.nvox
-        sums = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+        sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
                  float(ctx.slope), _stream())
         gy = torch.empty_like(y)
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
-                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), _stream())
+                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), 0, _stream())
         return gy, None, dgamma, dbeta, None, None, None, None, None, None
 
 
+class ConvBnLrelu(Function):
+    """ConvBlock3D/2D as ONE autograd node (reference modules/networks_3d.py:48-56).
+    forward : conv (+bias) with BatchNorm sums fused into its epilogue -> finalize + normalise + affine + LeakyReLU (1 launch)
+    backward: BN/LReLU backward reduce -> apply (also emits the conv-bias gradient) -> data gradient -> weight gradient.
+    First-order only: BatchNorm blocks live in the generators, which are never differentiated twice."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope):
+        _require_cuda(x, w, gamma, beta)
+        cout = w.shape[0]
+        stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
+        y = conv_raw(x, w, bias, pad, False, True, stats=stats)
+        n, c, d, h, wd = dims_of(y)
+        nvox = n * d * h * wd
+        scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+        mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+        out = torch.empty_like(y)
+        lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                 _ptr(nbt), float(momentum), float(eps), _ptr(scale_shift), _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
+        ctx.pad, ctx.slope, ctx.c, ctx.nvox, ctx.has_bias = pad, slope, c, nvox, bias is not None
+        ctx.save_for_backward(x, w, y, scale_shift, mean_invstd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x, w, y, scale_shift, mean_invstd = ctx.saved_tensors
+        gout = gout.contiguous()
+        c, nvox = ctx.c, ctx.nvox
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        fuse_gb = want_gb and _chsum_fusable(c)
+        sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
+        lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
+                 float(ctx.slope), _stream())
+        gy = torch.empty_like(y)
+        dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
+        dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
+        lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _stream())
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = conv_raw(gy, w, None, 2 - ctx.pad, True, is_wide(x))
+        if ctx.needs_input_grad[1]:
+            gw, _ = wgrad_raw(x, gy, ctx.pad, tuple(w.shape))
+        if want_gb:
+            gb = sums[2 * c:] if fuse_gb else channel_sum(gy)
+        return gx, gw, gb, dgamma, dbeta, None, None, None, None, None, None, None
+
+
 def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum=0.1, eps=1e-5, slope=0.2):
-    """ConvBlock3D/2D forward (reference modules/networks_3d.py:48-56): conv (+bias) with fused batch sums, then
-    normalise + affine + LeakyReLU in one pass."""
-    cout = w.shape[0]
-    stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
-    y = ConvFwd.apply(x, w, bias, pad, True, None, stats)
-    return BnLrelu.apply(y, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, slope)
+    """ConvBlock3D/2D (reference modules/networks_3d.py:48-56) through the fused node"""
+    return ConvBnLrelu.apply(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope)
 
 
 # ---------------------------------------------------------------------------------------------------------------

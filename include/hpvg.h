@@ -105,9 +105,11 @@ int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long
  * bn_finalize: from the conv-epilogue sums -> scale_shift[0..C) = gamma*invstd, [C..2C) = beta - mean*scale ;
  *   mean_invstd[0..C) = mean, [C..2C) = invstd ; running_mean/var updated with `momentum` (unbiased variance),
  *   num_batches_tracked += 1 (int64, may be NULL).
- * bn_apply_lrelu: out = lrelu(y*scale + shift).
- * bn_lrelu_bwd_reduce: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat with dz = gout * lrelu'(y*scale+shift).
- * bn_lrelu_bwd_apply: gy = scale * (dz - sums0/M - xhat*sums1/M) ; dgamma = sums1, dbeta = sums0 (written once).
+ * bn_apply_lrelu: out = lrelu(y*scale + shift).   bn_finalize_apply_lrelu: both of the above in one launch.
+ * bn_lrelu_bwd_reduce: `sums` is float32 [3*C], zeroed here; sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat with
+ *   dz = gout * lrelu'(y*scale+shift).
+ * bn_lrelu_bwd_apply: gy = scale * (dz - sums0/M - xhat*sums1/M) ; dgamma = sums1, dbeta = sums0 (written once); with
+ *   want_chsum, sums[2C..3C) += per-channel sum of the stored gy = the bias gradient of the preceding convolution.
  * ------------------------------------------------------------------------------------------------------------- */
 int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, long long* num_batches_tracked, float momentum, float eps,
@@ -117,11 +119,18 @@ int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long
 int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
                              float* sums, long long nvox, int C, float slope, void* stream);
 int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
-                            const float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
-                            float slope, void* stream);
+                            float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
+                            float slope, int want_chsum, void* stream);
+int hpvg_bn_finalize_apply_lrelu(const void* y, const float* stats, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                                 float eps, float* scale_shift, float* mean_invstd, void* out, long long nvox, int C,
+                                 float slope, void* stream);
 
-/* gz = gout * (out > 0 ? 1 : slope)   — aten::leaky_relu_backward on the saved in-place output (bf16 tensors) */
-int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, void* stream);
+/* gz = gout * (out > 0 ? 1 : slope)   — aten::leaky_relu_backward on the saved in-place output (bf16 NDHWC tensors).
+ * chsum (may be NULL; float32 [C], overwritten) receives the per-channel sum of gz: the bias gradient of the
+ * spectral-norm convolution in front of this activation, fused into the same pass. */
+int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long numel, float slope, int C, float* chsum,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Trilinear / bilinear resize with align_corners=True on NCDHW float32 tensors, replaces utils.upscale /
