@@ -637,6 +637,105 @@ __global__ void sn_bwd_kernel(const float* __restrict__ gw_sn, const float* __re
   }
 }
 
+
+// ---- the same four steps for up to HPVG_SN_MAX_LAYERS layers at once (blockIdx.y = layer): one network's spectral-norm
+// weights are all computed before its first convolution, in 4 launches instead of 4 per layer ----------------------------
+struct SnBatch {
+  int n;
+  const float* w[HPVG_SN_MAX_LAYERS];
+  float* u[HPVG_SN_MAX_LAYERS];
+  float* v[HPVG_SN_MAX_LAYERS];
+  float* sigma[HPVG_SN_MAX_LAYERS];
+  float* w_sn[HPVG_SN_MAX_LAYERS];
+  float* scratch[HPVG_SN_MAX_LAYERS];     // K + Cout + 4 floats: v_raw, t_raw, norms
+  const float* gw_sn[HPVG_SN_MAX_LAYERS];  // backward only
+  float* gw[HPVG_SN_MAX_LAYERS];
+  int cout[HPVG_SN_MAX_LAYERS], k[HPVG_SN_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(256) snb_wtu_kernel(const SnBatch b) {
+  __shared__ float red[8];
+  const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= K) return;
+  const float* W = b.w[l];
+  const float* u = b.u[l];
+  float acc = 0.f;
+  if (k < K)
+    for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
+  if (k < K) b.scratch[l][k] = acc;
+  const float s = block_sum_256(k < K ? acc * acc : 0.f, red);
+  if (threadIdx.x == 0) atomicAdd(b.scratch[l] + K + Cout, s);
+}
+__global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update_uv) {
+  __shared__ float red[8];
+  const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
+  const int r = blockIdx.x;
+  if (r >= Cout) return;
+  const float* W = b.w[l];
+  const float* vec = update_uv ? b.scratch[l] : b.v[l];
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) acc = fmaf(W[(size_t)r * K + k], vec[k], acc);
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) {
+    b.scratch[l][K + r] = s;
+    atomicAdd(b.scratch[l] + K + Cout + 1, s * s);
+  }
+}
+__global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int update_uv, float eps) {
+  __shared__ float red[8];
+  const int l = blockIdx.x, K = b.k[l], Cout = b.cout[l];
+  const float* v_raw = b.scratch[l];
+  const float* t_raw = b.scratch[l] + K;
+  const float* norms = b.scratch[l] + K + Cout;
+  if (update_uv) {
+    const float nv = fmaxf(sqrtf(norms[0]), eps);
+    const float tn = sqrtf(norms[1]) / nv;  // || W v ||
+    const float nu = fmaxf(tn, eps);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) b.v[l][k] = v_raw[k] / nv;
+    for (int r = threadIdx.x; r < Cout; r += blockDim.x) b.u[l][r] = (t_raw[r] / nv) / nu;
+    if (threadIdx.x == 0) b.sigma[l][0] = tn * tn / nu;  // u^T (W v)
+  } else {
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < Cout; r += blockDim.x) acc = fmaf(b.u[l][r], t_raw[r], acc);
+    const float s = block_sum_256(acc, red);
+    if (threadIdx.x == 0) b.sigma[l][0] = s;
+  }
+}
+__global__ void snb_scale_kernel(const SnBatch b) {
+  const int l = blockIdx.y;
+  const long long n = (long long)b.cout[l] * b.k[l];
+  const float inv = 1.f / b.sigma[l][0];
+  const float* w = b.w[l];
+  float* o = b.w_sn[l];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = w[i] * inv;
+}
+// backward: scratch[l][0] = sum gw_sn * w_sn ; gw = (gw_sn - dot * u v^T) / sigma      (b.w holds w_sn here)
+__global__ void __launch_bounds__(256) snb_dot_kernel(const SnBatch b) {
+  __shared__ float red[8];
+  const int l = blockIdx.y;
+  const long long n = (long long)b.cout[l] * b.k[l];
+  const float* a = b.gw_sn[l];
+  const float* w = b.w[l];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(a[i], w[i], acc);
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) atomicAdd(b.scratch[l], s);
+}
+__global__ void snb_bwd_kernel(const SnBatch b) {
+  const int l = blockIdx.y, K = b.k[l];
+  const long long total = (long long)b.cout[l] * K;
+  const float inv = 1.f / b.sigma[l][0], d = b.scratch[l][0];
+  const float* g = b.gw_sn[l];
+  const float* u = b.u[l];
+  const float* v = b.v[l];
+  float* o = b.gw[l];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K), r = (int)(i / K);
+    o[i] = (g[i] - d * u[r] * v[k]) * inv;
+  }
+}
+
 }  // namespace hpvg
 
 // =================================================================================================================
@@ -887,6 +986,65 @@ int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, cons
   HPVG_CHECK_LAUNCH("sn_dot");
   sn_bwd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(gw_sn, u, v, sigma, scratch, gw_orig, Cout, K);
   HPVG_CHECK_LAUNCH("sn_bwd");
+  return 0;
+}
+
+// Batched forms: `n` layers (<= HPVG_SN_MAX_LAYERS) in 4 (forward) / 2 (backward) launches.  Pointer arrays live in host
+// memory and are copied into the kernel parameters.
+static int sn_fill_batch(SnBatch& b, int n, const int* cout, const int* k, const char* who) {
+  HPVG_CHECK_ARG(n > 0 && n <= HPVG_SN_MAX_LAYERS, "%s: %d layers (max %d)", who, n, HPVG_SN_MAX_LAYERS);
+  b.n = n;
+  for (int l = 0; l < n; ++l) {
+    HPVG_CHECK_ARG(cout[l] > 0 && k[l] > 0, "%s: bad shape of layer %d", who, l);
+    b.cout[l] = cout[l];
+    b.k[l] = k[l];
+  }
+  return 0;
+}
+
+int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
+                               float* const* w_sn, float* const* scratch, const int* cout, const int* k, int update_uv, float eps,
+                               void* stream) {
+  SnBatch b;
+  if (int rc = sn_fill_batch(b, n, cout, k, "sn_power_iter_batched")) return rc;
+  int maxk = 0, maxc = 0;
+  long long maxn = 0;
+  for (int l = 0; l < n; ++l) {
+    b.w[l] = w_orig[l]; b.u[l] = u[l]; b.v[l] = v[l]; b.sigma[l] = sigma[l]; b.w_sn[l] = w_sn[l]; b.scratch[l] = scratch[l];
+    maxk = max(maxk, k[l]); maxc = max(maxc, cout[l]);
+    maxn = max(maxn, (long long)cout[l] * k[l]);
+    MEMSET0(scratch[l] + k[l] + cout[l], 4 * sizeof(float), ST(stream), "sn_power_iter_batched");
+  }
+  if (update_uv) {
+    snb_wtu_kernel<<<dim3((unsigned)cdiv(maxk, 256), n), 256, 0, ST(stream)>>>(b);
+    HPVG_CHECK_LAUNCH("snb_wtu");
+  }
+  snb_wv_kernel<<<dim3(maxc, n), 256, 0, ST(stream)>>>(b, update_uv);
+  HPVG_CHECK_LAUNCH("snb_wv");
+  snb_finalize_kernel<<<n, 256, 0, ST(stream)>>>(b, update_uv, eps);
+  HPVG_CHECK_LAUNCH("snb_finalize");
+  snb_scale_kernel<<<dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream)>>>(b);
+  HPVG_CHECK_LAUNCH("snb_scale");
+  return 0;
+}
+
+int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* const* w_sn, const float* const* u, const float* const* v,
+                             const float* const* sigma, float* const* gw_orig, float* const* scratch, const int* cout, const int* k,
+                             void* stream) {
+  SnBatch b;
+  if (int rc = sn_fill_batch(b, n, cout, k, "sn_backward_batched")) return rc;
+  long long maxn = 0;
+  for (int l = 0; l < n; ++l) {
+    b.gw_sn[l] = gw_sn[l]; b.w[l] = w_sn[l]; b.u[l] = const_cast<float*>(u[l]); b.v[l] = const_cast<float*>(v[l]);
+    b.sigma[l] = const_cast<float*>(sigma[l]); b.gw[l] = gw_orig[l]; b.scratch[l] = scratch[l];
+    maxn = max(maxn, (long long)cout[l] * k[l]);
+    MEMSET0(scratch[l], sizeof(float), ST(stream), "sn_backward_batched");
+  }
+  const unsigned bx = (unsigned)min(cdiv(maxn, 256), 32LL);
+  snb_dot_kernel<<<dim3(bx, n), 256, 0, ST(stream)>>>(b);
+  HPVG_CHECK_LAUNCH("snb_dot");
+  snb_bwd_kernel<<<dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream)>>>(b);
+  HPVG_CHECK_LAUNCH("snb_bwd");
   return 0;
 }
 

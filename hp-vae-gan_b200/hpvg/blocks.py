@@ -104,8 +104,10 @@ class ConvBlockSN(nn.Sequential):
         conv = self.conv
         return ops.SpectralWeight.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, 1e-12)
 
-    def run(self, x, out_wide=True):
-        return ops.conv(x, self.weight(), self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None)
+    def run(self, x, out_wide=True, weight=None):
+        """`weight`: W / sigma computed by the caller for all layers of the network at once (ops.spectral_weights)"""
+        w = self.weight() if weight is None else weight
+        return ops.conv(x, w, self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None)
 
     def forward(self, x):
         _check_device(x)
@@ -115,6 +117,16 @@ class ConvBlockSN(nn.Sequential):
 def _run_chain(seq, x):
     for m in seq:
         x = m.run(x)
+    return x
+
+
+def _run_sn_chain(blocks, x):
+    """a chain of spectral-norm blocks: one batched power iteration for all of them (the layers are independent, as in
+    the reference where every forward pre-hook runs on its own weight), then the convolutions"""
+    blocks = list(blocks)
+    weights = ops.spectral_weights([b.conv for b in blocks])
+    for b, w in zip(blocks, weights):
+        x = b.run(x, weight=w)
     return x
 
 
@@ -141,7 +153,7 @@ def make_family(dims):
                 self.add_module('conv_block_{}'.format(i), _ConvBlockSN(cin, out_channel, ker_size, padding, stride))
 
         def run(self, x):
-            return _run_chain(self, x)
+            return _run_sn_chain(self, x)
 
         def forward(self, x):
             _check_device(x)
@@ -183,8 +195,7 @@ def make_family(dims):
 
         def forward(self, x):
             _check_device(x)
-            h = self.head.run(as5d(x).contiguous())
-            h = _run_chain(self.body, h)
+            h = _run_sn_chain([self.head] + list(self.body), as5d(x).contiguous())
             out = ops.conv(h, self.tail.weight, self.tail.bias, 1, False)   # thin critic map [N,1,(T,)H,W]
             return like_input(out, dims)
 

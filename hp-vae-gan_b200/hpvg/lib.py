@@ -54,6 +54,10 @@ PROTOTYPES = {
     "hpvg_sn_power_iter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p]),
     "hpvg_sn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hpvg_sn_power_iter_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_float, c_void_p]),
+    "hpvg_sn_backward_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -86,6 +90,18 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise HpvgError("%s failed (%d): %s" % (name, rc, lib.hpvg_last_error().decode(errors="replace")))
+
+
+SN_MAX_LAYERS = 8
+
+
+def ptr_array(tensors):
+    """host array of device pointers (for the *_batched entry points)"""
+    return (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def int_array(values):
+    return (c_int * len(values))(*[int(v) for v in values])
 
 
 def launch_count():

@@ -635,3 +635,71 @@ class SpectralWeight(Function):
         lib.call("hpvg_sn_backward", _ptr(gw_sn.contiguous()), _ptr(w_sn), _ptr(u), _ptr(v), _ptr(sigma), _ptr(gw), _ptr(scratch),
                  cout, k, _stream())
         return gw, None, None, None, None
+
+
+class SpectralWeights(Function):
+    """SpectralWeight for all spectral-norm layers of one network in 4 launches (forward) / 2 (backward) instead of 4 / 2
+    per layer.  apply(update_uv, eps, w0, u0, v0, w1, u1, v1, ...) -> (w_sn0, w_sn1, ...)"""
+
+    @staticmethod
+    def forward(ctx, update_uv, eps, *tensors):
+        n = len(tensors) // 3
+        if n == 0 or n > lib.SN_MAX_LAYERS or len(tensors) != 3 * n:
+            raise ValueError("SpectralWeights takes 1..%d (w_orig, u, v) triples" % lib.SN_MAX_LAYERS)
+        ws = [tensors[3 * i].contiguous() for i in range(n)]
+        us = [tensors[3 * i + 1] for i in range(n)]
+        vs = [tensors[3 * i + 2] for i in range(n)]
+        _require_cuda(*ws)
+        dev = ws[0].device
+        couts = [w.shape[0] for w in ws]
+        ks = [w.numel() // w.shape[0] for w in ws]
+        sigmas = torch.empty((n,), dtype=torch.float32, device=dev)
+        sig = [sigmas[i:i + 1] for i in range(n)]
+        outs = [torch.empty_like(w) for w in ws]
+        offs, total = [], 0
+        for c, k in zip(couts, ks):
+            offs.append(total)
+            total += k + c + 4
+        scratch_all = torch.empty((total,), dtype=torch.float32, device=dev)
+        scratch = [scratch_all[o:] for o in offs]
+        lib.call("hpvg_sn_power_iter_batched", n, lib.ptr_array(ws), lib.ptr_array(us), lib.ptr_array(vs), lib.ptr_array(sig),
+                 lib.ptr_array(outs), lib.ptr_array(scratch), lib.int_array(couts), lib.int_array(ks), int(bool(update_uv)), float(eps),
+                 _stream())
+        # u, v are buffers mutated in place; the backward must see the values used for these sigmas
+        ctx.n, ctx.couts, ctx.ks = n, couts, ks
+        ctx.save_for_backward(sigmas, *outs, *[u.clone() for u in us], *[v.clone() for v in vs])
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        sigmas, outs, us, vs = saved[0], saved[1:1 + n], saved[1 + n:1 + 2 * n], saved[1 + 2 * n:1 + 3 * n]
+        idx = [i for i in range(n) if grads[i] is not None and ctx.needs_input_grad[2 + 3 * i]]
+        result = [None, None] + [None] * (3 * n)
+        if idx:
+            dev = sigmas.device
+            gs = [grads[i].contiguous() for i in idx]
+            gws = [torch.empty_like(outs[i]) for i in idx]
+            scratch_all = torch.empty((len(idx),), dtype=torch.float32, device=dev)
+            scratch = [scratch_all[j:j + 1] for j in range(len(idx))]
+            lib.call("hpvg_sn_backward_batched", len(idx), lib.ptr_array(gs), lib.ptr_array([outs[i] for i in idx]),
+                     lib.ptr_array([us[i] for i in idx]), lib.ptr_array([vs[i] for i in idx]),
+                     lib.ptr_array([sigmas[i:i + 1] for i in idx]), lib.ptr_array(gws), lib.ptr_array(scratch),
+                     lib.int_array([ctx.couts[i] for i in idx]), lib.int_array([ctx.ks[i] for i in idx]), _stream())
+            for j, i in enumerate(idx):
+                result[2 + 3 * i] = gws[j]
+        return tuple(result)
+
+
+def spectral_weights(convs, eps=1e-12):
+    """w_sn for a list of legacy-spectral_norm convolutions (attributes weight_orig / weight_u / weight_v), batched"""
+    out = []
+    for i in range(0, len(convs), lib.SN_MAX_LAYERS):
+        chunk = convs[i:i + lib.SN_MAX_LAYERS]
+        args = []
+        for c in chunk:
+            args += [c.weight_orig, c.weight_u, c.weight_v]
+        out += list(SpectralWeights.apply(chunk[0].training, eps, *args))
+    return out

@@ -185,6 +185,15 @@ int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, fl
                        int K, int update_uv, float eps, void* stream);
 int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, const float* v, const float* sigma,
                      float* gw_orig, float* scratch, int Cout, int K, void* stream);
+/* the same for all spectral-norm layers of one network at once (n <= HPVG_SN_MAX_LAYERS): arrays of n device pointers
+ * (the arrays themselves are host memory) and n shapes; scratch[l] holds K[l] + Cout[l] + 4 floats (forward) / 1 (backward) */
+#define HPVG_SN_MAX_LAYERS 8
+int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
+                               float* const* w_sn, float* const* scratch, const int* Cout, const int* K, int update_uv,
+                               float eps, void* stream);
+int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* const* w_sn, const float* const* u,
+                             const float* const* v, const float* const* sigma, float* const* gw_orig, float* const* scratch,
+                             const int* Cout, const int* K, void* stream);
 
 #ifdef __cplusplus
 }
