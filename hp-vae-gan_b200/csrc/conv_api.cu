@@ -10,8 +10,9 @@ bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_pa
 int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
             float* stats, const void* mask_src, cudaStream_t st);
 bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* mask_src);
-int expand_conv(const void* x, const float* w, const float* bias, void* y, const ConvGeom& g, int transposed, int act, float slope,
-                float* stats, cudaStream_t st);
+int expand_conv(const void* x, const float* w, const float* w_tco, const float* bias, void* y, const ConvGeom& g, int transposed,
+                int act, float slope, float* stats, cudaStream_t st);
+int pack_expand(const float* w, float* out, int Cin, int taps, int transposed, cudaStream_t st);
 bool narrow_wgrad_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g);
 int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbias_wide, const ConvGeom& g, void* workspace,
@@ -79,7 +80,7 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
   HPVG_CHECK_ARG(mask_src == nullptr || y_fmt == HPVG_FMT_NDHWC_BF16, "conv_forward: mask_src requires an NDHWC_BF16 output");
   if (backend != HPVG_BACKEND_DIRECT && expand_conv_supported(x_fmt, y_fmt, g, mask_src)) {
     void* ph = prof_begin(HPVG_PROF_CONV_EXPAND, flops, st);
-    int rc = expand_conv(x, w_f32, bias, y, g, transposed, act, lrelu_slope, stats, st);
+    int rc = expand_conv(x, w_f32, reinterpret_cast<const float*>(w_packed), bias, y, g, transposed, act, lrelu_slope, stats, st);
     prof_end(ph, st);
     return rc;
   }
@@ -87,6 +88,11 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
   int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
   prof_end(ph, st);
   return rc;
+}
+
+int hpvg_pack_weights_expand(const float* w_f32, float* w_tco, int Cin, int taps, int transposed, void* stream) {
+  HPVG_CHECK_ARG(w_f32 && w_tco && Cin > 0 && Cin <= 4 && (taps == 9 || taps == 27), "pack_weights_expand: bad arguments");
+  return pack_expand(w_f32, w_tco, Cin, taps, transposed, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t hpvg_conv_wgrad_workspace(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int gy_fmt) {

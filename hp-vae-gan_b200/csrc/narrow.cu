@@ -15,16 +15,17 @@
 
 namespace hpvg {
 
-constexpr int EX_TH = 8, EX_TW = 32;             // output tile of the expand kernel: 1 x 8 x 32 voxels, 2 per thread
-constexpr int EX_HW = EX_TW + 2, EX_HH = EX_TH + 2;
+constexpr int EX_TH = 8, EX_TW = 32;             // output tile of the expand kernel: 1 x 8 x 32 voxels; thread = 4 voxels x 32 channels
+constexpr int EX_HW = EX_TW + 4, EX_HH = EX_TH + 2;   // halo row padded to an even length (64-bit loads)
 
 // ---------------------------------------------------------------------------------------------------------------
 // thin -> wide convolution, Cout == 64
 // ---------------------------------------------------------------------------------------------------------------
 template <int KDT>
 __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, ConvGeom g,
-                                                          int transposed, int act, float slope, float* __restrict__ stats) {
+                                                             const float* __restrict__ w_tco, const float* __restrict__ bias,
+                                                             __nv_bfloat16* __restrict__ y, ConvGeom g, int transposed, int act,
+                                                             float slope, float* __restrict__ stats) {
   extern __shared__ float sm[];
   constexpr int TAPS = KDT * 9;
   float* ws = sm;                                   // [TAPS][Cin][64]
@@ -39,9 +40,17 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
   const int n = b / g.Do;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < TAPS * g.Cin * 64; i += 128) {
-    const int co = i & 63, ci = (i >> 6) % g.Cin, t = i / (64 * g.Cin);
-    ws[i] = transposed ? w[((size_t)ci * 64 + co) * TAPS + (TAPS - 1 - t)] : w[((size_t)co * g.Cin + ci) * TAPS + t];
+  if (w_tco) {
+    // filter already arranged [tap][ci][co] by hpvg_pack_weights_expand: a straight 128-bit copy.  (Gathering it from
+    // the PyTorch layout in every block — 40 rounds of 324-byte-strided loads — cost more than the convolution itself.)
+    const float4* src = reinterpret_cast<const float4*>(w_tco);
+    float4* dst = reinterpret_cast<float4*>(ws);
+    for (int i = tid; i < TAPS * g.Cin * 16; i += 128) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < TAPS * g.Cin * 64; i += 128) {
+      const int co = i & 63, ci = (i >> 6) % g.Cin, t = i / (64 * g.Cin);
+      ws[i] = transposed ? w[((size_t)ci * 64 + co) * TAPS + (TAPS - 1 - t)] : w[((size_t)co * g.Cin + ci) * TAPS + t];
+    }
   }
   const size_t in_sp = (size_t)g.Di * g.Hi * g.Wi;
   for (int i = tid; i < g.Cin * KDT * EX_HH * EX_HW; i += 128) {
@@ -54,35 +63,40 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
   }
   __syncthreads();
 
-  const int ty = tid >> 4, tx = tid & 15;          // output row ty, output columns 2*tx and 2*tx + 1 of the tile
-  float acc0[64], acc1[64];
+  // thread = 4 consecutive output voxels (along w) x 32 output channels.  The loop is bound by the shared-memory pipe,
+  // not by FMA issue: a (broadcast) 128-bit filter load occupies it for 4 cycles, so each one has to feed 16 FFMA (4 voxels
+  // x 4 channels) to keep the 128 FMA lanes of the SM busy; 2 voxels x 64 channels fed 8 and ran at a quarter of peak.
+  const int half = tid & 1, quad = tid >> 1;        // channel half, voxel quad 0..63
+  const int ty = quad >> 3, tx = (quad & 7) * 4;    // tile row, first tile column
+  float acc[4][32];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) acc0[j] = acc1[j] = 0.f;
-  // the (ci, kd, kh) loops stay rolled: the body (48 LDS.128 + 384 FFMA) is already long enough to pipeline, and a
-  // fully unrolled kernel (27x larger) stalled on instruction fetch (ncu: stall_no_inst was the top reason)
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[v][j] = 0.f;
+  // the (ci, kd, kh) loops stay rolled: a fully unrolled kernel stalled on instruction fetch (ncu: stall_no_inst on top)
 #pragma unroll 1
   for (int ci = 0; ci < g.Cin; ++ci) {
 #pragma unroll 1
     for (int kd = 0; kd < KDT; ++kd) {
 #pragma unroll 1
       for (int kh = 0; kh < 3; ++kh) {
-        const float* xr = xs + ((ci * KDT + kd) * EX_HH + ty + kh) * EX_HW + 2 * tx;
-        const float2 xa = *reinterpret_cast<const float2*>(xr), xb = *reinterpret_cast<const float2*>(xr + 2);
-        const float xv[4] = {xa.x, xa.y, xb.x, xb.y};
+        const float* xr = xs + ((ci * KDT + kd) * EX_HH + ty + kh) * EX_HW + tx;
+        const float2 x01 = *reinterpret_cast<const float2*>(xr), x23 = *reinterpret_cast<const float2*>(xr + 2),
+                     x45 = *reinterpret_cast<const float2*>(xr + 4);
+        const float xv[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float4* w4 = reinterpret_cast<const float4*>(ws + (((kd * 3 + kh) * 3 + kw) * g.Cin + ci) * 64);
+          const float4* w4 = reinterpret_cast<const float4*>(ws + (((kd * 3 + kh) * 3 + kw) * g.Cin + ci) * 64 + half * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float4 q = w4[j];
-            acc0[4 * j + 0] = fmaf(xv[kw], q.x, acc0[4 * j + 0]);
-            acc0[4 * j + 1] = fmaf(xv[kw], q.y, acc0[4 * j + 1]);
-            acc0[4 * j + 2] = fmaf(xv[kw], q.z, acc0[4 * j + 2]);
-            acc0[4 * j + 3] = fmaf(xv[kw], q.w, acc0[4 * j + 3]);
-            acc1[4 * j + 0] = fmaf(xv[kw + 1], q.x, acc1[4 * j + 0]);
-            acc1[4 * j + 1] = fmaf(xv[kw + 1], q.y, acc1[4 * j + 1]);
-            acc1[4 * j + 2] = fmaf(xv[kw + 1], q.z, acc1[4 * j + 2]);
-            acc1[4 * j + 3] = fmaf(xv[kw + 1], q.w, acc1[4 * j + 3]);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc[v][4 * j + 0] = fmaf(xv[kw + v], q.x, acc[v][4 * j + 0]);
+              acc[v][4 * j + 1] = fmaf(xv[kw + v], q.y, acc[v][4 * j + 1]);
+              acc[v][4 * j + 2] = fmaf(xv[kw + v], q.z, acc[v][4 * j + 2]);
+              acc[v][4 * j + 3] = fmaf(xv[kw + v], q.w, acc[v][4 * j + 3]);
+            }
           }
         }
       }
@@ -90,54 +104,55 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
   }
 
   // epilogue: bias, activation, bf16 rounding, store, BatchNorm sums of the stored values
-  const int oh = h0 + ty, ow = w0 + 2 * tx;
-  const bool ok0 = oh < g.Ho && ow < g.Wo, ok1 = oh < g.Ho && ow + 1 < g.Wo;
+  const int oh = h0 + ty;
+  float ssum[32], ssq[32];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const float bv = bias ? __ldg(bias + j) : 0.f;
-    float a = acc0[j] + bv, c = acc1[j] + bv;
-    if (act == HPVG_ACT_LRELU) {
-      a = a > 0.f ? a : a * slope;
-      c = c > 0.f ? c : c * slope;
+  for (int j = 0; j < 32; ++j) ssum[j] = ssq[j] = 0.f;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int ow = w0 + tx + v;
+    const bool ok = oh < g.Ho && ow < g.Wo;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float a = acc[v][j] + (bias ? __ldg(bias + half * 32 + j) : 0.f);
+      if (act == HPVG_ACT_LRELU) a = a > 0.f ? a : a * slope;
+      a = ok ? bf2f(f2bf(a)) : 0.f;
+      acc[v][j] = a;
+      ssum[j] += a;
+      ssq[j] = fmaf(a, a, ssq[j]);
     }
-    acc0[j] = ok0 ? bf2f(f2bf(a)) : 0.f;
-    acc1[j] = ok1 ? bf2f(f2bf(c)) : 0.f;
-  }
-  __nv_bfloat16* yp = y + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 64;
-  if (ok0) {
+    if (ok) {
+      __nv_bfloat16* yp = y + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 64 + half * 32;
 #pragma unroll
-    for (int j = 0; j < 64; j += 8) {
-      uint4 q;
-      q.x = pack_bf16x2(acc0[j + 0], acc0[j + 1]); q.y = pack_bf16x2(acc0[j + 2], acc0[j + 3]);
-      q.z = pack_bf16x2(acc0[j + 4], acc0[j + 5]); q.w = pack_bf16x2(acc0[j + 6], acc0[j + 7]);
-      *reinterpret_cast<uint4*>(yp + j) = q;
-    }
-  }
-  if (ok1) {
-#pragma unroll
-    for (int j = 0; j < 64; j += 8) {
-      uint4 q;
-      q.x = pack_bf16x2(acc1[j + 0], acc1[j + 1]); q.y = pack_bf16x2(acc1[j + 2], acc1[j + 3]);
-      q.z = pack_bf16x2(acc1[j + 4], acc1[j + 5]); q.w = pack_bf16x2(acc1[j + 6], acc1[j + 7]);
-      *reinterpret_cast<uint4*>(yp + 64 + j) = q;
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(acc[v][j + 0], acc[v][j + 1]); q.y = pack_bf16x2(acc[v][j + 2], acc[v][j + 3]);
+        q.z = pack_bf16x2(acc[v][j + 4], acc[v][j + 5]); q.w = pack_bf16x2(acc[v][j + 6], acc[v][j + 7]);
+        *reinterpret_cast<uint4*>(yp + j) = q;
+      }
     }
   }
   if (stats) {
     __syncthreads();                 // the filter stage is dead: reuse it for the block reduction [2][64]
     float* red = sm;
-    if (tid < 128) red[tid] = 0.f;
+    red[tid] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      const float s = warp_sum(acc0[j] + acc1[j]);
-      const float s2 = warp_sum(acc0[j] * acc0[j] + acc1[j] * acc1[j]);
-      if ((tid & 31) == 0) {
-        atomicAdd(red + j, s);
-        atomicAdd(red + 64 + j, s2);
+    for (int j = 0; j < 32; ++j) {
+      // lanes of equal parity hold the same channel half: reduce over the 16 lanes that share it
+      float s = ssum[j], s2 = ssq[j];
+#pragma unroll
+      for (int o = 16; o >= 2; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if ((tid & 31) < 2) {
+        atomicAdd(red + half * 32 + j, s);
+        atomicAdd(red + 64 + half * 32 + j, s2);
       }
     }
     __syncthreads();
-    if (tid < 128) atomicAdd(stats + tid, red[tid]);
+    atomicAdd(stats + tid, red[tid]);
   }
 }
 
@@ -145,16 +160,31 @@ bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* 
   return x_fmt == HPVG_FMT_NCDHW_F32 && y_fmt == HPVG_FMT_NDHWC_BF16 && g.Cin <= 4 && g.Cout == 64 && mask_src == nullptr;
 }
 
-int expand_conv(const void* x, const float* w, const float* bias, void* y, const ConvGeom& g, int transposed, int act, float slope,
-                float* stats, cudaStream_t st) {
+// [tap][ci][co] float32 image of a narrow layer's filter (co = 64), `transposed` as in hpvg_conv_forward
+__global__ void pack_expand_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int taps, int transposed) {
+  const int total = taps * Cin * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i & 63, ci = (i >> 6) % Cin, t = i / (64 * Cin);
+    out[i] = transposed ? w[((size_t)ci * 64 + co) * taps + (taps - 1 - t)] : w[((size_t)co * Cin + ci) * taps + t];
+  }
+}
+
+int pack_expand(const float* w, float* out, int Cin, int taps, int transposed, cudaStream_t st) {
+  pack_expand_kernel<<<(unsigned)cdiv(taps * Cin * 64, 256), 256, 0, st>>>(w, out, Cin, taps, transposed);
+  HPVG_CHECK_LAUNCH("pack_expand_kernel");
+  return 0;
+}
+
+int expand_conv(const void* x, const float* w, const float* w_tco, const float* bias, void* y, const ConvGeom& g, int transposed,
+                int act, float slope, float* stats, cudaStream_t st) {
   const int tiles_w = (int)cdiv(g.Wo, EX_TW), tiles_h = (int)cdiv(g.Ho, EX_TH);
   const long long blocks = (long long)g.N * g.Do * tiles_h * tiles_w;
   const size_t smem = ((size_t)g.taps * g.Cin * 64 + (size_t)g.Cin * g.KD * EX_HH * EX_HW) * sizeof(float);
   if (g.KD == 3)
-    expand_conv_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+    expand_conv_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                               g, transposed, act, slope, stats);
   else
-    expand_conv_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, bias, reinterpret_cast<__nv_bfloat16*>(y),
+    expand_conv_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                               g, transposed, act, slope, stats);
   HPVG_CHECK_LAUNCH("expand_conv_kernel");
   return 0;

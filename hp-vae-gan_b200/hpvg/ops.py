@@ -131,6 +131,26 @@ def packed_for(w, cout, cin, taps, transposed, rows):
     return packed
 
 
+def expand_image_for(w, cin, taps, transposed):
+    """float32 [taps][cin][64] filter image for the thin -> wide kernel, cached on the weight like packed_for()"""
+    key = ('expand', bool(transposed))
+    stamp = (w._version, _PACK_GEN[0], w.data_ptr())
+    cache = getattr(w, '_hpvg_packs', None)
+    if cache is not None:
+        hit = cache.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+    out = torch.empty((taps, cin, 64), dtype=torch.float32, device=w.device)
+    lib.call("hpvg_pack_weights_expand", _ptr(w), _ptr(out), cin, taps, int(transposed), _stream())
+    if cache is None:
+        try:
+            w._hpvg_packs = cache = {}
+        except (AttributeError, RuntimeError):
+            return out
+    cache[key] = (stamp, out)
+    return out
+
+
 def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None):
     """One hpvg_conv_forward call.  `w` is the float32 weight of the *forward* convolution ([Cout_f, Cin_f, (3,)3,3]);
     transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f)."""
@@ -154,6 +174,8 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
     packed = None
     if _tc_eligible(cin, cout, is_wide(x), out_wide, plain=act_slope is None and stats is None and mask_src is None):
         packed = packed_for(w, cout, cin, taps, transposed, cout if out_wide else THIN_ROWS)
+    elif (not is_wide(x)) and out_wide and cin <= 4 and cout == 64 and mask_src is None and lib.get_conv_backend() != lib.BACKEND_DIRECT:
+        packed = expand_image_for(w, cin, taps, transposed)
     if bias is not None:
         bias = bias.contiguous()
     lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,

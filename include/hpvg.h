@@ -96,6 +96,11 @@ int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float*
 int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed,
                       const float* inv_scale_of, int rows_per_tap, void* stream);
 
+/* float32 [taps][Cin][64] image of the filter of a thin -> wide layer (Cin <= 4, 64 output channels; `transposed` as in
+ * hpvg_conv_forward), passed as `w_packed` to hpvg_conv_forward for NCDHW_F32 -> NDHWC_BF16 calls: optional, but lets every
+ * block of the kernel copy the filter instead of gathering it from the PyTorch layout. */
+int hpvg_pack_weights_expand(const float* w_f32, float* w_tco, int Cin, int taps, int transposed, void* stream);
+
 /* per-channel sum of a tensor: out[c] = sum_{n,o} t[n,c,o]   (bias gradient) */
 int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long spatial, void* stream);
 
