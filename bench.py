@@ -34,7 +34,7 @@ for p in (PKG, ROOT):
 
 import torch  # noqa: E402
 
-CONV_GFLOP_PER_ITER = 1720.43      # SURVEY.md App. B, config 2 finest level
+CONV_GFLOP_PER_ITER = 1720.43      # SURVEY.md App. B, config 2 finest level (config 5: 12 650.99)
 METRIC = "train_iters_per_s_finest_scale"
 UNIT = "iter/s"
 
@@ -42,9 +42,15 @@ UNIT = "iter/s"
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
+WORKLOAD = {"name": "cfg2"}
+
+
 def make_opt():
     from oracle import port            # Opt is only the argparse-namespace stand-in (no oracle compute on this path)
-    o = port.Opt(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
+    if WORKLOAD["name"] == "cfg5":     # BASELINE configs[4]: 32-frame 128x128 clip (--img-size 128 --sampling-rates 31 1)
+        o = port.Opt(img_size=128, sampling_rates=[31, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
+    else:
+        o = port.Opt(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
     o.scale_idx = o.stop_scale
     o.Noise_Amps = [1.0] + [0.07] * (o.stop_scale - 1)      # survey-observed amplitudes; the finest one is computed at iteration 0
     s0, t0 = port.scale_size(0, o), port.time_depth(0, o)
@@ -60,6 +66,9 @@ def level_shape(o, idx):
 
 
 def workload_name(o):
+    if WORKLOAD["name"] == "cfg5":
+        return ("configs[4]: 3D HP-VAE-GAN, synthetic 32-frame 128x128 clip, vae-levels 3, nfc 64, rates 31 1, "
+                "finest level %d of %d (GAN), batch 1 per GPU" % (o.scale_idx, o.stop_scale))
     return ("configs[1]: train_video.py 3D HP-VAE-GAN, synthetic 16-frame 64x64 clip, vae-levels 3, nfc 64, rates 5 3 1, "
             "finest level %d of %d (GAN), batch 1 per GPU" % (o.scale_idx, o.stop_scale))
 
@@ -351,12 +360,12 @@ def run_hpvg(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat NCCL grad all-reduce)" % world if distributed else "single GPU",
                            "l2": "no explicit flush: one iteration touches %.0f MB of activations (peak allocated), above the 126 MB L2" % peak_mb,
-                           "conv_gflop_per_iter": CONV_GFLOP_PER_ITER,
+                           "conv_gflop_per_iter": CONV_GFLOP_PER_ITER if WORKLOAD["name"] == "cfg2" else 12650.99,
                            "launch": ("one CUDA graph replay per iteration (%d libhpvg kernels recorded)" % launches_per_iter) if use_graph
                            else "eager launches"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-                "model_tflops": value * CONV_GFLOP_PER_ITER / 1e3 / world,
+                "model_tflops": value * (CONV_GFLOP_PER_ITER if WORKLOAD["name"] == "cfg2" else 12650.99) / 1e3 / world,
                 "generation": {"metric": "generated_frames_per_s", "value": world * frames[0] / (ms_gen * 1e-3), "unit": "frames/s",
                                "draws": args.draws, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
                                "ms_per_draw": ms_gen / draws_rank,
@@ -389,7 +398,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128)")
     args = ap.parse_args()
+    WORKLOAD["name"] = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -231,6 +231,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint64_t a_base = umma_desc(s_slab, 16, SLAB_W * 128, 2);
       const uint64_t b_base = umma_desc(s_b, 16, 1024, 2);
       uint32_t bstage = 0, bphase = 0;
+      // phase parity of every slab barrier: a slab that lies outside the volume (zero padding) is neither loaded nor waited
+      // for, so its barrier does not complete in that unit — the parity is tracked per slab, not derived from the unit count
+      uint32_t slab_phase = 0;
       int it = 0;
       long long t_start = clock64(), t_bwait = 0, t_swait = 0;
       for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
@@ -278,7 +281,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     // first touch: one MMA per accumulator so that each gets its own "overwrite" flag
                     if (!((waited >> j) & 1u)) {
                       if (p.dbg) t_swait -= clock64();
-                      mbar_wait(bar_slab_full(j), (uint32_t)(it & 1));
+                      mbar_wait(bar_slab_full(j), (slab_phase >> j) & 1u);
+                      slab_phase ^= 1u << j;
                       if (p.dbg) t_swait += clock64();
                       tc_fence_after();
                       waited |= 1u << j;
@@ -353,7 +357,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               if ((waited >> slot) & 1u) continue;
               waited |= 1u << slot;
 #pragma unroll
-              for (int kc = 0; kc < KCHUNKS; ++kc) mbar_wait(bar_slab_full(slot * KCHUNKS + kc), (uint32_t)(it & 1));
+              for (int kc = 0; kc < KCHUNKS; ++kc) {
+                const int si = slot * KCHUNKS + kc;
+                mbar_wait(bar_slab_full(si), (slab_phase >> si) & 1u);
+                slab_phase ^= 1u << si;
+              }
             }
             if (p.dbg) t_swait += clock64();
             tc_fence_after();

@@ -307,3 +307,35 @@ def test_full_size_batchnorm_statistics():
     # LeakyReLU(0.2) of a zero-mean unit-variance channel: compare with the same transform of the normalised conv output
     ref = F.leaky_relu((yf - yf.mean(0)) / torch.sqrt(yf.var(0, unbiased=False) + 1e-5) * m.norm.weight.detach() + m.norm.bias.detach(), 0.2)
     assert rel_err(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("cin,cout,vol,pad", [(64, 64, (37, 64, 64), 1), (64, 64, (9, 130, 70), 1), (128, 64, (12, 48, 40), 1),
+                                              (64, 64, (22, 50, 50), 0), (64, 3, (37, 64, 64), 1)])
+def test_tcgen05_kernels_with_several_units_per_cta(cin, cout, vol, pad):
+    """volumes with more work units than SMs (every CTA loops over several units, with different zero-padding patterns per
+    unit: BASELINE configs[4], 32 x 128 x 128, is such a case): tcgen05 kernels against the library's CUDA-core kernels"""
+    from hpvg import lib, ops
+    d, h, w = vol
+    x = _wide_randn((1, d, h, w, cin), 11)
+    gen = torch.Generator(device='cuda').manual_seed(12)
+    wt = (torch.randn((cout, cin, 3, 3, 3), device='cuda', generator=gen) * 0.02).bfloat16().float()
+    bias = torch.randn((cout,), device='cuda', generator=gen)
+    wide_out = cout >= 64
+    try:
+        lib.set_conv_backend(lib.BACKEND_TCGEN05)
+        y = ops.conv_raw(x, wt, bias, pad, False, wide_out)
+        if wide_out:
+            g = _wide_randn(tuple(y.shape), 13)
+            gx = ops.conv_raw(g, wt, None, 2 - pad, True, True)
+            dw, _ = ops.wgrad_raw(x, g, pad, tuple(wt.shape))
+        lib.set_conv_backend(lib.BACKEND_DIRECT)
+        y_ref = ops.conv_raw(x, wt, bias, pad, False, wide_out)
+        if wide_out:
+            gx_ref = ops.conv_raw(g, wt, None, 2 - pad, True, True)
+            dw_ref, _ = ops.wgrad_raw(x, g, pad, tuple(wt.shape))
+    finally:
+        lib.set_conv_backend(lib.BACKEND_AUTO)
+    assert rel_err(y.float(), y_ref.float()) < 3e-3          # both round the same fp32 sums to bf16 (thin output: fp32)
+    if wide_out:
+        assert rel_err(gx.float(), gx_ref.float()) < 3e-3
+        assert rel_err(dw, dw_ref) < 1e-3
