@@ -12,9 +12,39 @@ V = D * H * W
 flush = torch.empty(256 * 2**20 // 4, device=dev)
 
 
+GRAPHED = os.environ.get("BENCH_GRAPHED") == "1"
+
+
 def timeit(fn, name, flops=None, nbytes=None):
     for _ in range(3):
         fn()
+    if GRAPHED:
+        # 10 launches recorded into a CUDA graph and replayed: no host launch latency between the events (inputs stay in L2)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(10):
+                fn()
+        gr.replay()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 100.0)
+        ts.sort()
+        med = ts[len(ts) // 2]
+        msg = "%-34s graphed x10: %8.1f us per launch" % (name, med)
+        if flops:
+            msg += "  %7.1f TFLOP/s" % (flops / med / 1e6)
+        if nbytes:
+            msg += "  %7.1f GB/s" % (nbytes / med / 1e3)
+        print(msg, flush=True)
+        return
     ts = []
     for _ in range(reps):
         flush.zero_()

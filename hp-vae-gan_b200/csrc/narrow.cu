@@ -12,6 +12,7 @@
 // FMA / HBM bound; the kernels stage a halo tile of the thin tensor and the filter in shared memory and keep
 // 24-128 accumulators per thread.  (The wide -> thin direction runs on tcgen05: conv_tc.cu, NOUT = 16.)
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hpvg {
 
@@ -156,6 +157,181 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// thin -> wide convolution on the tensor cores: implicit GEMM [voxels x K] x [K x 64] with K = taps * Cin (81 -> 88),
+// TF32 mma.sync.m16n8k8 (fp32 operands rounded to 10-bit mantissas, fp32 accumulation).  K = 81 is far below a tcgen05
+// tile and the layer is bound by the 8.4 MB bf16 output, so the legacy warp-level MMA is the right size here: it removes
+// the 5184 FFMA per voxel of the CUDA-core kernel above (kept as the fallback for Cin = 4 / odd shapes).
+// Block = 8 warps, tile = 8 x 32 output voxels; warp = one tile row = 2 m16 tiles x 8 n8 tiles (64 accumulators).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EM_KMAX = 88;                      // K padded to a multiple of 8 (Cin <= 3: 27 * 3 = 81)
+constexpr int EM_BSTRIDE = 72;                   // floats per filter row in smem: 72 = 64 + 8 keeps the B loads conflict free
+constexpr int EM_HW = EX_TW + 4;                 // halo row length
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KDT>
+__global__ void __launch_bounds__(256, 2) expand_conv_mma_kernel(const float* __restrict__ x, const float* __restrict__ w_tco,
+                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                                 ConvGeom g, int act, float slope, float* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t em_smem[];
+  constexpr int TAPS = KDT * 9;
+  const int K = TAPS * g.Cin;                                   // <= 81
+  const int ksteps = (K + 7) >> 3;
+  uint32_t* bs = reinterpret_cast<uint32_t*>(em_smem);          // [EM_KMAX][EM_BSTRIDE] tf32 filter, k = tap * Cin + ci
+  uint32_t* xs = bs + EM_KMAX * EM_BSTRIDE;                     // [Cin][KDT][EX_HH][EM_HW] tf32 halo tile
+  constexpr int MAIN_WORDS = EM_KMAX * EM_BSTRIDE + 3 * KDT * EX_HH * EM_HW;
+  constexpr int STAGE_WORDS = 8 * 32 * 128 / 4;                 // the epilogue staging tile (8 warps x 32 voxels) overlays bs / xs
+  int* koff = reinterpret_cast<int*>(em_smem) + (MAIN_WORDS > STAGE_WORDS ? MAIN_WORDS : STAGE_WORDS);   // [EM_KMAX]
+  float* red = reinterpret_cast<float*>(koff + EM_KMAX);        // [128] BatchNorm partial sums
+  float* bias_s = red + 128;                                    // [64]
+  const int tiles_w = (g.Wo + EX_TW - 1) / EX_TW, tiles_h = (g.Ho + EX_TH - 1) / EX_TH;
+  int b = blockIdx.x;
+  const int w0 = (b % tiles_w) * EX_TW;
+  b /= tiles_w;
+  const int h0 = (b % tiles_h) * EX_TH;
+  b /= tiles_h;
+  const int od = b % g.Do;
+  const int n = b / g.Do;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+
+  // filter: [K][64] fp32 image (hpvg_pack_weights_expand), 128-bit copies into rows of EM_BSTRIDE words; rows >= K are zero
+  for (int i = tid; i < EM_KMAX * 16; i += 256) {
+    const int k = i >> 4, c4 = i & 15;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k < K) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(w_tco) + i);
+      v = make_uint4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
+    }
+    *reinterpret_cast<uint4*>(bs + k * EM_BSTRIDE + c4 * 4) = v;
+  }
+  // halo tile: one warp per (ci, kd, row), lanes along w (no per-element index arithmetic)
+  const size_t in_sp = (size_t)g.Di * g.Hi * g.Wi;
+  for (int r = warp; r < g.Cin * KDT * EX_HH; r += 8) {
+    const int hh = r % EX_HH, kd = (r / EX_HH) % KDT, ci = r / (EX_HH * KDT);
+    const int id = od + kd - g.pad_d, ih = h0 + hh - g.pad;
+    const bool row_ok = id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi;
+    const float* src = x + ((size_t)n * g.Cin + ci) * in_sp + ((size_t)(row_ok ? id : 0) * g.Hi + (row_ok ? ih : 0)) * g.Wi;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ww = lane + 32 * half;
+      if (ww < EM_HW) {
+        const int iw = w0 + ww - g.pad;
+        const float v = (row_ok && iw >= 0 && iw < g.Wi) ? __ldg(src + iw) : 0.f;
+        xs[r * EM_HW + ww] = to_tf32(v);
+      }
+    }
+  }
+  if (tid < EM_KMAX) {
+    int o = 0;
+    if (tid < K) {
+      const int tap = tid / g.Cin, ci = tid % g.Cin;
+      const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+      o = ((ci * KDT + kd) * EX_HH + kh) * EM_HW + kw;
+    }
+    koff[tid] = o;
+  }
+  if (tid < 128) red[tid] = 0.f;
+  if (tid < 64) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
+  __syncthreads();
+
+  // warp = tile row `warp`: 2 m16 tiles (columns 0-15, 16-31) x 8 n8 tiles = 64 accumulators per thread
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  const int rowbase = warp * EM_HW + gq;
+#pragma unroll 1
+  for (int s = 0; s < ksteps; ++s) {
+    const int k0 = 8 * s + tq;
+    const int o0 = koff[k0], o1 = koff[k0 + 4];
+    uint32_t bf[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      bf[nt][0] = bs[k0 * EM_BSTRIDE + nt * 8 + gq];
+      bf[nt][1] = bs[(k0 + 4) * EM_BSTRIDE + nt * 8 + gq];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t a[4];
+      a[0] = xs[rowbase + mt * 16 + o0];
+      a[1] = xs[rowbase + mt * 16 + 8 + o0];
+      a[2] = xs[rowbase + mt * 16 + o1];
+      a[3] = xs[rowbase + mt * 16 + 8 + o1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32(acc[mt][nt], a, bf[nt][0], bf[nt][1]);
+    }
+  }
+  __syncthreads();                       // filter / halo stages are dead: reuse them as the bf16 staging tile
+
+  // epilogue: bias, activation, bf16 -> swizzled staging [32 voxels][64] per warp -> coalesced stores; BatchNorm sums
+  uint8_t* stg = em_smem + warp * (32 * 128);
+  const int oh = h0 + warp;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int vox = mt * 16 + gq + 8 * hrow;                  // voxel = column inside the warp's tile row
+      const bool ok = oh < g.Ho && w0 + vox < g.Wo;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float a0 = acc[mt][nt][2 * hrow] + bias_s[nt * 8 + 2 * tq], a1 = acc[mt][nt][2 * hrow + 1] + bias_s[nt * 8 + 2 * tq + 1];
+        if (act == HPVG_ACT_LRELU) {
+          a0 = a0 > 0.f ? a0 : a0 * slope;
+          a1 = a1 > 0.f ? a1 : a1 * slope;
+        }
+        if (!ok) a0 = a1 = 0.f;
+        *reinterpret_cast<uint32_t*>(stg + vox * 128 + ((nt ^ (vox & 7)) << 4) + 4 * tq) = pack_bf16x2(a0, a1);
+      }
+    }
+  }
+  __syncwarp();
+  if (oh < g.Ho) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int vox = (lane >> 3) + 4 * i, chunk = lane & 7;
+      if (w0 + vox < g.Wo) {
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + vox * 128 + ((chunk ^ (vox & 7)) << 4));
+        *reinterpret_cast<uint4*>(y + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + w0 + vox) * 64 + chunk * 8) = v;
+      }
+    }
+  }
+  if (stats) {
+    // lane -> channels 2*lane, 2*lane+1 over the warp's 32 staged voxels (invalid voxels were staged as zeros)
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll 8
+    for (int vox = 0; vox < 32; ++vox) {
+      const uint32_t pr = *reinterpret_cast<const uint32_t*>(stg + vox * 128 + ((chunk ^ (vox & 7)) << 4) + within);
+      const float2 f = unpack_bf16x2(pr);
+      s0 += f.x; s1 += f.y;
+      q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+    }
+    atomicAdd(red + 2 * lane, s0);
+    atomicAdd(red + 2 * lane + 1, s1);
+    atomicAdd(red + 64 + 2 * lane, q0);
+    atomicAdd(red + 64 + 2 * lane + 1, q1);
+    __syncthreads();
+    if (tid < 128) atomicAdd(stats + tid, red[tid]);
+  }
+}
+
+static size_t expand_mma_smem(int KD) {
+  const size_t main_bytes = (size_t)(EM_KMAX * EM_BSTRIDE + 3 * KD * EX_HH * EM_HW) * 4;
+  const size_t stage_bytes = 8 * 32 * 128;                       // staging overlays the filter/halo
+  return (main_bytes > stage_bytes ? main_bytes : stage_bytes) + EM_KMAX * 4 + 128 * 4 + 64 * 4;
+}
+
 bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* mask_src) {
   return x_fmt == HPVG_FMT_NCDHW_F32 && y_fmt == HPVG_FMT_NDHWC_BF16 && g.Cin <= 4 && g.Cout == 64 && mask_src == nullptr;
 }
@@ -179,6 +355,24 @@ int expand_conv(const void* x, const float* w, const float* w_tco, const float* 
                 int act, float slope, float* stats, cudaStream_t st) {
   const int tiles_w = (int)cdiv(g.Wo, EX_TW), tiles_h = (int)cdiv(g.Ho, EX_TH);
   const long long blocks = (long long)g.N * g.Do * tiles_h * tiles_w;
+  static const bool no_mma = getenv("HPVG_EXPAND_FMA") != nullptr;     // development aid: force the CUDA-core kernel
+  if (w_tco != nullptr && g.Cin <= 3 && !no_mma) {
+    const size_t smem_mma = expand_mma_smem(g.KD);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(expand_conv_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(expand_conv_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr_done = true;
+    }
+    if (g.KD == 3)
+      expand_conv_mma_kernel<3><<<(unsigned)blocks, 256, smem_mma, st>>>(reinterpret_cast<const float*>(x), w_tco, bias,
+                                                                        reinterpret_cast<__nv_bfloat16*>(y), g, act, slope, stats);
+    else
+      expand_conv_mma_kernel<1><<<(unsigned)blocks, 256, smem_mma, st>>>(reinterpret_cast<const float*>(x), w_tco, bias,
+                                                                        reinterpret_cast<__nv_bfloat16*>(y), g, act, slope, stats);
+    HPVG_CHECK_LAUNCH("expand_conv_mma_kernel");
+    return 0;
+  }
   const size_t smem = ((size_t)g.taps * g.Cin * 64 + (size_t)g.Cin * g.KD * EX_HH * EX_HW) * sizeof(float);
   if (g.KD == 3)
     expand_conv_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),

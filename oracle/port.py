@@ -70,6 +70,20 @@ def store_grad(t):
     return _RoundGradBf16.apply(t) if _STORAGE[-1] == 'bf16' else t
 
 
+def _tf32(t):
+    """round to TF32 (10 explicit mantissa bits), as cvt.rna.tf32.f32 does for the operands of the 3 -> 64 head layers"""
+    bits = t.detach().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def head_operand(t, w):
+    """operands (input or weight) of a thin -> wide layer (Cin <= 3, Cout = 64): the CUDA path multiplies them on the
+    tensor cores in TF32; gradients pass straight through"""
+    if _STORAGE[-1] == 'bf16' and t.dtype == torch.float32 and w.shape[1] <= 3 and w.shape[0] == 64:
+        return t + (_tf32(t) - t).detach()
+    return t
+
+
 def mma_weight(w):
     """weights of the tcgen05 layers (Cin in {64,128} with Cout a multiple of 64, and the 64 -> nc_im / 64 -> 1 tails)
     are fed to the tensor core in bf16; the master weight and its gradient stay fp32 (straight-through)"""
@@ -107,7 +121,8 @@ def batch_norm_train(sd, prefix, y):
 
 def conv_block(sd, prefix, x, pad):
     """ConvBlock3D/2D: conv [+ BatchNorm] [+ LeakyReLU]; the mu/logvar heads have neither (networks_3d.py:48-56, :99-100)"""
-    y = store(conv(x, mma_weight(sd[prefix + 'conv.weight']), sd[prefix + 'conv.bias'], pad))
+    w = sd[prefix + 'conv.weight']
+    y = store(conv(head_operand(x, w), head_operand(mma_weight(w), w), sd[prefix + 'conv.bias'], pad))
     if prefix + 'norm.weight' in sd:
         y = store(F.leaky_relu(batch_norm_train(sd, prefix + 'norm.', y), SLOPE))
     return y
@@ -130,7 +145,8 @@ def spectral_weight(sd, prefix, training=True):
 
 def conv_block_sn(sd, prefix, x, pad):
     """ConvBlock3DSN/2DSN with bn=True: spectral-norm conv + LeakyReLU, no BatchNorm (networks_3d.py:59-70)"""
-    y = conv(x, mma_weight(spectral_weight(sd, prefix + 'conv.')), sd[prefix + 'conv.bias'], pad)
+    w = mma_weight(spectral_weight(sd, prefix + 'conv.'))
+    y = conv(head_operand(x, w), head_operand(w, w), sd[prefix + 'conv.bias'], pad)
     return store(F.leaky_relu(store_grad(y), SLOPE))
 
 
