@@ -100,8 +100,11 @@ if which in ("all", "ew"):
     out = torch.empty_like(xw)
     timeit(lambda: lib.call("hpvg_bn_apply_lrelu", xw.data_ptr(), ss.data_ptr(), out.data_ptr(), V, 64, 0.2, torch.cuda.current_stream().cuda_stream),
            "bn_apply_lrelu", None, V * 256)
-    timeit(lambda: lib.call("hpvg_lrelu_bwd", gw.data_ptr(), xw.data_ptr(), out.data_ptr(), V * 64, 0.2, torch.cuda.current_stream().cuda_stream),
+    timeit(lambda: lib.call("hpvg_lrelu_bwd", gw.data_ptr(), xw.data_ptr(), out.data_ptr(), V * 64, 0.2, 64, None, torch.cuda.current_stream().cuda_stream),
            "lrelu_bwd", None, V * 384)
+    chs = torch.zeros(64, device=dev)
+    timeit(lambda: lib.call("hpvg_lrelu_bwd", gw.data_ptr(), xw.data_ptr(), out.data_ptr(), V * 64, 0.2, 64, chs.data_ptr(), torch.cuda.current_stream().cuda_stream),
+           "lrelu_bwd + channel sum", None, V * 384)
     timeit(lambda: ops.channel_sum(xw), "channel_sum wide", None, V * 128)
 if which == "clk":
     packed = ops.pack_weights(w64, 64, 64, 27, False)

@@ -803,7 +803,9 @@ int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_
                             void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && (256 % (C / 8)) == 0, "bn_lrelu_bwd_apply: C=%d must be a multiple of 8 dividing 2048", C);
   const long long nvec = nvox * (C / 8);
-  bn_lrelu_bwd_apply_kernel<<<ew_blocks(nvec, 256), 256, 7 * C * sizeof(float), ST(stream)>>>(
+  // with the fused channel sum every block ends with C global atomics on the same C addresses: keep the grid at 2 CTAs per SM
+  const int blocks = want_chsum ? min(ew_blocks(nvec, 256), 2 * num_sms()) : ew_blocks(nvec, 256);
+  bn_lrelu_bwd_apply_kernel<<<blocks, 256, 7 * C * sizeof(float), ST(stream)>>>(
       reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift, mean_invstd, sums,
       reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr);
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
@@ -817,7 +819,8 @@ int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long 
                  "lrelu_bwd: fused channel sum needs C (=%d) a multiple of 8 dividing 2048", C);
   if (chsum) MEMSET0(chsum, C * sizeof(float), ST(stream), "lrelu_bwd");
   const long long nvec = numel / 8;
-  lrelu_bwd_kernel<<<ew_blocks(nvec, 256), 256, chsum ? C * sizeof(float) : 0, ST(stream)>>>(
+  const int blocks = chsum ? min(ew_blocks(nvec, 256), 2 * num_sms()) : ew_blocks(nvec, 256);
+  lrelu_bwd_kernel<<<blocks, 256, chsum ? C * sizeof(float) : 0, ST(stream)>>>(
       reinterpret_cast<const uint4*>(gout), reinterpret_cast<const uint4*>(out_saved), reinterpret_cast<uint4*>(gz), nvec, slope, C,
       chsum);
   HPVG_CHECK_LAUNCH("lrelu_bwd");

@@ -541,6 +541,158 @@ __global__ void __launch_bounds__(256) outer_corr_reduce_kernel(const float* __r
     dw[((size_t)j * 64 + k) * taps + t] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same reduction on the tensor cores:  OUT[c][k] = sum_p A[c][p] * B[p][k]  with A[c][p] = THIN[j_c][p + s_c]
+// (fp32 halo tile, rounded to bf16 as it is loaded into the fragment) and B = the bf16 WIDE tile, read transposed with
+// ldmatrix.  mma.sync.m16n8k16 bf16, fp32 accumulation; 6 warps = 6 m16 tiles of (j, t) combinations (96 >= 27 * 3 + 1:
+// the extra row multiplies by 1.0 and yields the channel sum of WIDE), each warp all 8 n8 tiles of the 64 channels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int OM_WARPS = 6, OM_THREADS = 32 * OM_WARPS, OM_ROWS = 16 * OM_WARPS;
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <int KDT>
+__global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const OuterCorrParams p) {
+  extern __shared__ __align__(16) uint8_t osm[];
+  constexpr int TAPS = KDT * 9;
+  constexpr int WT_BYTES = OC_TH * OC_TW * 128;
+  float* th = reinterpret_cast<float*>(osm + WT_BYTES);                 // [J][KDT][OC_HH][OC_HW] then OC_ONES ones
+  const int th_elems = p.J * KDT * OC_HH * OC_HW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int ncomb = TAPS * p.J;
+  // halo offsets of this thread's two combination rows (gq and gq + 8 of m-tile `warp`)
+  int off[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = warp * 16 + gq + 8 * h;
+    off[h] = 0;
+    if (c < ncomb) {
+      const int j = c / TAPS, t = c % TAPS;
+      const int kd = t / 9, kh = (t % 9) / 3, kw = t % 3;
+      const int dd = (KDT == 3) ? (p.sign * kd + (p.sign > 0 ? 0 : 2)) : 0;
+      const int hh = p.sign * kh + (p.sign > 0 ? 0 : 2);
+      const int ww = p.sign * kw + (p.sign > 0 ? 0 : 2);
+      off[h] = ((j * KDT + dd) * OC_HH + hh) * OC_HW + ww;
+    } else if (c == ncomb && p.want_sum) {
+      off[h] = th_elems;                                               // a run of ones: OUT row = channel sum of WIDE
+    }
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  for (int i = tid; i < OC_ONES; i += OM_THREADS) th[th_elems + i] = 1.0f;
+
+  const uint32_t s_wt = smem_u32(osm);
+  // ldmatrix row address of this lane: voxel (lane & 7) + 8 * ((lane >> 3) & 1) of the k16 step, channels of n-tile (lane >> 4)
+  const uint32_t ld_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 128 + (lane >> 4) * 16);
+  const size_t thin_sp = (size_t)p.Dt * p.Ht * p.Wt;
+  for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    long long b = tile;
+    const int w0 = (int)(b % p.tiles_w) * OC_TW;
+    b /= p.tiles_w;
+    const int h0 = (int)(b % p.tiles_h) * OC_TH;
+    b /= p.tiles_h;
+    const int d0 = (int)(b % p.Dw);
+    const int n = (int)(b / p.Dw);
+    __syncthreads();
+    for (int i = tid; i < OC_TH * OC_TW * 8; i += OM_THREADS) {
+      const int chunk = i & 7, vox = i >> 3;
+      const int hh = vox / OC_TW, ww = vox % OC_TW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (h0 + hh < p.Hw && w0 + ww < p.Ww)
+        v = __ldg(reinterpret_cast<const uint4*>(p.wide + ((((size_t)n * p.Dw + d0) * p.Hw + h0 + hh) * p.Ww + w0 + ww) * 64) + chunk);
+      reinterpret_cast<uint4*>(osm)[i] = v;
+    }
+    const int od = d0 + p.shift_d - (KDT == 3 ? (p.sign > 0 ? 0 : 2) : 0);
+    const int oh = h0 + p.shift - (p.sign > 0 ? 0 : 2), ow = w0 + p.shift - (p.sign > 0 ? 0 : 2);
+    for (int r = warp; r < p.J * KDT * OC_HH; r += OM_WARPS) {
+      const int hh = r % OC_HH, dd = (r / OC_HH) % KDT, j = r / (OC_HH * KDT);
+      const int id = od + dd, ih = oh + hh;
+      const bool row_ok = id >= 0 && id < p.Dt && ih >= 0 && ih < p.Ht;
+      const float* src = p.thin + ((size_t)n * p.J + j) * thin_sp + ((size_t)(row_ok ? id : 0) * p.Ht + (row_ok ? ih : 0)) * p.Wt;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ww = lane + 32 * half;
+        if (ww < OC_HW) {
+          const int iw = ow + ww;
+          th[r * OC_HW + ww] = (row_ok && iw >= 0 && iw < p.Wt) ? __ldg(src + iw) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < OC_TH * OC_TW / 16; ++ks) {              // 16 voxels per step: half a tile row
+      const int hh = ks >> 1, ww = (ks & 1) * 16;
+      const int base = hh * OC_HW + ww + 2 * tq;
+      uint32_t a[4];
+      {
+        const float* r0 = th + base + off[0];
+        const float* r1 = th + base + off[1];
+        a[0] = pack_bf16x2(r0[0], r0[1]);
+        a[1] = pack_bf16x2(r1[0], r1[1]);
+        a[2] = pack_bf16x2(r0[8], r0[9]);
+        a[3] = pack_bf16x2(r1[8], r1[9]);
+      }
+      const uint32_t wrow = s_wt + (uint32_t)(ks * 16) * 128u + ld_lane;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {                              // n-tile pairs (2 np, 2 np + 1)
+        uint32_t bfrag[4];
+        ldmatrix_x4_trans(bfrag, wrow + np * 32);
+        mma_bf16(acc[2 * np], a, bfrag[0], bfrag[1]);
+        mma_bf16(acc[2 * np + 1], a, bfrag[2], bfrag[3]);
+      }
+    }
+  }
+  // per-block partial [OM_ROWS][64]
+  float* dst = p.partial + (size_t)blockIdx.x * (OM_ROWS * 64);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<float2*>(dst + (warp * 16 + gq) * 64 + nt * 8 + 2 * tq) = make_float2(acc[nt][0], acc[nt][1]);
+    *reinterpret_cast<float2*>(dst + (warp * 16 + gq + 8) * 64 + nt * 8 + 2 * tq) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+}
+
+// dw[...] = sum over blocks of partial[b][c][k]; a block owns 32 consecutive (c, k) entries (one 128-byte line of every
+// partial row) and walks the ~300 rows with 32 threads per entry, so each thread has ~10 independent loads in flight
+__global__ void __launch_bounds__(1024) outer_corr_mma_reduce_kernel(const float* __restrict__ partial, int blocks, int taps, int J,
+                                                                     int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum) {
+  __shared__ float red[32][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int total = OM_ROWS * 64;
+  const int idx = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (idx < total) {
+#pragma unroll 4
+    for (int b = slice; b < blocks; b += 32) s += __ldg(partial + (size_t)b * total + idx);
+  }
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || idx >= total) return;
+#pragma unroll
+  for (int k = 1; k < 32; ++k) s += red[k][lane];
+  const int c = idx >> 6, k = idx & 63;
+  const int ncomb = taps * J;
+  if (c == ncomb) {
+    if (wide_sum) wide_sum[k] = s;
+    return;
+  }
+  if (c > ncomb) return;
+  const int j = c / taps, t = c % taps;
+  if (wide_is_gy)
+    dw[((size_t)k * J + j) * taps + t] = s;
+  else
+    dw[((size_t)j * 64 + k) * taps + t] = s;
+}
+
 bool narrow_wgrad_supported(int x_fmt, int gy_fmt, const ConvGeom& g) {
   if (x_fmt == HPVG_FMT_NCDHW_F32 && gy_fmt == HPVG_FMT_NDHWC_BF16) return g.Cin <= 4 && g.Cout == 64;
   if (x_fmt == HPVG_FMT_NDHWC_BF16 && gy_fmt == HPVG_FMT_NCDHW_F32) return g.Cin == 64 && g.Cout <= 4;
@@ -606,8 +758,33 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
   p.tiles_h = (int)cdiv(p.Hw, OC_TH);
   p.tiles_w = (int)cdiv(p.Ww, OC_TW);
   p.tiles = (long long)p.N * p.Dw * p.tiles_h * p.tiles_w;
-  const int nc = oc_slots(g, head, p.want_sum != 0);
   const int grid = oc_grid(g, head);
+  static const bool no_mma = getenv("HPVG_WGRAD_FMA") != nullptr;      // development aid: force the CUDA-core kernel
+  if (g.taps * p.J + 1 <= OM_ROWS && !no_mma) {
+    const size_t need_mma = (size_t)grid * OM_ROWS * 64 * sizeof(float);
+    if (workspace == nullptr || ws_bytes < need_mma) {
+      set_error("narrow_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need_mma);
+      return -1;
+    }
+    p.partial = reinterpret_cast<float*>(workspace);
+    const size_t smem_mma = (size_t)OC_TH * OC_TW * 128 + ((size_t)p.J * g.KD * OC_HH * OC_HW + OC_ONES) * sizeof(float);
+    static bool attr_mma = false;
+    if (!attr_mma) {
+      cudaFuncSetAttribute(outer_corr_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(outer_corr_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr_mma = true;
+    }
+    if (g.KD == 3)
+      outer_corr_mma_kernel<3><<<grid, OM_THREADS, smem_mma, st>>>(p);
+    else
+      outer_corr_mma_kernel<1><<<grid, OM_THREADS, smem_mma, st>>>(p);
+    HPVG_CHECK_LAUNCH("outer_corr_mma_kernel");
+    outer_corr_mma_reduce_kernel<<<(unsigned)cdiv(OM_ROWS * 64, 32), 1024, 0, st>>>(p.partial, grid, g.taps, p.J, head ? 1 : 0, dw,
+                                                                                p.want_sum ? dbias_wide : nullptr);
+    HPVG_CHECK_LAUNCH("outer_corr_mma_reduce_kernel");
+    return 0;
+  }
+  const int nc = oc_slots(g, head, p.want_sum != 0);
   const size_t need = (size_t)grid * nc * 4 * OC_THREADS * sizeof(float);
   if (workspace == nullptr || ws_bytes < need) {
     set_error("narrow_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need);
