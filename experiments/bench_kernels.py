@@ -133,3 +133,14 @@ if which == "clk":
         d = dbg.view(148, 8).cpu()
         print("  rep", rep, "mean", d[:128, :5].float().mean(0).tolist())
     lib.call("hpvg_debug_set_clock_buffer", None)
+
+if which == "clkw":
+    dbg = torch.zeros(160 * 8, dtype=torch.int64, device=dev)
+    lib.call("hpvg_debug_set_clock_buffer", dbg.data_ptr())
+    for rep in range(3):
+        flush.zero_() if rep == 0 else None
+        ops.wgrad_raw(xw, gw, 1, (64, 64, 3, 3, 3))
+        torch.cuda.synchronize()
+        d = dbg.view(160, 8).cpu()
+        print("rep", rep, "wgrad_tc per-CTA mean [mma loop, wait tma, drain wait acc, drain]", [int(v) for v in d[:147, :4].float().mean(0).tolist()])
+    lib.call("hpvg_debug_set_clock_buffer", None)

@@ -38,6 +38,7 @@ struct WgParams {
   long long bricks_per_split;
   int splits;
   float* partial;             // [splits][taps][Cin][Cout] fp32
+  long long* dbg;             // optional per-CTA phase clocks (development aid)
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -75,6 +76,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  long long t_d0 = 0, t_d1 = 0;   // drain-phase clocks (development aid)
   const long long b_begin = (long long)split * p.bricks_per_split;
   const long long b_end = min(p.num_bricks, b_begin + p.bricks_per_split);
 
@@ -111,10 +113,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);   // A and B MN-major
       uint32_t stage = 0, phase = 0;
       uint32_t first = 1;
+      long long t_start = clock64(), t_wait = 0;
       for (long long b = b_begin; b < b_end; ++b) {
         int n, od, h0, w0;
         if (!decode(b, n, od, h0, w0)) continue;
+        if (p.dbg) t_wait -= clock64();
         mbar_wait(bar_full(stage), phase);
+        if (p.dbg) t_wait += clock64();
         tc_fence_after();
         const uint32_t sa = sbase + stage * WG_STAGE_BYTES;
         const uint64_t b_base = umma_desc(sa + WG_SLAB_STRIDE, 16, 1024, 2);
@@ -137,6 +142,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(bar_acc);
+      if (p.dbg) {
+        const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.dbg[cta * 8 + 0] = clock64() - t_start;    // MMA issue loop
+        p.dbg[cta * 8 + 1] = t_wait;                 // waiting for TMA stages
+      }
     }
     __syncwarp();
   } else {
@@ -146,7 +156,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int n, od, h0, w0;
       if (decode(b, n, od, h0, w0)) { any = true; break; }
     }
+    t_d0 = clock64();
     mbar_wait(bar_acc, 0);
+    t_d1 = clock64();
     tc_fence_after();
     const int q = warp & 3;
     const int m = q * 32 + lane;           // TMEM lane: (m / 64) selects the tap of the pair, m % 64 = ci
@@ -172,6 +184,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                                __uint_as_float(r[4 * j + 3]));
       }
     }
+  }
+  if (p.dbg && threadIdx.x == 64) {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    p.dbg[cta * 8 + 2] = t_d1 - t_d0;              // drain warps waiting for the accumulators
+    p.dbg[cta * 8 + 3] = clock64() - t_d1;         // drain (TMEM -> global partial)
   }
   tc_fence_before();
   __syncthreads();
@@ -224,6 +241,7 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
     return -1;
   }
   p.partial = reinterpret_cast<float*>(workspace);
+  p.dbg = debug_clock_buffer();
   CUtensorMap mx, mg;
   {
     uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.Di, (uint64_t)g.N};
