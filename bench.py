@@ -310,13 +310,15 @@ def run_hpvg(args):
     # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
     _, draws_rank = train.draws_for_rank(args.draws, world, rank)
     draws_rank = max(1, draws_rank)
-    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph)
+    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph, streams=args.gen_streams)
     frames = [0]
 
     def gen_all():
         n = 0
+        sampler.begin()
         for _ in range(draws_rank):
             n += sampler.frames_per_call(sampler.sample())
+        sampler.wait()
         frames[0] = n
     gen_all()
     ms_gen = timed(gen_all, 1)
@@ -368,7 +370,7 @@ def run_hpvg(args):
                 "model_tflops": value * (CONV_GFLOP_PER_ITER if WORKLOAD["name"] == "cfg2" else 12650.99) / 1e3 / world,
                 "generation": {"metric": "generated_frames_per_s", "value": world * frames[0] / (ms_gen * 1e-3), "unit": "frames/s",
                                "draws": args.draws, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
-                               "ms_per_draw": ms_gen / draws_rank,
+                               "ms_per_draw": ms_gen / draws_rank, "streams": sampler.nstreams,
                                "note": "draws split over ranks, no collective; rank 0's share timed x N (equal shares)"}}
         if distributed:
             line["allreduce_bytes_per_step"] = trainer.allreduce_bytes // max(1, trainer.iterations)
@@ -395,6 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
     ap.add_argument("--draws", type=int, default=256, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
+    ap.add_argument("--gen-streams", type=int, default=4, help="independent draws in flight on separate CUDA streams (generation leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")

@@ -377,6 +377,25 @@ class BnLrelu(Function):
         return gy, None, dgamma, dbeta, None, None, None, None, None, None
 
 
+_BN_TRACK = [True]
+
+
+class bn_running_stats:
+    """Context: BatchNorm layers inside it do not advance running_mean / running_var / num_batches_tracked.  Used by the
+    multi-stream sampler, where concurrent draws would race on those buffers; they are never read by the path (the
+    generator is never put in eval mode)."""
+
+    def __init__(self, track):
+        self.track = track
+
+    def __enter__(self):
+        self.prev = _BN_TRACK[0]
+        _BN_TRACK[0] = self.track
+
+    def __exit__(self, *a):
+        _BN_TRACK[0] = self.prev
+
+
 class ConvBnLrelu(Function):
     """ConvBlock3D/2D as ONE autograd node (reference modules/networks_3d.py:48-56).
     forward : conv (+bias) with BatchNorm sums fused into its epilogue -> finalize + normalise + affine + LeakyReLU (1 launch)
@@ -394,8 +413,10 @@ class ConvBnLrelu(Function):
         scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
         mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
         out = torch.empty_like(y)
-        lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
-                 _ptr(nbt), float(momentum), float(eps), _ptr(scale_shift), _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
+        track = _BN_TRACK[0]
+        lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean if track else None),
+                 _ptr(running_var if track else None), _ptr(nbt if track else None), float(momentum), float(eps), _ptr(scale_shift),
+                 _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
         ctx.pad, ctx.slope, ctx.c, ctx.nvox, ctx.has_bias = pad, slope, c, nvox, bias is not None
         ctx.save_for_backward(x, w, y, scale_shift, mean_invstd)
         return out
