@@ -82,9 +82,13 @@ class GradBucket:
 class ScaleTrainer:
     """state of one `train(opt, netG)` call of the reference: optimizers and the iteration body"""
 
-    def __init__(self, opt, netG, netD=None, distributed=False, dims=3, capturable=False):
+    def __init__(self, opt, netG, netD=None, distributed=False, dims=3, capturable=False, overlap=None):
         """capturable=True builds the Adam optimizers with device-side step counters (torch's `capturable` flag: same
-        arithmetic), which capture() needs to record the whole iteration into one CUDA graph."""
+        arithmetic), which capture() needs to record the whole iteration into one CUDA graph.
+        overlap (default: on at GAN scales on CUDA): the generator's 'rec' pass runs on a second CUDA stream, concurrently
+        with the critic's pass on the real clip; autograd then runs the backward of the reconstruction path on that stream
+        too, concurrently with the adversarial path.  Same kernels, same arithmetic, same RNG order (draws are ordered by
+        the host); the two passes touch disjoint buffers (the 'rand' pass starts after the join)."""
         _train_defaults(opt)
         self.opt, self.netG, self.netD, self.dims = opt, netG, netD, dims
         self.gan = opt.vae_levels < opt.scale_idx + 1
@@ -100,6 +104,11 @@ class ScaleTrainer:
         self.allreduce_bytes = 0
         self.iterations = 0
         self.graph = None
+        self.overlap = (self.gan and torch.cuda.is_available()) if overlap is None else bool(overlap)
+        self._side = None
+        if self.overlap:
+            # parameters receive gradients from nodes on several streams by design; the engine synchronises them
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
     # train_video.py:126 — drawn every iteration, also at VAE scales where it is unused (keeps the RNG stream aligned)
     def _noise_init(self, device):
@@ -135,7 +144,16 @@ class ScaleTrainer:
         if self.iterations == 0 and len(opt.Noise_Amps) < opt.scale_idx + 1:
             self.calc_noise_amp(real, real_zero)
         out = {}
-        generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
+        side = None
+        if self.gan and self.overlap and real.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=real.device)
+            side, main = self._side, torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
+        else:
+            generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
         if not self.gan:
             rec_vae_loss = F.mse_loss(generated, real) + F.mse_loss(generated_vae, real_zero)
             kl_loss = kl_criterion(mu, logvar)
@@ -144,6 +162,10 @@ class ScaleTrainer:
         else:
             D.zero_grad()
             errD_real = -D(real).mean()
+            if side is not None:
+                # (a third stream for this pass, so that its backward overlaps the fake / gradient-penalty backward, was
+                # measured: no further gain)
+                torch.cuda.current_stream().wait_stream(side)      # the 'rand' pass shares BatchNorm buffers with 'rec'
             fake, _ = G(noise_init, opt.Noise_Amps, noise_init=noise_init, mode="rand")
             errD_fake = D(fake.detach()).mean()
             gradient_penalty = calc_gradient_penalty(D, real, fake, opt.lambda_grad, real.device)
