@@ -116,7 +116,8 @@ def packed_for(w, cout, cin, taps, transposed, rows):
     by the 'rec' and 'rand' generator passes and, transposed, by their data-gradient passes within one iteration"""
     key = (bool(transposed), rows)
     stamp = (w._version, _PACK_GEN[0], w.data_ptr())
-    cache = getattr(w, '_hpvg_packs', None)
+    owner = w._base if (w._base is not None and w._base.shape == w.shape) else w    # WeightProxy hands out full views
+    cache = getattr(owner, '_hpvg_packs', None)
     if cache is not None:
         hit = cache.get(key)
         if hit is not None and hit[0] == stamp:
@@ -124,7 +125,7 @@ def packed_for(w, cout, cin, taps, transposed, rows):
     packed = pack_weights(w, cout, cin, taps, transposed, rows=rows)
     if cache is None:
         try:
-            w._hpvg_packs = cache = {}
+            owner._hpvg_packs = cache = {}
         except (AttributeError, RuntimeError):
             return packed
     cache[key] = (stamp, packed)
@@ -135,7 +136,8 @@ def expand_image_for(w, cin, taps, transposed):
     """float32 [taps][cin][64] filter image for the thin -> wide kernel, cached on the weight like packed_for()"""
     key = ('expand', bool(transposed))
     stamp = (w._version, _PACK_GEN[0], w.data_ptr())
-    cache = getattr(w, '_hpvg_packs', None)
+    owner = w._base if (w._base is not None and w._base.shape == w.shape) else w
+    cache = getattr(owner, '_hpvg_packs', None)
     if cache is not None:
         hit = cache.get(key)
         if hit is not None and hit[0] == stamp:
@@ -144,7 +146,7 @@ def expand_image_for(w, cin, taps, transposed):
     lib.call("hpvg_pack_weights_expand", _ptr(w), _ptr(out), cin, taps, int(transposed), _stream())
     if cache is None:
         try:
-            w._hpvg_packs = cache = {}
+            owner._hpvg_packs = cache = {}
         except (AttributeError, RuntimeError):
             return out
     cache[key] = (stamp, out)
@@ -396,6 +398,57 @@ class bn_running_stats:
         _BN_TRACK[0] = self.prev
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# weight gradients on a second stream.  A weight gradient is needed only by the optimizer, while the data gradient is on
+# the critical path of the backward sweep.  WeightProxy is an identity node created under the side stream's context, so
+# autograd runs ITS backward on that stream (with the engine's own event synchronisation before it and before the
+# gradient is accumulated); the convolution node only deposits (x, gy) and returns a placeholder.
+# ---------------------------------------------------------------------------------------------------------------
+_WGRAD_STREAM = [None]
+
+
+class wgrad_stream:
+    """Context: convolution blocks built inside it compute their weight gradients on `stream` during backward."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        self.prev = _WGRAD_STREAM[0]
+        _WGRAD_STREAM[0] = self.stream
+
+    def __exit__(self, *a):
+        _WGRAD_STREAM[0] = self.prev
+
+
+class _Deferred:
+    __slots__ = ("slot",)
+
+    def __init__(self):
+        self.slot = None
+
+
+class WeightProxy(Function):
+    @staticmethod
+    def forward(ctx, w, token):
+        ctx.token = token
+        ctx.wshape = tuple(w.shape)
+        return w.view_as(w)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, placeholder):
+        job, ctx.token.slot = ctx.token.slot, None
+        if job is None:
+            return None, None
+        x, gy, pad = job
+        side = torch.cuda.current_stream()
+        x.record_stream(side)
+        gy.record_stream(side)
+        gw, _ = wgrad_raw(x, gy, pad, ctx.wshape)
+        return gw, None
+
+
 class ConvBnLrelu(Function):
     """ConvBlock3D/2D as ONE autograd node (reference modules/networks_3d.py:48-56).
     forward : conv (+bias) with BatchNorm sums fused into its epilogue -> finalize + normalise + affine + LeakyReLU (1 launch)
@@ -403,8 +456,9 @@ class ConvBnLrelu(Function):
     First-order only: BatchNorm blocks live in the generators, which are never differentiated twice."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope):
+    def forward(ctx, x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope, token=None):
         _require_cuda(x, w, gamma, beta)
+        ctx.token = token
         cout = w.shape[0]
         stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
         y = conv_raw(x, w, bias, pad, False, True, stats=stats)
@@ -441,15 +495,25 @@ class ConvBnLrelu(Function):
         if ctx.needs_input_grad[0]:
             gx = conv_raw(gy, w, None, 2 - ctx.pad, True, is_wide(x))
         if ctx.needs_input_grad[1]:
-            gw, _ = wgrad_raw(x, gy, ctx.pad, tuple(w.shape))
+            if ctx.token is not None:
+                ctx.token.slot = (x, gy, ctx.pad)            # WeightProxy.backward computes it on the side stream
+                gw = torch.empty(tuple(w.shape), dtype=torch.float32, device=w.device)
+            else:
+                gw, _ = wgrad_raw(x, gy, ctx.pad, tuple(w.shape))
         if want_gb:
             gb = sums[2 * c:] if fuse_gb else channel_sum(gy)
-        return gx, gw, gb, dgamma, dbeta, None, None, None, None, None, None, None
+        return gx, gw, gb, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum=0.1, eps=1e-5, slope=0.2):
     """ConvBlock3D/2D (reference modules/networks_3d.py:48-56) through the fused node"""
-    return ConvBnLrelu.apply(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope)
+    token = None
+    side = _WGRAD_STREAM[0]
+    if side is not None and torch.is_grad_enabled() and w.requires_grad:
+        token = _Deferred()
+        with torch.cuda.stream(side):
+            w = WeightProxy.apply(w, token)
+    return ConvBnLrelu.apply(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope, token)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -104,8 +104,8 @@ class ScaleTrainer:
         self.allreduce_bytes = 0
         self.iterations = 0
         self.graph = None
-        self.overlap = (self.gan and torch.cuda.is_available()) if overlap is None else bool(overlap)
-        self._side = None
+        self.overlap = torch.cuda.is_available() if overlap is None else bool(overlap)
+        self._side = self._wside = None
         if self.overlap:
             # parameters receive gradients from nodes on several streams by design; the engine synchronises them
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -144,6 +144,21 @@ class ScaleTrainer:
         if self.iterations == 0 and len(opt.Noise_Amps) < opt.scale_idx + 1:
             self.calc_noise_amp(real, real_zero)
         out = {}
+        side = None
+        if self.overlap and real.is_cuda and self._wside is None:
+            self._wside = torch.cuda.Stream(device=real.device)
+        if self._wside is not None:
+            self._wside.wait_stream(torch.cuda.current_stream())     # fork (also makes it part of a graph capture)
+        with ops.wgrad_stream(self._wside):
+            out = self._iteration_body(real, real_zero, noise_init, out)
+        if self._wside is not None:
+            torch.cuda.current_stream().wait_stream(self._wside)     # join (the engine already did after each backward)
+        return out
+
+    def _iteration_body(self, real, real_zero, noise_init, out):
+        opt, G, D = self.opt, self.netG, self.netD
+        from modules.losses import kl_criterion
+        from modules.utils import calc_gradient_penalty
         side = None
         if self.gan and self.overlap and real.is_cuda:
             if self._side is None:
