@@ -49,9 +49,12 @@ struct TcCfg {
   static constexpr int BTILE_BYTES = NOUT * 128;                // one tap: NOUT output channels x 64 input channels bf16
   static constexpr int STAGE_TILES = STACK ? 3 : 1;
   static constexpr int STAGE_BYTES = STAGE_TILES * BTILE_BYTES;
-  static constexpr int NB = STACK ? (THIN ? 4 : (NGRP == 2 ? 3 : 2)) : (THIN ? 8 : ((KCHUNKS == 1) ? 6 : 3));   // weight ring depth (stages)
-  static constexpr int NSTG = THIN ? 0 : ((KCHUNKS == 1 && !(STACK && NGRP == 2)) ? 2 : 1); // output staging buffers
-  static constexpr int NEPI = THIN ? NEPI_THIN : NEPI_WIDE;
+  static constexpr int NB = STACK ? (THIN ? 4 : (NGRP == 2 ? 3 : 2)) : (THIN ? 8 : ((KCHUNKS == 1) ? (NACC == 1 ? 3 : 6) : 3));   // weight ring depth (stages)
+  static constexpr int NSTG = THIN ? 0 : ((KCHUNKS == 1 && NACC > 1 && !(STACK && NGRP == 2)) ? 2 : 1); // output staging buffers
+  // NACC == 1 is the "two CTAs per SM" configuration for volumes with fewer 4-slice units than SMs: half the shared memory,
+  // 4 epilogue warps (register budget), and the two co-resident CTAs overlap each other's prologue / MMA / epilogue phases
+  static constexpr int NEPI = THIN ? NEPI_THIN : (NACC == 1 ? 4 : NEPI_WIDE);
+  static constexpr int MIN_CTAS = (NACC == 1 && !THIN) ? 2 : 1;
   static constexpr int THREADS = 32 * (1 + NMMA) + 32 * NEPI;
   static constexpr int EPI_WARP0 = 1 + NMMA;
   static constexpr int ACC_COLS = NACC * NOUT;
@@ -82,7 +85,7 @@ struct TcParams {
 };
 
 template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK>
-__global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::THREADS), 1)
+__global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::THREADS), (TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::MIN_CTAS))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const TcParams p) {
   using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
@@ -437,7 +440,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           uint32_t r[CPT];
           if (p.dbg) t_ld -= clock64();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col(a) + ch * CPT;
-          if (CPT == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+          if (CPT == 64) {
+            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + 32, r + (CPT == 64 ? 32 : 0));
+          } else if (CPT == 32) {
+            tmem_ld32(taddr, r);
+          } else {
+            tmem_ld16(taddr, r);
+          }
           tmem_ld_wait();
           if (p.dbg) t_ld += clock64();
           float v[CPT];
@@ -478,9 +488,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
           if (p.dbg) t_bar += clock64();
           const uint32_t sdst = s_stg + stg * STG_BYTES + m * 128;
+          const uint32_t sphase = (sdst >> 7) & 7u;      // 128-byte swizzle phase of this row (absolute address bits)
 #pragma unroll
           for (int c = 0; c < CPT / 8; ++c) {
-            const uint32_t addr = sdst + ((uint32_t)((ch * (CPT / 8) + c) ^ (m & 7)) << 4);
+            const uint32_t addr = sdst + ((uint32_t)((ch * (CPT / 8) + c) ^ sphase) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[8 * c + 0], v[8 * c + 1])),
                          "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
                          "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7]))
@@ -499,11 +510,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             // column sums over the staged (bf16-rounded, invalid rows zeroed) tile: thread = channel, RPT rows each
             const int c = et & 63, rg = et >> 6;
             const uint8_t* tile = sgen + Cfg::OFF_STG + stg * STG_BYTES;
+            const uint32_t tile_row0 = (s_stg + stg * STG_BYTES) >> 7;
 #pragma unroll
             for (int rr = 0; rr < RPT; ++rr) {
               const int row = rg * RPT + rr;
-              const __nv_bfloat16 bv =
-                  *reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((c >> 3) ^ (row & 7)) << 4) + (c & 7) * 2);
+              const __nv_bfloat16 bv = *reinterpret_cast<const __nv_bfloat16*>(
+                  tile + row * 128 + (((c >> 3) ^ ((tile_row0 + row) & 7)) << 4) + (c & 7) * 2);
               const float f = bf2f(bv);
               st_s += f;
               st_s2 = fmaf(f, f, st_s2);
@@ -648,6 +660,7 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
       if (variant == 1) return launch_tc<1, 4, 3, 1, 64>(mx, mw, my, p, st);
       if (variant == 2) return launch_tc<1, 4, 3, 2, 64>(mx, mw, my, p, st);
       if (variant == 3) return launch_tc<1, 4, 3, 2, 64, true>(mx, mw, my, p, st);
+      if (variant == 4) return launch_tc<1, 1, 3, 1, 64>(mx, mw, my, p, st);
       return launch_tc<1, 4, 3, 1, 64, true>(mx, mw, my, p, st);
     }
     return launch_tc<2, 2, 3, 2, 64>(mx, mw, my, p, st);
