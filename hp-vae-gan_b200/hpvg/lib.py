@@ -52,6 +52,8 @@ PROTOTYPES = {
     "hpvg_gp_penalty_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_float, c_void_p]),
     "hpvg_convert_format": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p]),
     "hpvg_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "hpvg_clip_from_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpvg_frames_to_uint8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hpvg_sn_power_iter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p]),
     "hpvg_sn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

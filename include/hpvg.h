@@ -181,6 +181,17 @@ int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, in
 int hpvg_lerp(const float* a, const float* b, float* out, const float* alpha, long long numel, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Data formats either side of the path (bit-exact restatements of host code of the reference).
+ * clip_from_frames: what SingleVideoDataset.__getitem__ builds per iteration (datasets/video.py:44-92) from the frames of
+ *   the current pyramid level, kept resident as uint8 [num_frames][H][W][3] (RGB):
+ *     clip[c][t][h][w] = ((frames[first + t*every][h][w'][c] / 255) - 0.5) / 0.5 ,  w' = hflip ? W-1-w : w     (float32 [3][T][H][W])
+ * frames_to_uint8: utils/saver.py:16-18  out[t][h][w][c] = uint8((video[c][t][h][w] + 1) * 127.5)   (uint8 [T][H][W][3])
+ * ------------------------------------------------------------------------------------------------------------- */
+int hpvg_clip_from_frames(const uint8_t* frames, float* clip, int num_frames, int first, int every, int T, int H, int W,
+                          int hflip, void* stream);
+int hpvg_frames_to_uint8(const float* video, uint8_t* out, int T, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Spectral normalisation, one power iteration (nn.utils.spectral_norm as used by ConvBlock3DSN/2DSN,
  * networks_3d.py:63): w_mat = w_orig viewed [Cout][K].  In place: v <- normalize(W^T u), u <- normalize(W v);
  * sigma[0] = u^T W v.  `scratch` holds K + Cout + 4 floats.  Then w_sn = w_orig / sigma.

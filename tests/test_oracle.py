@@ -179,3 +179,23 @@ def test_numpy_primitives_match_torch():
     assert abs(np_ops.kl(mu.numpy(), lv.numpy()) - port.kl_criterion(mu, lv).item()) < 1e-12
     g = port.det_tensor((2, 3, 2, 4, 4), 69).double()
     assert abs(np_ops.gp_penalty(g.numpy(), 0.1) - (((g.norm(2, dim=1) - 1) ** 2).mean() * 0.1).item()) < 1e-12
+
+
+def test_data_path_restatement():
+    """oracle/data_ref.py: the reference's per-iteration clip construction (datasets/video.py:44-82) and the uint8 frame
+    conversion of utils/saver.py:16-18 on hand-checkable values"""
+    import numpy as np
+    from oracle import data_ref
+    frames = np.zeros((9, 2, 3, 3), dtype=np.uint8)
+    for f in range(9):
+        frames[f] = f * 25
+    frames[:, 0, 0, 1] = 255
+    clip = data_ref.clip_from_frames(frames, 1, 6, 3)          # frames 1, 4, 7
+    assert tuple(clip.shape) == (3, 3, 2, 3) and clip.dtype == torch.float32
+    assert clip[1, :, 0, 0].tolist() == [1.0, 1.0, 1.0]
+    expect = [(np.float32(v) / np.float32(255) - np.float32(0.5)) / np.float32(0.5) for v in (25, 100, 175)]
+    assert clip[0, :, 1, 2].tolist() == [float(e) for e in expect]
+    flipped = data_ref.clip_from_frames(frames, 1, 6, 3, hflip=True)
+    assert torch.equal(flipped, clip.flip(-1))
+    video = np.array([-1.0, -0.5, 0.0, 0.5, 1.0, 0.999], dtype=np.float32).reshape(1, 1, 1, 6).repeat(3, 0)
+    assert data_ref.frames_to_uint8(video)[0, 0, :, 0].tolist() == [0, 63, 127, 191, 255, 254]
