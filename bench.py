@@ -46,23 +46,21 @@ WORKLOAD = {"name": "cfg2"}
 
 
 def make_opt():
-    from oracle import port            # Opt is only the argparse-namespace stand-in (no oracle compute on this path)
+    from hpvg.options import Options   # the argparse-namespace stand-in with the reference's defaults
     if WORKLOAD["name"] == "cfg5":     # BASELINE configs[4]: 32-frame 128x128 clip (--img-size 128 --sampling-rates 31 1)
-        o = port.Opt(img_size=128, sampling_rates=[31, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
+        o = Options(img_size=128, sampling_rates=[31, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5, batch_size=1)
     else:
-        o = port.Opt(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5)
+        o = Options(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5, batch_size=1)
     o.scale_idx = o.stop_scale
     o.Noise_Amps = [1.0] + [0.07] * (o.stop_scale - 1)      # survey-observed amplitudes; the finest one is computed at iteration 0
-    s0, t0 = port.scale_size(0, o), port.time_depth(0, o)
-    o.Z_init_size = [1, o.latent_dim, t0, s0, s0]
-    o.batch_size = 1
+    t0, h0, w0 = o.level_size(0)
+    o.Z_init_size = [1, o.latent_dim, t0, h0, w0]
     return o
 
 
 def level_shape(o, idx):
-    from oracle import port
-    s = port.scale_size(idx, o)
-    return (1, 3, port.time_depth(idx, o), s, s)
+    t, h, w = o.level_size(idx)
+    return (1, 3, t, h, w)
 
 
 def workload_name(o):
