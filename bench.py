@@ -308,7 +308,7 @@ def run_hpvg(args):
     # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
     _, draws_rank = train.draws_for_rank(args.draws, world, rank)
     draws_rank = max(1, draws_rank)
-    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph, streams=args.gen_streams)
+    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph, streams=args.gen_streams, static_weights=True)   # G is not trained during this leg
     frames = [0]
 
     def gen_all():

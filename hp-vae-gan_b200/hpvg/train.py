@@ -225,6 +225,9 @@ class ScaleTrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        # packed weight images: layers this trainer updates are repacked inside the recording (their version counters moved
+        # in the warm-up steps); frozen stages keep the images cached before the capture, which stay valid for the lifetime
+        # of this trainer because nothing else writes those weights.  Re-capture after load_state_dict().
         ops._GpAlpha.external = True
         try:
             with torch.cuda.graph(self.graph):
@@ -266,8 +269,12 @@ class Sampler:
     config 2: 20.8 k frames/s with 1 stream, 46 k with 4, 50.7 k with 6.  BatchNorm running statistics are not advanced in
     that mode (concurrent draws would race on them; nothing on the path reads them)."""
 
-    def __init__(self, netG, opt, device, batch=1, graph=True, streams=1):
+    def __init__(self, netG, opt, device, batch=1, graph=True, streams=1, static_weights=False):
+        """static_weights=True: the bf16 weight images are packed once, outside the recordings (the generator is not
+        trained while this sampler is in use; build a new Sampler after its weights change).  Default: every recording
+        repacks its images, so replays always read the generator's current weights."""
         self.netG, self.opt, self.device, self.batch = netG, opt, device, batch
+        self.static_weights = static_weights
         self.size = [batch] + list(opt.Z_init_size[1:])
         self.nstreams = max(1, int(streams)) if graph else 1
         self.track_bn = self.nstreams == 1
@@ -285,6 +292,10 @@ class Sampler:
                     st.wait_stream(side)
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
+                    # every graph packs its own bf16 weight images inside the recording, so a replay always reads the
+                    # generator's current weights (a cache hit would freeze the images of the moment of capture)
+                    if not self.static_weights:
+                        ops.invalidate_packed_weights()
                     with torch.no_grad(), torch.cuda.graph(g):
                         fake = self._draw()
                 self.graphs.append(g)
