@@ -300,9 +300,19 @@ def run_hpvg(args):
         # and not host launch latency (eager launching is CPU-bound on this workload)
         torch.cuda._sleep(int(0.12 * 1.9e9))
         trainer.iteration(real, real_zero)
+    # one kernel at a time: the reconstruction / weight-gradient side streams are joined into the main stream and the
+    # programmatic launch overlap is off for this leg, so an event pair brackets exactly one kernel running alone — its
+    # duration, not its share of a GPU that another stream's kernel is also using
+    saved = (trainer.overlap, trainer._side, trainer._wside)
+    trainer.overlap, trainer._side, trainer._wside = False, None, None
+    pdl_was = lib.set_pdl(False)
+    step_eager()
+    torch.cuda.synchronize()
     lib.profile_enable(True)
     ms_prof = timed(step_eager, prof_steps)
     lib.profile_enable(False)
+    lib.set_pdl(pdl_was)
+    trainer.overlap, trainer._side, trainer._wside = saved
     rows = lib.profile_dump()
 
     # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
@@ -349,9 +359,10 @@ def run_hpvg(args):
                         "share_of_step": (top["ms"] / prof_steps) / (ms / args.steps),
                         "by_kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in by_kind.items()},
                         "by_kernel_tflops": {k: (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None) for k, v in by_kind.items()},
-                        "note": "per-launch CUDA events need eager launches: this leg runs the same iteration un-graphed behind a "
-                                "GPU-side delay so that launches are queued ahead of the GPU; share_of_step = kernel ms per "
-                                "iteration / graph-replay ms per iteration"}
+                        "note": "per-launch CUDA events need eager launches: this leg runs the same iteration un-graphed on ONE stream "
+                                "(no concurrent side-stream kernels, no programmatic launch overlap) behind a GPU-side delay so "
+                                "that launches are queued ahead of the GPU; share_of_step = kernel ms per iteration / "
+                                "graph-replay ms per iteration (the replay overlaps streams, so shares can sum above 1)"}
         value = world * args.steps / (ms * 1e-3)
         e2e = world * args.steps / (ms_e2e * 1e-3)
         bi = (real_h.numel() + real_zero_h.numel()) * 4

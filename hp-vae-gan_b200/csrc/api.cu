@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -22,6 +23,25 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv_backend() { return g_backend.load(std::memory_order_relaxed); }
+
+static int pdl_default() {
+  const char* e = getenv("HPVG_PDL");
+  return (e && atoi(e) == 0) ? 0 : 1;
+}
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = pdl_default();
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+int set_pdl(int on) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 
 // ---- optional per-launch device timing (bench.py's roofline leg): CUDA events around selected kernels, on the stream
 // they are launched on.  Off by default; never used under stream capture.
@@ -124,6 +144,8 @@ int hpvg_debug_set_clock_buffer(long long* device_buffer) {
   hpvg::g_dbg.store(device_buffer);
   return 0;
 }
+
+int hpvg_set_pdl(int on) { return hpvg::set_pdl(on); }
 
 int hpvg_profile_enable(int on) {
   hpvg::g_prof_on.store(on ? 1 : 0);

@@ -54,6 +54,32 @@ static inline int num_sms() {
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (HPVG_PDL=0 turns it off): every libhpvg kernel is launched with the programmatic
+// stream-serialization attribute and starts with pdl_enter() (or, in the tcgen05 kernels, runs its barrier / TMEM /
+// descriptor set-up first and then pdl_wait()).  The next kernel of the stream is scheduled while this one drains and
+// blocks in griddepcontrol.wait until this grid has completed and flushed, so a chain of dependent launches — a pyramid
+// pass is a few hundred of them — does not pay the launch latency between every pair.  Inside a stream capture the
+// attribute becomes a programmatic edge of the CUDA graph.
+bool pdl_enabled();
+int set_pdl(int on);
+
+#ifdef __CUDACC__
+template <typename... P, typename... A>
+static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+#endif
+
 // geometry of one convolution call (k = 3 on H and W, KD in {1,3} on D, stride 1)
 struct ConvGeom {
   int N, Cin, Cout;
@@ -66,6 +92,16 @@ struct ConvGeom {
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// griddepcontrol.wait: returns once every grid this launch programmatically depends on has completed and its writes are
+// visible (at once when there is no such dependency).  launch_dependents: lets the next kernel of the stream be scheduled
+// as soon as every CTA of this grid has executed it (or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
 
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const void* __restrict
                                                           const float* __restrict__ bias, void* __restrict__ yv, ConvGeom g,
                                                           int transposed, int act, float slope, float* __restrict__ stats,
                                                           const __nv_bfloat16* __restrict__ mask_src) {
+  pdl_enter();
   extern __shared__ float ws[];  // [taps][CI_CHUNK][CO_TILE]
   const int co0 = blockIdx.y * CO_TILE;
   const long long out_vox = (long long)g.N * g.Do * g.Ho * g.Wo;
@@ -204,7 +205,7 @@ static int launch_direct(const void* x, const float* w, const float* bias, void*
   const long long out_vox = (long long)g.N * g.Do * g.Ho * g.Wo;
   dim3 grid((unsigned)cdiv(out_vox, 128), (unsigned)cdiv(g.Cout, CO_TILE));
   size_t smem = (size_t)g.taps * CI_CHUNK * CO_TILE * sizeof(float);
-  conv_direct_kernel<XFMT, YFMT, CO_TILE, CI_CHUNK><<<grid, 128, smem, st>>>(
+  launch_k(conv_direct_kernel<XFMT, YFMT, CO_TILE, CI_CHUNK>, grid, 128, smem, st, 
       x, w, bias, y, g, transposed, act, slope, stats, reinterpret_cast<const __nv_bfloat16*>(mask_src));
   HPVG_CHECK_LAUNCH("conv_direct_kernel");
   return 0;
@@ -236,6 +237,7 @@ int conv_direct(const void* x, int x_fmt, const float* w, const float* bias, voi
 template <int XFMT, int GFMT, int TAPS>
 __global__ void __launch_bounds__(256) wgrad_direct_kernel(const void* __restrict__ xv, const void* __restrict__ gv,
                                                            float* __restrict__ dw, ConvGeom g, long long vox_per_block) {
+  pdl_enter();
   const int pairs = g.Cin * g.Cout;
   const int p = blockIdx.y * blockDim.x + threadIdx.x;
   const bool live = p < pairs;
@@ -310,9 +312,9 @@ static int launch_wgrad_direct(const void* x, const void* gy, float* dw, const C
   chunks = cdiv(out_vox, vpb);
   dim3 grid((unsigned)chunks, (unsigned)pair_blocks);
   if (g.taps == 27)
-    wgrad_direct_kernel<XFMT, GFMT, 27><<<grid, 256, 0, st>>>(x, gy, dw, g, vpb);
+    launch_k(wgrad_direct_kernel<XFMT, GFMT, 27>, grid, 256, 0, st, x, gy, dw, g, vpb);
   else
-    wgrad_direct_kernel<XFMT, GFMT, 9><<<grid, 256, 0, st>>>(x, gy, dw, g, vpb);
+    launch_k(wgrad_direct_kernel<XFMT, GFMT, 9>, grid, 256, 0, st, x, gy, dw, g, vpb);
   HPVG_CHECK_LAUNCH("wgrad_direct_kernel");
   return 0;
 }

@@ -81,6 +81,8 @@ struct TcParams {
   float* stats;
   const __nv_bfloat16* mask_src;
   float* y_thin;    // NOUT == 16: float32 NCDHW output
+  const uint8_t* w_img;      // packed weight image (for the L2 prefetch; nullptr = off)
+  unsigned w_img_bytes;
   long long* dbg;   // optional per-CTA phase clocks (development aid, hpvg_debug_set_clock_buffer)
 };
 
@@ -129,7 +131,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_w);
     if (!Cfg::THIN) tma_prefetch_desc(&tmap_y);
   }
+  if (threadIdx.x == 64 && p.w_img) {
+    // Pull the whole packed weight image into L2, one slice per CTA.  The image of a frozen pyramid stage was last read an
+    // iteration ago, so every ring stage would otherwise pay a DRAM round trip (about one stage time: the two-stage ring
+    // cannot hide it), and all CTAs stream the same tiles in the same order.
+    const unsigned chunk = ((p.w_img_bytes + gridDim.x - 1) / gridDim.x + 127u) & ~127u;
+    const unsigned off = blockIdx.x * chunk;
+    if (off < p.w_img_bytes) {
+      const unsigned n = min(chunk, p.w_img_bytes - off);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.w_img + off), "r"(n) : "memory");
+    }
+  }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  // Programmatic dependent launch: everything above (barriers, tensor-map and weight prefetch, TMEM allocation) touches
+  // nothing the previous kernel of the stream produces and overlaps its tail; from here on this CTA reads its output.
+  // The trigger for the NEXT kernel is given at once: it is scheduled when every CTA of this grid is resident (the grid
+  // is at most one CTA per SM), waits in its own griddepcontrol.wait and costs this kernel nothing but idle slots.
+  pdl_trigger();
+  pdl_wait();
   float* bias_s = reinterpret_cast<float*>(sgen + Cfg::OFF_BIAS);
   for (int i = threadIdx.x; i < MAX_COUT; i += Cfg::THREADS) bias_s[i] = (p.bias && i < g.Cout) ? p.bias[i] : 0.f;
   tc_fence_before();
@@ -602,7 +621,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   p.nblocks = NOUT == 64 ? g.Cout / 64 : 1;
   p.num_units = (long long)p.nblocks * g.N * p.units_d * p.units_h * p.units_w;
   const int grid = (int)min((long long)num_sms(), p.num_units);
-  conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mx, mw, my, p);
+  launch_k(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, mx, mw, my, p);
   HPVG_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
 }
@@ -650,6 +669,9 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
   p.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask_src);
   p.y_thin = thin ? reinterpret_cast<float*>(y) : nullptr;
   p.dbg = debug_clock_buffer();
+  static const bool w_prefetch = !(getenv("HPVG_TC_WPREFETCH") && atoi(getenv("HPVG_TC_WPREFETCH")) == 0);
+  p.w_img = w_prefetch ? reinterpret_cast<const uint8_t*>(w_packed) : nullptr;
+  p.w_img_bytes = (unsigned)((size_t)g.taps * (thin ? 16 : g.Cout) * g.Cin * 2);
   static const int variant = getenv("HPVG_TC_VARIANT") ? atoi(getenv("HPVG_TC_VARIANT")) : 0;   // tuning knob: 1 = unstacked, 2 = unstacked two groups, 3 = stacked two groups (measured: 24.5 us vs 22.4 us for the default)
   if (thin) {
     if (g.KD == 3) return variant == 1 ? launch_tc<1, 4, 3, 1, 16>(mx, mw, my, p, st) : launch_tc<1, 4, 3, 1, 16, true>(mx, mw, my, p, st);

@@ -19,6 +19,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float momentum, float eps, long long count,
                                    float* __restrict__ scale_shift, float* __restrict__ mean_invstd, int C) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const double inv = 1.0 / (double)count;
@@ -42,6 +43,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 
 __global__ void __launch_bounds__(256) bn_apply_lrelu_kernel(const uint4* __restrict__ y, const float* __restrict__ scale_shift,
                                                              uint4* __restrict__ out, long long nvec, int C, float slope) {
+  pdl_enter();
   extern __shared__ float ss[];  // scale[C], shift[C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ss[i] = scale_shift[i];
   __syncthreads();
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_lrelu_kernel(const uint
                                                                       long long count, float* __restrict__ scale_shift,
                                                                       float* __restrict__ mean_invstd, uint4* __restrict__ out,
                                                                       long long nvec, int C, float slope) {
+  pdl_enter();
   extern __shared__ float ss[];  // scale[C], shift[C]
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double inv = 1.0 / (double)count;
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* _
                                                                   const float* __restrict__ scale_shift,
                                                                   const float* __restrict__ mean_invstd, float* __restrict__ sums,
                                                                   long long nvox, int C, float slope) {
+  pdl_enter();
   extern __shared__ float sm[];  // [4*C] params, then [rows][2*C] partials
   float* prm = sm;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
                                                                  uint4* __restrict__ gy, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, long long nvox, int C, float slope,
                                                                  float* __restrict__ chsum) {
+  pdl_enter();
   extern __shared__ float prm[];  // scale, shift, mean, invstd, m0 = sum dz / M, m1 = sum dz*xhat / M, [C] reduction scratch
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int my_c0 = 0;
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
 __global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict__ gout, const uint4* __restrict__ outv,
                                                         uint4* __restrict__ gz, long long nvec, float slope, int C,
                                                         float* __restrict__ chsum) {
+  pdl_enter();
   extern __shared__ float red[];   // [C] when chsum
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
@@ -285,6 +291,7 @@ __device__ __forceinline__ void lin_src(int o, float scale, int in, int& i0, int
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                            const float* __restrict__ noise, float amp, int NC, int Di, int Hi, int Wi,
                                                            int Do, int Ho, int Wo, float sd, float sh, float sw) {
+  pdl_enter();
   const long long total = (long long)NC * Do * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
@@ -327,6 +334,7 @@ __device__ __forceinline__ float adj_weight(int o, int i, float scale, int in) {
 
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int NC, int Di, int Hi,
                                                            int Wi, int Do, int Ho, int Wo, float sd, float sh, float sw) {
+  pdl_enter();
   const long long total = (long long)NC * Di * Hi * Wi;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
@@ -362,6 +370,7 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
 // tanh(+residual)                          reference: modules/networks_3d.py:377,404
 // ===============================================================================================================
 __global__ void tanh_add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = a[i];
     if (b) v += b[i];
@@ -369,6 +378,7 @@ __global__ void tanh_add_fwd_kernel(const float* __restrict__ a, const float* __
   }
 }
 __global__ void tanh_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out, float* __restrict__ g, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float o = out[i];
     g[i] = gout[i] * (1.f - o * o);
@@ -382,6 +392,7 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ gout, const float* __r
 __global__ void __launch_bounds__(256) reparam_fwd_kernel(const uint4* __restrict__ mu, const uint4* __restrict__ logvar,
                                                           const float* __restrict__ eps, uint4* __restrict__ z, int N, int C,
                                                           long long S) {
+  pdl_enter();
   const int cvec = C >> 3;
   const long long total = (long long)N * S * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -407,6 +418,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const uint4* __restric
 __global__ void __launch_bounds__(256) reparam_bwd_kernel(const uint4* __restrict__ gz, const uint4* __restrict__ logvar,
                                                           const float* __restrict__ eps, uint4* __restrict__ gmu,
                                                           uint4* __restrict__ glogvar, int N, int C, long long S) {
+  pdl_enter();
   const int cvec = C >> 3;
   const long long total = (long long)N * S * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -445,6 +457,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, float* __restrict__ out,
                                                      long long n, float inv_n) {
+  pdl_enter();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -456,6 +469,7 @@ __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ m
 }
 __global__ void kl_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ mu, const float* __restrict__ logvar,
                               float* __restrict__ gmu, float* __restrict__ glogvar, long long n, float inv_n) {
+  pdl_enter();
   const float g = gout[0] * inv_n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     gmu[i] = g * mu[i];
@@ -468,6 +482,7 @@ __global__ void kl_bwd_kernel(const float* __restrict__ gout, const float* __res
 // ===============================================================================================================
 __global__ void __launch_bounds__(256) gp_fwd_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int C, long long S,
                                                      float coef) {
+  pdl_enter();
   __shared__ float red[8];
   float acc = 0.f;
   const long long total = (long long)N * S;
@@ -486,6 +501,7 @@ __global__ void __launch_bounds__(256) gp_fwd_kernel(const float* __restrict__ g
 }
 __global__ void gp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ g, float* __restrict__ gg, int N, int C,
                               long long S, float coef) {
+  pdl_enter();
   const float go = gout[0] * coef * 2.f;
   const long long total = (long long)N * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -505,6 +521,7 @@ __global__ void gp_bwd_kernel(const float* __restrict__ gout, const float* __res
 // layout / dtype conversion, lerp, channel sums, weight packing
 // ===============================================================================================================
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C, long long S) {
+  pdl_enter();
   const long long total = (long long)N * S * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -513,6 +530,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, __nv_bfloat
   }
 }
 __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int N, int C, long long S) {
+  pdl_enter();
   const long long total = (long long)N * S * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long s = i % S;
@@ -523,6 +541,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, flo
 }
 __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                             const float* __restrict__ alpha_ptr, long long n) {
+  pdl_enter();
   const float alpha = __ldg(alpha_ptr);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = alpha * a[i] + (1.f - alpha) * b[i];
@@ -531,6 +550,7 @@ __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict
 // NDHWC bf16: block = 256 threads = (256/C rows) x C channels
 __global__ void __launch_bounds__(256) channel_sum_ndhwc_kernel(const __nv_bfloat16* __restrict__ t, float* __restrict__ out, long long rows,
                                                                 int C) {
+  pdl_enter();
   __shared__ float part[256];
   const int rpb = blockDim.x / C;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
@@ -547,6 +567,7 @@ __global__ void __launch_bounds__(256) channel_sum_ndhwc_kernel(const __nv_bfloa
 }
 // NCDHW fp32: blockIdx.y = n*C + c, blockIdx.x = chunk of the spatial run
 __global__ void __launch_bounds__(256) channel_sum_ncdhw_kernel(const float* __restrict__ t, float* __restrict__ out, int C, long long S) {
+  pdl_enter();
   __shared__ float red[8];
   const int c = blockIdx.y % C;
   const float* p = t + (long long)blockIdx.y * S;
@@ -558,6 +579,7 @@ __global__ void __launch_bounds__(256) channel_sum_ncdhw_kernel(const float* __r
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int transposed,
                                     const float* __restrict__ sigma, int rows_per_tap) {
+  pdl_enter();
   const float inv = sigma ? 1.f / sigma[0] : 1.f;
   const long long total = (long long)taps * rows_per_tap * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -576,6 +598,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // v_raw[k] = sum_r W[r][k] u[r] ; norm2_v += v_raw[k]^2
 __global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ v_raw,
                                                      float* __restrict__ norm2_v, int Cout, int K) {
+  pdl_enter();
   __shared__ float red[8];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   float acc = 0.f;
@@ -588,6 +611,7 @@ __global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W
 // t_raw[r] = sum_k W[r][k] vec[k] ; norm2 += t_raw[r]^2
 __global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ vec, float* __restrict__ t_raw,
                                                     float* __restrict__ norm2, int K) {
+  pdl_enter();
   __shared__ float red[8];
   const int r = blockIdx.x;
   float acc = 0.f;
@@ -601,6 +625,7 @@ __global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W,
 __global__ void __launch_bounds__(256) sn_finalize_kernel(float* __restrict__ u, float* __restrict__ v, float* __restrict__ sigma,
                                                           const float* __restrict__ v_raw, const float* __restrict__ t_raw,
                                                           const float* __restrict__ norms, int Cout, int K, int update_uv, float eps) {
+  pdl_enter();
   __shared__ float red[8];
   if (update_uv) {
     const float nv = fmaxf(sqrtf(norms[0]), eps);
@@ -617,10 +642,12 @@ __global__ void __launch_bounds__(256) sn_finalize_kernel(float* __restrict__ u,
   }
 }
 __global__ void sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ sigma, float* __restrict__ w_sn, long long n) {
+  pdl_enter();
   const float inv = 1.f / sigma[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w_sn[i] = w[i] * inv;
 }
 __global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  pdl_enter();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(a[i], b[i], acc);
@@ -629,6 +656,7 @@ __global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, c
 }
 __global__ void sn_bwd_kernel(const float* __restrict__ gw_sn, const float* __restrict__ u, const float* __restrict__ v,
                               const float* __restrict__ sigma, const float* __restrict__ dot, float* __restrict__ gw, int Cout, int K) {
+  pdl_enter();
   const float inv = 1.f / sigma[0], d = dot[0];
   const long long total = (long long)Cout * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -654,6 +682,7 @@ struct SnBatch {
 };
 
 __global__ void __launch_bounds__(256) snb_wtu_kernel(const SnBatch b) {
+  pdl_enter();
   __shared__ float red[8];
   const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -668,6 +697,7 @@ __global__ void __launch_bounds__(256) snb_wtu_kernel(const SnBatch b) {
   if (threadIdx.x == 0) atomicAdd(b.scratch[l] + K + Cout, s);
 }
 __global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update_uv) {
+  pdl_enter();
   __shared__ float red[8];
   const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
   const int r = blockIdx.x;
@@ -683,6 +713,7 @@ __global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update
   }
 }
 __global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int update_uv, float eps) {
+  pdl_enter();
   __shared__ float red[8];
   const int l = blockIdx.x, K = b.k[l], Cout = b.cout[l];
   const float* v_raw = b.scratch[l];
@@ -703,6 +734,7 @@ __global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int 
   }
 }
 __global__ void snb_scale_kernel(const SnBatch b) {
+  pdl_enter();
   const int l = blockIdx.y;
   const long long n = (long long)b.cout[l] * b.k[l];
   const float inv = 1.f / b.sigma[l][0];
@@ -712,6 +744,7 @@ __global__ void snb_scale_kernel(const SnBatch b) {
 }
 // backward: scratch[l][0] = sum gw_sn * w_sn ; gw = (gw_sn - dot * u v^T) / sigma      (b.w holds w_sn here)
 __global__ void __launch_bounds__(256) snb_dot_kernel(const SnBatch b) {
+  pdl_enter();
   __shared__ float red[8];
   const int l = blockIdx.y;
   const long long n = (long long)b.cout[l] * b.k[l];
@@ -723,6 +756,7 @@ __global__ void __launch_bounds__(256) snb_dot_kernel(const SnBatch b) {
   if (threadIdx.x == 0) atomicAdd(b.scratch[l], s);
 }
 __global__ void snb_bwd_kernel(const SnBatch b) {
+  pdl_enter();
   const int l = blockIdx.y, K = b.k[l];
   const long long total = (long long)b.cout[l] * K;
   const float inv = 1.f / b.sigma[l][0], d = b.scratch[l][0];
@@ -759,7 +793,7 @@ int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, 
                      long long* nbt, float momentum, float eps, long long count, float* scale_shift, float* mean_invstd, int C,
                      void* stream) {
   HPVG_CHECK_ARG(C > 0 && count > 0, "bn_finalize: bad C=%d count=%lld", C, count);
-  bn_finalize_kernel<<<(unsigned)cdiv(C, 128), 128, 0, ST(stream)>>>(stats, gamma, beta, running_mean, running_var, nbt, momentum, eps,
+  launch_k(bn_finalize_kernel, (unsigned)cdiv(C, 128), 128, 0, ST(stream), stats, gamma, beta, running_mean, running_var, nbt, momentum, eps,
                                                                       count, scale_shift, mean_invstd, C);
   HPVG_CHECK_LAUNCH("bn_finalize");
   return 0;
@@ -768,7 +802,7 @@ int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, 
 int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long long nvox, int C, float slope, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 1024, "bn_apply_lrelu: C=%d must be a multiple of 8 (<= 1024)", C);
   const long long nvec = nvox * (C / 8);
-  bn_apply_lrelu_kernel<<<ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream)>>>(
+  launch_k(bn_apply_lrelu_kernel, ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream), 
       reinterpret_cast<const uint4*>(y), scale_shift, reinterpret_cast<uint4*>(out), nvec, C, slope);
   HPVG_CHECK_LAUNCH("bn_apply_lrelu");
   return 0;
@@ -779,7 +813,7 @@ int hpvg_bn_finalize_apply_lrelu(const void* y, const float* stats, const float*
                                  float* mean_invstd, void* out, long long nvox, int C, float slope, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && nvox > 0, "bn_finalize_apply_lrelu: C=%d must be a multiple of 8 (<= 256)", C);
   const long long nvec = nvox * (C / 8);
-  bn_finalize_apply_lrelu_kernel<<<ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream)>>>(
+  launch_k(bn_finalize_apply_lrelu_kernel, ew_blocks(nvec, 256), 256, 2 * C * sizeof(float), ST(stream), 
       reinterpret_cast<const uint4*>(y), stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, nvox, scale_shift,
       mean_invstd, reinterpret_cast<uint4*>(out), nvec, C, slope);
   HPVG_CHECK_LAUNCH("bn_finalize_apply_lrelu");
@@ -793,7 +827,7 @@ int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale
   const int rows = 256 / (C / 8);
   const size_t smem = (size_t)(4 * C + rows * 2 * C) * sizeof(float);
   const int blocks = (int)max(1LL, min(cdiv(nvox, rows), (long long)num_sms() * 4));
-  bn_lrelu_bwd_reduce_kernel<<<blocks, 256, smem, ST(stream)>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout),
+  launch_k(bn_lrelu_bwd_reduce_kernel, blocks, 256, smem, ST(stream), reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout),
                                                                 scale_shift, mean_invstd, sums, nvox, C, slope);
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_reduce");
   return 0;
@@ -805,7 +839,7 @@ int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_
   const long long nvec = nvox * (C / 8);
   // with the fused channel sum every block ends with C global atomics on the same C addresses: keep the grid at 2 CTAs per SM
   const int blocks = want_chsum ? min(ew_blocks(nvec, 256), 2 * num_sms()) : ew_blocks(nvec, 256);
-  bn_lrelu_bwd_apply_kernel<<<blocks, 256, 7 * C * sizeof(float), ST(stream)>>>(
+  launch_k(bn_lrelu_bwd_apply_kernel, blocks, 256, 7 * C * sizeof(float), ST(stream), 
       reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift, mean_invstd, sums,
       reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr);
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
@@ -820,7 +854,7 @@ int hpvg_lrelu_bwd(const void* gout, const void* out_saved, void* gz, long long 
   if (chsum) MEMSET0(chsum, C * sizeof(float), ST(stream), "lrelu_bwd");
   const long long nvec = numel / 8;
   const int blocks = chsum ? min(ew_blocks(nvec, 256), 2 * num_sms()) : ew_blocks(nvec, 256);
-  lrelu_bwd_kernel<<<blocks, 256, chsum ? C * sizeof(float) : 0, ST(stream)>>>(
+  launch_k(lrelu_bwd_kernel, blocks, 256, chsum ? C * sizeof(float) : 0, ST(stream), 
       reinterpret_cast<const uint4*>(gout), reinterpret_cast<const uint4*>(out_saved), reinterpret_cast<uint4*>(gz), nvec, slope, C,
       chsum);
   HPVG_CHECK_LAUNCH("lrelu_bwd");
@@ -833,7 +867,7 @@ int hpvg_upsample_linear_fwd(const float* x, float* out, const float* noise, flo
                              int Ho, int Wo, void* stream) {
   HPVG_CHECK_ARG(NC > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample_linear_fwd: bad extents");
   const long long total = (long long)NC * Do * Ho * Wo;
-  upsample_fwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(x, out, noise, noise_amp, NC, Di, Hi, Wi, Do, Ho, Wo,
+  launch_k(upsample_fwd_kernel, ew_blocks(total, 256), 256, 0, ST(stream), x, out, noise, noise_amp, NC, Di, Hi, Wi, Do, Ho, Wo,
                                                                      ac_scale(Di, Do), ac_scale(Hi, Ho), ac_scale(Wi, Wo));
   HPVG_CHECK_LAUNCH("upsample_linear_fwd");
   return 0;
@@ -842,19 +876,19 @@ int hpvg_upsample_linear_fwd(const float* x, float* out, const float* noise, flo
 int hpvg_upsample_linear_bwd(const float* gout, float* gx, int NC, int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream) {
   HPVG_CHECK_ARG(NC > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample_linear_bwd: bad extents");
   const long long total = (long long)NC * Di * Hi * Wi;
-  upsample_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(gout, gx, NC, Di, Hi, Wi, Do, Ho, Wo, ac_scale(Di, Do),
+  launch_k(upsample_bwd_kernel, ew_blocks(total, 256), 256, 0, ST(stream), gout, gx, NC, Di, Hi, Wi, Do, Ho, Wo, ac_scale(Di, Do),
                                                                      ac_scale(Hi, Ho), ac_scale(Wi, Wo));
   HPVG_CHECK_LAUNCH("upsample_linear_bwd");
   return 0;
 }
 
 int hpvg_tanh_add_fwd(const float* a, const float* b, float* out, long long numel, void* stream) {
-  tanh_add_fwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(a, b, out, numel);
+  launch_k(tanh_add_fwd_kernel, ew_blocks(numel, 256), 256, 0, ST(stream), a, b, out, numel);
   HPVG_CHECK_LAUNCH("tanh_add_fwd");
   return 0;
 }
 int hpvg_tanh_bwd(const float* gout, const float* out, float* g, long long numel, void* stream) {
-  tanh_bwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(gout, out, g, numel);
+  launch_k(tanh_bwd_kernel, ew_blocks(numel, 256), 256, 0, ST(stream), gout, out, g, numel);
   HPVG_CHECK_LAUNCH("tanh_bwd");
   return 0;
 }
@@ -862,7 +896,7 @@ int hpvg_tanh_bwd(const float* gout, const float* out, float* g, long long numel
 int hpvg_reparam_fwd(const void* mu, const void* logvar, const float* eps, void* z, int N, int C, long long spatial, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0, "reparam_fwd: C=%d must be a multiple of 8", C);
   const long long total = (long long)N * spatial * (C / 8);
-  reparam_fwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(mu), reinterpret_cast<const uint4*>(logvar),
+  launch_k(reparam_fwd_kernel, ew_blocks(total, 256), 256, 0, ST(stream), reinterpret_cast<const uint4*>(mu), reinterpret_cast<const uint4*>(logvar),
                                                                     eps, reinterpret_cast<uint4*>(z), N, C, spatial);
   HPVG_CHECK_LAUNCH("reparam_fwd");
   return 0;
@@ -871,7 +905,7 @@ int hpvg_reparam_bwd(const void* gz, const void* logvar, const float* eps, void*
                      void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0, "reparam_bwd: C=%d must be a multiple of 8", C);
   const long long total = (long long)N * spatial * (C / 8);
-  reparam_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(gz), reinterpret_cast<const uint4*>(logvar),
+  launch_k(reparam_bwd_kernel, ew_blocks(total, 256), 256, 0, ST(stream), reinterpret_cast<const uint4*>(gz), reinterpret_cast<const uint4*>(logvar),
                                                                     eps, reinterpret_cast<uint4*>(gmu), reinterpret_cast<uint4*>(glogvar), N, C,
                                                                     spatial);
   HPVG_CHECK_LAUNCH("reparam_bwd");
@@ -881,12 +915,12 @@ int hpvg_reparam_bwd(const void* gz, const void* logvar, const float* eps, void*
 int hpvg_kl_fwd(const float* mu, const float* logvar, float* out, long long numel, void* stream) {
   HPVG_CHECK_ARG(numel > 0, "kl_fwd: empty input");
   MEMSET0(out, sizeof(float), ST(stream), "kl_fwd");
-  kl_fwd_kernel<<<(int)min((long long)num_sms() * 2, cdiv(numel, 256)), 256, 0, ST(stream)>>>(mu, logvar, out, numel, 1.f / (float)numel);
+  launch_k(kl_fwd_kernel, (int)min((long long)num_sms() * 2, cdiv(numel, 256)), 256, 0, ST(stream), mu, logvar, out, numel, 1.f / (float)numel);
   HPVG_CHECK_LAUNCH("kl_fwd");
   return 0;
 }
 int hpvg_kl_bwd(const float* gout, const float* mu, const float* logvar, float* gmu, float* glogvar, long long numel, void* stream) {
-  kl_bwd_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(gout, mu, logvar, gmu, glogvar, numel, 1.f / (float)numel);
+  launch_k(kl_bwd_kernel, ew_blocks(numel, 256), 256, 0, ST(stream), gout, mu, logvar, gmu, glogvar, numel, 1.f / (float)numel);
   HPVG_CHECK_LAUNCH("kl_bwd");
   return 0;
 }
@@ -895,13 +929,13 @@ int hpvg_gp_penalty_fwd(const float* g, float* out, int N, int C, long long spat
   HPVG_CHECK_ARG(N > 0 && C > 0 && spatial > 0, "gp_penalty_fwd: bad extents");
   MEMSET0(out, sizeof(float), ST(stream), "gp_penalty_fwd");
   const long long total = (long long)N * spatial;
-  gp_fwd_kernel<<<(int)min((long long)num_sms() * 2, cdiv(total, 256)), 256, 0, ST(stream)>>>(g, out, N, C, spatial, lambda / (float)total);
+  launch_k(gp_fwd_kernel, (int)min((long long)num_sms() * 2, cdiv(total, 256)), 256, 0, ST(stream), g, out, N, C, spatial, lambda / (float)total);
   HPVG_CHECK_LAUNCH("gp_penalty_fwd");
   return 0;
 }
 int hpvg_gp_penalty_bwd(const float* gout, const float* g, float* gg, int N, int C, long long spatial, float lambda, void* stream) {
   const long long total = (long long)N * spatial;
-  gp_bwd_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(gout, g, gg, N, C, spatial, lambda / (float)total);
+  launch_k(gp_bwd_kernel, ew_blocks(total, 256), 256, 0, ST(stream), gout, g, gg, N, C, spatial, lambda / (float)total);
   HPVG_CHECK_LAUNCH("gp_penalty_bwd");
   return 0;
 }
@@ -909,10 +943,10 @@ int hpvg_gp_penalty_bwd(const float* gout, const float* g, float* gg, int N, int
 int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, int N, int C, long long spatial, void* stream) {
   const long long total = (long long)N * C * spatial;
   if (src_fmt == HPVG_FMT_NCDHW_F32 && dst_fmt == HPVG_FMT_NDHWC_BF16) {
-    ncdhw_to_ndhwc_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src),
+    launch_k(ncdhw_to_ndhwc_kernel, ew_blocks(total, 256), 256, 0, ST(stream), reinterpret_cast<const float*>(src),
                                                                          reinterpret_cast<__nv_bfloat16*>(dst), N, C, spatial);
   } else if (src_fmt == HPVG_FMT_NDHWC_BF16 && dst_fmt == HPVG_FMT_NCDHW_F32) {
-    ndhwc_to_ncdhw_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+    launch_k(ndhwc_to_ncdhw_kernel, ew_blocks(total, 256), 256, 0, ST(stream), reinterpret_cast<const __nv_bfloat16*>(src),
                                                                          reinterpret_cast<float*>(dst), N, C, spatial);
   } else {
     set_error("convert_format: unsupported conversion %d -> %d", src_fmt, dst_fmt);
@@ -924,7 +958,7 @@ int hpvg_convert_format(const void* src, int src_fmt, void* dst, int dst_fmt, in
 
 int hpvg_lerp(const float* a, const float* b, float* out, const float* alpha, long long numel, void* stream) {
   HPVG_CHECK_ARG(alpha != nullptr, "lerp: alpha must point to a device float");
-  lerp_kernel<<<ew_blocks(numel, 256), 256, 0, ST(stream)>>>(a, b, out, alpha, numel);
+  launch_k(lerp_kernel, ew_blocks(numel, 256), 256, 0, ST(stream), a, b, out, alpha, numel);
   HPVG_CHECK_LAUNCH("lerp");
   return 0;
 }
@@ -937,10 +971,10 @@ int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long
     const long long rows = (long long)N * spatial;
     const int rpb = 256 / C;
     const int blocks = (int)max(1LL, min(cdiv(rows, (long long)rpb * 8), (long long)num_sms() * 4));
-    channel_sum_ndhwc_kernel<<<blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(t), out, rows, C);
+    launch_k(channel_sum_ndhwc_kernel, blocks, 256, 0, ST(stream), reinterpret_cast<const __nv_bfloat16*>(t), out, rows, C);
   } else {
     dim3 grid((unsigned)max(1LL, min(cdiv(spatial, 2048), 64LL)), (unsigned)(N * C));
-    channel_sum_ncdhw_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(t), out, C, spatial);
+    launch_k(channel_sum_ncdhw_kernel, grid, 256, 0, ST(stream), reinterpret_cast<const float*>(t), out, C, spatial);
   }
   HPVG_CHECK_LAUNCH("channel_sum");
   return 0;
@@ -950,7 +984,7 @@ int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int
                       int rows_per_tap, void* stream) {
   HPVG_CHECK_ARG(rows_per_tap >= Cout, "pack_weights: rows_per_tap (%d) < Cout (%d)", rows_per_tap, Cout);
   const long long total = (long long)taps * rows_per_tap * Cin;
-  pack_weights_kernel<<<ew_blocks(total, 256), 256, 0, ST(stream)>>>(w_f32, reinterpret_cast<__nv_bfloat16*>(w_packed), Cout, Cin, taps,
+  launch_k(pack_weights_kernel, ew_blocks(total, 256), 256, 0, ST(stream), w_f32, reinterpret_cast<__nv_bfloat16*>(w_packed), Cout, Cin, taps,
                                                                      transposed, inv_scale_of, rows_per_tap);
   HPVG_CHECK_LAUNCH("pack_weights");
   return 0;
@@ -964,18 +998,18 @@ int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, fl
   float* norms = scratch + K + Cout;
   MEMSET0(norms, 4 * sizeof(float), ST(stream), "sn_power_iter");
   if (update_uv) {
-    sn_wtu_kernel<<<(unsigned)cdiv(K, 256), 256, 0, ST(stream)>>>(w_orig, u, v_raw, norms, Cout, K);
+    launch_k(sn_wtu_kernel, (unsigned)cdiv(K, 256), 256, 0, ST(stream), w_orig, u, v_raw, norms, Cout, K);
     HPVG_CHECK_LAUNCH("sn_wtu");
-    sn_wv_kernel<<<Cout, 256, 0, ST(stream)>>>(w_orig, v_raw, t_raw, norms + 1, K);
+    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v_raw, t_raw, norms + 1, K);
   } else {
-    sn_wv_kernel<<<Cout, 256, 0, ST(stream)>>>(w_orig, v, t_raw, norms + 1, K);
+    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v, t_raw, norms + 1, K);
   }
   HPVG_CHECK_LAUNCH("sn_wv");
-  sn_finalize_kernel<<<1, 256, 0, ST(stream)>>>(u, v, sigma, v_raw, t_raw, norms, Cout, K, update_uv, eps);
+  launch_k(sn_finalize_kernel, 1, 256, 0, ST(stream), u, v, sigma, v_raw, t_raw, norms, Cout, K, update_uv, eps);
   HPVG_CHECK_LAUNCH("sn_finalize");
   if (w_sn) {
     const long long n = (long long)Cout * K;
-    sn_scale_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(w_orig, sigma, w_sn, n);
+    launch_k(sn_scale_kernel, ew_blocks(n, 256), 256, 0, ST(stream), w_orig, sigma, w_sn, n);
     HPVG_CHECK_LAUNCH("sn_scale");
   }
   return 0;
@@ -985,9 +1019,9 @@ int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, cons
                      float* scratch, int Cout, int K, void* stream) {
   const long long n = (long long)Cout * K;
   MEMSET0(scratch, sizeof(float), ST(stream), "sn_backward");
-  dot_kernel<<<(int)min((long long)num_sms(), cdiv(n, 256)), 256, 0, ST(stream)>>>(gw_sn, w_sn, scratch, n);
+  launch_k(dot_kernel, (int)min((long long)num_sms(), cdiv(n, 256)), 256, 0, ST(stream), gw_sn, w_sn, scratch, n);
   HPVG_CHECK_LAUNCH("sn_dot");
-  sn_bwd_kernel<<<ew_blocks(n, 256), 256, 0, ST(stream)>>>(gw_sn, u, v, sigma, scratch, gw_orig, Cout, K);
+  launch_k(sn_bwd_kernel, ew_blocks(n, 256), 256, 0, ST(stream), gw_sn, u, v, sigma, scratch, gw_orig, Cout, K);
   HPVG_CHECK_LAUNCH("sn_bwd");
   return 0;
 }
@@ -1019,14 +1053,14 @@ int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* 
     MEMSET0(scratch[l] + k[l] + cout[l], 4 * sizeof(float), ST(stream), "sn_power_iter_batched");
   }
   if (update_uv) {
-    snb_wtu_kernel<<<dim3((unsigned)cdiv(maxk, 256), n), 256, 0, ST(stream)>>>(b);
+    launch_k(snb_wtu_kernel, dim3((unsigned)cdiv(maxk, 256), n), 256, 0, ST(stream), b);
     HPVG_CHECK_LAUNCH("snb_wtu");
   }
-  snb_wv_kernel<<<dim3(maxc, n), 256, 0, ST(stream)>>>(b, update_uv);
+  launch_k(snb_wv_kernel, dim3(maxc, n), 256, 0, ST(stream), b, update_uv);
   HPVG_CHECK_LAUNCH("snb_wv");
-  snb_finalize_kernel<<<n, 256, 0, ST(stream)>>>(b, update_uv, eps);
+  launch_k(snb_finalize_kernel, n, 256, 0, ST(stream), b, update_uv, eps);
   HPVG_CHECK_LAUNCH("snb_finalize");
-  snb_scale_kernel<<<dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream)>>>(b);
+  launch_k(snb_scale_kernel, dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream), b);
   HPVG_CHECK_LAUNCH("snb_scale");
   return 0;
 }
@@ -1044,9 +1078,9 @@ int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* cons
     MEMSET0(scratch[l], sizeof(float), ST(stream), "sn_backward_batched");
   }
   const unsigned bx = (unsigned)min(cdiv(maxn, 256), 32LL);
-  snb_dot_kernel<<<dim3(bx, n), 256, 0, ST(stream)>>>(b);
+  launch_k(snb_dot_kernel, dim3(bx, n), 256, 0, ST(stream), b);
   HPVG_CHECK_LAUNCH("snb_dot");
-  snb_bwd_kernel<<<dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream)>>>(b);
+  launch_k(snb_bwd_kernel, dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream), b);
   HPVG_CHECK_LAUNCH("snb_bwd");
   return 0;
 }

@@ -9,6 +9,7 @@ namespace hpvg {
 //   datasets/video.py:52-54 (slice + /255), :75 K.hflip, :78 K.normalize(x, 0.5, 0.5), :81 permute to CTHW
 __global__ void __launch_bounds__(256) clip_from_frames_kernel(const uint8_t* __restrict__ frames, float* __restrict__ clip, int f0,
                                                                int every, int T, int H, int W, int hflip) {
+  pdl_enter();
   const long long total = (long long)3 * T * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) clip_from_frames_kernel(const uint8_t* __
 // out[t][h][w][c] = uint8((video[c][t][h][w] + 1) * 127.5)      utils/saver.py:16-18 (float32 arithmetic, C truncation)
 __global__ void __launch_bounds__(256) frames_to_uint8_kernel(const float* __restrict__ video, uint8_t* __restrict__ out, int T, int H,
                                                               int W) {
+  pdl_enter();
   const long long total = (long long)T * H * W * 3;
   const size_t plane = (size_t)T * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -50,7 +52,7 @@ int hpvg_clip_from_frames(const uint8_t* frames, float* clip, int num_frames, in
                  first + (T - 1) * every, every, num_frames);
   const long long total = (long long)3 * T * H * W;
   const int blocks = (int)max(1LL, min(cdiv(total, 256), (long long)num_sms() * 8));
-  clip_from_frames_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, clip, first, every, T, H, W, hflip);
+  launch_k(clip_from_frames_kernel, blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), frames, clip, first, every, T, H, W, hflip);
   HPVG_CHECK_LAUNCH("clip_from_frames");
   return 0;
 }
@@ -59,7 +61,7 @@ int hpvg_frames_to_uint8(const float* video, uint8_t* out, int T, int H, int W, 
   HPVG_CHECK_ARG(video && out && T > 0 && H > 0 && W > 0, "frames_to_uint8: bad arguments");
   const long long total = (long long)3 * T * H * W;
   const int blocks = (int)max(1LL, min(cdiv(total, 256), (long long)num_sms() * 8));
-  frames_to_uint8_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(video, out, T, H, W);
+  launch_k(frames_to_uint8_kernel, blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), video, out, T, H, W);
   HPVG_CHECK_LAUNCH("frames_to_uint8");
   return 0;
 }

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
                                                              const float* __restrict__ w_tco, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ y, ConvGeom g, int transposed, int act,
                                                              float slope, float* __restrict__ stats) {
+  pdl_enter();
   extern __shared__ float sm[];
   constexpr int TAPS = KDT * 9;
   float* ws = sm;                                   // [TAPS][Cin][64]
@@ -183,6 +184,7 @@ template <int KDT>
 __global__ void __launch_bounds__(256, 2) expand_conv_mma_kernel(const float* __restrict__ x, const float* __restrict__ w_tco,
                                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                                  ConvGeom g, int act, float slope, float* __restrict__ stats) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t em_smem[];
   constexpr int TAPS = KDT * 9;
   const int K = TAPS * g.Cin;                                   // <= 81
@@ -338,6 +340,7 @@ bool expand_conv_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* 
 
 // [tap][ci][co] float32 image of a narrow layer's filter (co = 64), `transposed` as in hpvg_conv_forward
 __global__ void pack_expand_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int taps, int transposed) {
+  pdl_enter();
   const int total = taps * Cin * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i & 63, ci = (i >> 6) % Cin, t = i / (64 * Cin);
@@ -346,7 +349,7 @@ __global__ void pack_expand_kernel(const float* __restrict__ w, float* __restric
 }
 
 int pack_expand(const float* w, float* out, int Cin, int taps, int transposed, cudaStream_t st) {
-  pack_expand_kernel<<<(unsigned)cdiv(taps * Cin * 64, 256), 256, 0, st>>>(w, out, Cin, taps, transposed);
+  launch_k(pack_expand_kernel, (unsigned)cdiv(taps * Cin * 64, 256), 256, 0, st, w, out, Cin, taps, transposed);
   HPVG_CHECK_LAUNCH("pack_expand_kernel");
   return 0;
 }
@@ -365,20 +368,20 @@ int expand_conv(const void* x, const float* w, const float* w_tco, const float* 
       attr_done = true;
     }
     if (g.KD == 3)
-      expand_conv_mma_kernel<3><<<(unsigned)blocks, 256, smem_mma, st>>>(reinterpret_cast<const float*>(x), w_tco, bias,
+      launch_k(expand_conv_mma_kernel<3>, (unsigned)blocks, 256, smem_mma, st, reinterpret_cast<const float*>(x), w_tco, bias,
                                                                         reinterpret_cast<__nv_bfloat16*>(y), g, act, slope, stats);
     else
-      expand_conv_mma_kernel<1><<<(unsigned)blocks, 256, smem_mma, st>>>(reinterpret_cast<const float*>(x), w_tco, bias,
+      launch_k(expand_conv_mma_kernel<1>, (unsigned)blocks, 256, smem_mma, st, reinterpret_cast<const float*>(x), w_tco, bias,
                                                                         reinterpret_cast<__nv_bfloat16*>(y), g, act, slope, stats);
     HPVG_CHECK_LAUNCH("expand_conv_mma_kernel");
     return 0;
   }
   const size_t smem = ((size_t)g.taps * g.Cin * 64 + (size_t)g.Cin * g.KD * EX_HH * EX_HW) * sizeof(float);
   if (g.KD == 3)
-    expand_conv_kernel<3><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
+    launch_k(expand_conv_kernel<3>, (unsigned)blocks, 128, smem, st, reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                               g, transposed, act, slope, stats);
   else
-    expand_conv_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
+    launch_k(expand_conv_kernel<1>, (unsigned)blocks, 128, smem, st, reinterpret_cast<const float*>(x), w, w_tco, bias, reinterpret_cast<__nv_bfloat16*>(y),
                                                               g, transposed, act, slope, stats);
   HPVG_CHECK_LAUNCH("expand_conv_kernel");
   return 0;
@@ -421,6 +424,7 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
 // points into a run of ones, so that it accumulates the plain channel sum.
 template <int KDT, int NC>
 __global__ void __launch_bounds__(OC_THREADS, 2) outer_corr_kernel(const OuterCorrParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t osm[];
   constexpr int TAPS = KDT * 9;
   constexpr int WT_BYTES = OC_TH * OC_TW * 128;
@@ -512,6 +516,7 @@ __global__ void __launch_bounds__(OC_THREADS, 2) outer_corr_kernel(const OuterCo
 // row) with 8 threads per output walking the rows 8 apart, so the ~300 dependent loads of a serial sum become ~37.
 __global__ void __launch_bounds__(256) outer_corr_reduce_kernel(const float* __restrict__ partial, int blocks, int nc, int taps, int J,
                                                                 int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int total = nc * 4 * OC_THREADS;
@@ -562,6 +567,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 
 template <int KDT>
 __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const OuterCorrParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t osm[];
   constexpr int TAPS = KDT * 9;
   constexpr int WT_BYTES = OC_TH * OC_TW * 128;
@@ -665,6 +671,7 @@ __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const Out
 // partial row) and walks the ~300 rows with 32 threads per entry, so each thread has ~10 independent loads in flight
 __global__ void __launch_bounds__(1024) outer_corr_mma_reduce_kernel(const float* __restrict__ partial, int blocks, int taps, int J,
                                                                      int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum) {
+  pdl_enter();
   __shared__ float red[32][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int total = OM_ROWS * 64;
@@ -723,7 +730,7 @@ static void oc_launch(const OuterCorrParams& p, int grid, size_t smem, cudaStrea
     cudaFuncSetAttribute(outer_corr_kernel<KDT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_done = true;
   }
-  outer_corr_kernel<KDT, NC><<<grid, OC_THREADS, smem, st>>>(p);
+  launch_k(outer_corr_kernel<KDT, NC>, grid, OC_THREADS, smem, st, p);
 }
 
 // Two launches: per-block partial sums into `workspace` (deterministic, no atomics), then a fixed-order reduction into
@@ -775,11 +782,11 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
       attr_mma = true;
     }
     if (g.KD == 3)
-      outer_corr_mma_kernel<3><<<grid, OM_THREADS, smem_mma, st>>>(p);
+      launch_k(outer_corr_mma_kernel<3>, grid, OM_THREADS, smem_mma, st, p);
     else
-      outer_corr_mma_kernel<1><<<grid, OM_THREADS, smem_mma, st>>>(p);
+      launch_k(outer_corr_mma_kernel<1>, grid, OM_THREADS, smem_mma, st, p);
     HPVG_CHECK_LAUNCH("outer_corr_mma_kernel");
-    outer_corr_mma_reduce_kernel<<<(unsigned)cdiv(OM_ROWS * 64, 32), 1024, 0, st>>>(p.partial, grid, g.taps, p.J, head ? 1 : 0, dw,
+    launch_k(outer_corr_mma_reduce_kernel, (unsigned)cdiv(OM_ROWS * 64, 32), 1024, 0, st, p.partial, grid, g.taps, p.J, head ? 1 : 0, dw,
                                                                                 p.want_sum ? dbias_wide : nullptr);
     HPVG_CHECK_LAUNCH("outer_corr_mma_reduce_kernel");
     return 0;
@@ -805,7 +812,7 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
   }
   HPVG_CHECK_LAUNCH("outer_corr_kernel");
   const int total = nc * 4 * OC_THREADS;
-  outer_corr_reduce_kernel<<<(unsigned)cdiv(total, 32), 256, 0, st>>>(p.partial, grid, nc, g.taps, p.J, head ? 1 : 0, dw,
+  launch_k(outer_corr_reduce_kernel, (unsigned)cdiv(total, 32), 256, 0, st, p.partial, grid, nc, g.taps, p.J, head ? 1 : 0, dw,
                                                                       p.want_sum ? dbias_wide : nullptr);
   HPVG_CHECK_LAUNCH("outer_corr_reduce_kernel");
   return 0;

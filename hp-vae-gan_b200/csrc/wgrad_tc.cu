@@ -71,6 +71,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_gy);
   }
   if (warp == 1) tmem_alloc<WG_TMEM_COLS>(smem_u32(tmem_slot));
+  pdl_trigger();      // see conv_tc.cu: set-up above overlaps the previous kernel's tail, operands are read after the wait
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -199,6 +201,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // threads per output quad and combined through shared memory
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partial, float* __restrict__ dw, int splits,
                                                            int taps, int Cin, int Cout) {
+  pdl_enter();
   __shared__ float4 red[4][64];
   const long long total4 = (long long)taps * Cin * Cout / 4;
   const int q = threadIdx.x & 63, part = threadIdx.x >> 6;
@@ -283,10 +286,10 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
     attr_done = true;
   }
   dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), (unsigned)g.KD);
-  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(mx, mg, p);
+  launch_k(wgrad_tc_kernel, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
   HPVG_CHECK_LAUNCH("wgrad_tc_kernel");
   const long long total4 = (long long)g.taps * g.Cin * g.Cout / 4;
-  wgrad_reduce_kernel<<<(unsigned)cdiv(total4, 64), 256, 0, st>>>(reinterpret_cast<const float4*>(p.partial), dw, p.splits, g.taps,
+  launch_k(wgrad_reduce_kernel, (unsigned)cdiv(total4, 64), 256, 0, st, reinterpret_cast<const float4*>(p.partial), dw, p.splits, g.taps,
                                                                  g.Cin, g.Cout);
   HPVG_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;

@@ -104,10 +104,12 @@ class ConvBlockSN(nn.Sequential):
         conv = self.conv
         return ops.SpectralWeight.apply(conv.weight_orig, conv.weight_u, conv.weight_v, conv.training, 1e-12)
 
-    def run(self, x, out_wide=True, weight=None):
-        """`weight`: W / sigma computed by the caller for all layers of the network at once (ops.spectral_weights)"""
+    def run(self, x, out_wide=True, weight=None, in_link=None, out_link=None):
+        """`weight`: W / sigma computed by the caller for all layers of the network at once (ops.spectral_weights);
+        in_link / out_link: ops.ChainLink handshakes with the neighbouring blocks of a chain (_run_sn_chain)"""
         w = self.weight() if weight is None else weight
-        return ops.conv(x, w, self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None)
+        return ops.conv(x, w, self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None, in_link=in_link,
+                        out_link=out_link if self.has_act else None)
 
     def forward(self, x):
         _check_device(x)
@@ -125,8 +127,16 @@ def _run_sn_chain(blocks, x):
     the reference where every forward pre-hook runs on its own weight), then the convolutions"""
     blocks = list(blocks)
     weights = ops.spectral_weights([b.conv for b in blocks])
-    for b, w in zip(blocks, weights):
-        x = b.run(x, weight=w)
+    # each block's output feeds exactly the next block, so in the first-order backward the next block's data-gradient launch
+    # can apply this block's LeakyReLU derivative (and sum its bias gradient) in its epilogue: see ops.ChainLink
+    link = None
+    for i, (b, w) in enumerate(zip(blocks, weights)):
+        nxt = None
+        if b.has_act and i + 1 < len(blocks):
+            bias = b.conv.bias
+            nxt = ops.ChainLink(LRELU_SLOPE, bias is not None and bias.requires_grad)
+        x = b.run(x, weight=w, in_link=link, out_link=nxt)
+        link = nxt
     return x
 
 

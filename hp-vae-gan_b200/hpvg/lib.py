@@ -21,6 +21,7 @@ PROTOTYPES = {
     "hpvg_launch_count": (c_longlong, []),
     "hpvg_debug_set_clock_buffer": (c_int, [c_void_p]),
     "hpvg_profile_enable": (c_int, [c_int]),
+    "hpvg_set_pdl": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -120,6 +121,11 @@ def get_conv_backend():
 
 
 PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow"}
+
+
+def set_pdl(on):
+    """programmatic dependent launch of the library's kernels on/off; returns the previous setting"""
+    return int(load().hpvg_set_pdl(int(bool(on))))
 
 
 def profile_enable(on):

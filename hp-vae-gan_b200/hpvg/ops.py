@@ -10,6 +10,7 @@ written with the other Functions (never `once_differentiable`), so `torch.autogr
 in calc_gradient_penalty (reference modules/utils.py:14-16) builds the second-order graph out of the same
 kernels.
 """
+import os
 import threading
 
 import torch
@@ -153,9 +154,11 @@ def expand_image_for(w, cin, taps, transposed):
     return out
 
 
-def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None):
+def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None, mask_slope=None):
     """One hpvg_conv_forward call.  `w` is the float32 weight of the *forward* convolution ([Cout_f, Cin_f, (3,)3,3]);
-    transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f)."""
+    transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f).
+    mask_src / mask_slope: the epilogue multiplies the result by the LeakyReLU derivative read from `mask_src` (a wide
+    tensor of the output's extents): "dgrad then leaky_relu_backward" in one launch."""
     _require_cuda(x, w)
     x = x.contiguous()
     w = w.contiguous()
@@ -180,9 +183,14 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
         packed = expand_image_for(w, cin, taps, transposed)
     if bias is not None:
         bias = bias.contiguous()
+    if mask_src is not None:
+        if act_slope is not None or mask_slope is None or not out_wide or tuple(mask_src.shape) != tuple(y.shape):
+            raise ValueError("conv: mask_src needs a wide output of the same extents, a slope and no activation")
+        mask_src = mask_src.contiguous()
+    slope = act_slope if act_slope is not None else (mask_slope if mask_src is not None else 0.0)
     lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,
-             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE,
-             float(act_slope) if act_slope is not None else 0.0, _ptr(stats), _ptr(mask_src), _stream())
+             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE, float(slope), _ptr(stats), _ptr(mask_src),
+             _stream())
     return y
 
 
@@ -216,13 +224,41 @@ def channel_sum(t):
 # ---------------------------------------------------------------------------------------------------------------
 # convolution family (double differentiable)
 # ---------------------------------------------------------------------------------------------------------------
+class ChainLink:
+    """Handshake between two consecutive LeakyReLU conv blocks of a chain (critic, encoder features) for the plain
+    first-order backward.  The consumer's data-gradient launch applies the producer's LeakyReLU derivative in its epilogue
+    (mask read from the producer's stored activation = the consumer's input) and, if the producer has a bias, sums the
+    result per channel there: aten::leaky_relu_backward and the bias reduction cost no launch and no extra pass over the
+    8.4 MB gradient.  The producer's backward then finds `premasked` set and uses the gradient as is.  Valid only when the
+    producer's output has exactly one consumer (how _run_sn_chain builds the chain); never used under create_graph=True,
+    where the differentiable LReluBwd / ConvDgrad nodes are needed."""
+    __slots__ = ("slope", "want_gb", "premasked", "gb")
+
+    def __init__(self, slope, want_gb):
+        self.slope, self.want_gb, self.premasked, self.gb = slope, want_gb, False, None
+
+
+class _MaskLink:
+    """second-order twin of ChainLink, shared by the LReluBwd and ConvDgrad nodes that ConvFwd.backward creates in the
+    gradient-penalty sweep: ConvDgrad.backward applies LReluBwd.backward's mask in its own epilogue"""
+    __slots__ = ("y", "slope", "premasked")
+
+    def __init__(self, y, slope):
+        self.y, self.slope, self.premasked = y, slope, False
+
+
+_FUSE_MASK = [os.environ.get('HPVG_FUSE_MASK', '1') != '0']      # development switch (tests compare the fused and the unfused backward)
+
+
 class ConvFwd(Function):
-    """y = [lrelu](conv(x, w) + b); optional BatchNorm sums of y accumulate into `stats` (a side output)."""
+    """y = [lrelu](conv(x, w) + b); optional BatchNorm sums of y accumulate into `stats` (a side output).
+    in_link: x is the LeakyReLU output of the block owning that ChainLink; out_link: this block's own link."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, pad, out_wide, act_slope, stats):
+    def forward(ctx, x, w, bias, pad, out_wide, act_slope, stats, in_link=None, out_link=None):
         y = conv_raw(x, w, bias, pad, False, out_wide, act_slope=act_slope, stats=stats)
         ctx.pad, ctx.act_slope, ctx.has_bias = pad, act_slope, bias is not None
+        ctx.in_link, ctx.out_link = in_link, out_link
         ctx.save_for_backward(x, w, y if act_slope is not None else None)
         return y
 
@@ -230,31 +266,51 @@ class ConvFwd(Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         want_gb = ctx.has_bias and ctx.needs_input_grad[2] and not _input_only()
+        plain = not torch.is_grad_enabled()          # first-order backward without create_graph
         gx = gw = gb = None
-        if ctx.act_slope is not None:
+        out_link = ctx.out_link
+        if out_link is not None and out_link.premasked:
+            # the consumer's dgrad epilogue already applied this block's LeakyReLU derivative (and summed the bias gradient)
+            gz, out_link.premasked = gy.contiguous(), False
+            if want_gb and out_link.gb is not None:
+                gb = out_link.gb
+            out_link.gb = None
+        elif ctx.act_slope is not None:
             if want_gb and _chsum_fusable(y.shape[-1]):
                 gz, gb = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, True)    # bias gradient from the same pass
             else:
-                gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, False)
+                link = _MaskLink(y, ctx.act_slope) if (_FUSE_MASK[0] and not plain and _input_only() and is_wide(x)) else None
+                gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, False, link)
+                if ctx.needs_input_grad[0]:
+                    gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x), link)
         else:
             gz = gy.contiguous()
-        if ctx.needs_input_grad[0]:
-            gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
+        if ctx.needs_input_grad[0] and gx is None:
+            in_link = ctx.in_link
+            if _FUSE_MASK[0] and plain and in_link is not None and is_wide(x) and is_wide(gz):
+                stats = None
+                if in_link.want_gb and not _input_only():
+                    stats = torch.zeros((2 * x.shape[-1],), dtype=torch.float32, device=x.device)
+                gx = conv_raw(gz, w, None, 2 - ctx.pad, True, True, stats=stats, mask_src=x, mask_slope=in_link.slope)
+                in_link.premasked = True
+                in_link.gb = stats[:x.shape[-1]] if stats is not None else None
+            else:
+                gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
         if not _input_only():
             if ctx.needs_input_grad[1]:
                 gw = ConvWgrad.apply(x, gz, ctx.pad, tuple(w.shape))
             if want_gb and gb is None:
                 gb = ChannelSum.apply(gz)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None
 
 
 class ConvDgrad(Function):
     """gx = data gradient of conv(x, w) w.r.t. x given gz (a forward-type conv with flipped/transposed weights)."""
 
     @staticmethod
-    def forward(ctx, gz, w, pad, out_wide):
+    def forward(ctx, gz, w, pad, out_wide, link=None):
         gx = conv_raw(gz, w, None, 2 - pad, True, out_wide)
-        ctx.pad = pad
+        ctx.pad, ctx.link = pad, link
         ctx.save_for_backward(gz, w)
         return gx
 
@@ -263,11 +319,17 @@ class ConvDgrad(Function):
         gz, w = ctx.saved_tensors
         ggx = ggx.contiguous()
         g_gz = g_w = None
+        link = ctx.link
         if ctx.needs_input_grad[0]:
-            g_gz = ConvFwd.apply(ggx, w, None, ctx.pad, is_wide(gz), None, None)
+            if link is not None and not torch.is_grad_enabled() and is_wide(ggx) and is_wide(gz):
+                # gz came out of LReluBwd(., link.y): its backward is the same mask, applied here in the conv epilogue
+                g_gz = conv_raw(ggx, w, None, ctx.pad, False, True, mask_src=link.y, mask_slope=link.slope)
+                link.premasked = True
+            else:
+                g_gz = ConvFwd.apply(ggx, w, None, ctx.pad, is_wide(gz), None, None)
         if ctx.needs_input_grad[1] and not _input_only():
             g_w = ConvWgrad.apply(ggx, gz, ctx.pad, tuple(w.shape))
-        return g_gz, g_w, None, None
+        return g_gz, g_w, None, None, None
 
 
 class ConvWgrad(Function):
@@ -302,7 +364,7 @@ class LReluBwd(Function):
     With want_sum the kernel also returns the per-channel sum of gz (the bias gradient of the convolution in front)."""
 
     @staticmethod
-    def forward(ctx, gy, y, slope, want_sum=False):
+    def forward(ctx, gy, y, slope, want_sum=False, link=None):
         _require_cuda(gy, y)
         if not (is_wide(gy) and is_wide(y)):
             raise TypeError("LReluBwd works on wide (bf16 NDHWC) tensors")
@@ -310,7 +372,7 @@ class LReluBwd(Function):
         c = gy.shape[-1]
         gb = torch.empty((c,), dtype=torch.float32, device=gy.device) if want_sum else None
         lib.call("hpvg_lrelu_bwd", _ptr(gy), _ptr(y), _ptr(gz), gy.numel(), float(slope), c, _ptr(gb), _stream())
-        ctx.slope, ctx.want_sum = slope, want_sum
+        ctx.slope, ctx.want_sum, ctx.link = slope, want_sum, link
         ctx.save_for_backward(y)
         if want_sum:
             ctx.mark_non_differentiable(gb)
@@ -319,8 +381,12 @@ class LReluBwd(Function):
 
     @staticmethod
     def backward(ctx, ggz, *unused):
+        link = ctx.link
+        if link is not None and link.premasked:
+            link.premasked = False
+            return ggz, None, None, None, None        # ConvDgrad.backward applied this mask in its epilogue
         (y,) = ctx.saved_tensors
-        return LReluBwd.apply(ggz.contiguous(), y, ctx.slope, False), None, None, None
+        return LReluBwd.apply(ggz.contiguous(), y, ctx.slope, False), None, None, None, None
 
 
 class ChannelSum(Function):
@@ -338,8 +404,8 @@ class ChannelSum(Function):
         return g.view(1, -1, 1, 1, 1).expand(ctx.shape).contiguous()
 
 
-def conv(x, w, bias, pad, out_wide, act_slope=None, stats=None):
-    return ConvFwd.apply(x, w, bias, pad, out_wide, act_slope, stats)
+def conv(x, w, bias, pad, out_wide, act_slope=None, stats=None, in_link=None, out_link=None):
+    return ConvFwd.apply(x, w, bias, pad, out_wide, act_slope, stats, in_link, out_link)
 
 
 # ---------------------------------------------------------------------------------------------------------------

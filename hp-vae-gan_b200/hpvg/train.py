@@ -11,6 +11,8 @@ averaged over ranks with ONE flat-bucket NCCL all-reduce: the c
 the generator's after total_loss.backward() and before clip_grad_norm_, so every rank clips with the same norm and
 takes the same Adam step.  BatchNorm statistics stay per rank, as under the reference's nn.DataParallel.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -82,8 +84,13 @@ class GradBucket:
 class ScaleTrainer:
     """state of one `train(opt, netG)` call of the reference: optimizers and the iteration body"""
 
-    def __init__(self, opt, netG, netD=None, distributed=False, dims=3, capturable=False, overlap=None):
-        """capturable=True builds the Adam optimizers with device-side step counters (torch's `capturable` flag: same
+    def __init__(self, opt, netG, netD=None, distributed=False, dims=3, capturable=False, overlap=None, skip_critic_grads=None):
+        """skip_critic_grads: the generator step's `-D(fake).mean()` backward (train_video.py:194-199) also accumulates
+        weight gradients into the critic, which the next iteration's `D.zero_grad()` (:178) discards unread; with this flag
+        the critic's parameters do not require grad during that forward, so those weight-gradient and spectral-norm backward
+        kernels are not launched.  Losses, both optimizers' steps and every generator gradient are unchanged; only the
+        (never read) contents of D's .grad between the generator step and the next zero_grad differ from the reference.
+        capturable=True builds the Adam optimizers with device-side step counters (torch's `capturable` flag: same
         arithmetic), which capture() needs to record the whole iteration into one CUDA graph.
         overlap (default: on at GAN scales on CUDA): the generator's 'rec' pass runs on a second CUDA stream, concurrently
         with the critic's pass on the real clip; autograd then runs the backward of the reconstruction path on that stream
@@ -105,6 +112,9 @@ class ScaleTrainer:
         self.iterations = 0
         self.graph = None
         self.overlap = torch.cuda.is_available() if overlap is None else bool(overlap)
+        if skip_critic_grads is None:
+            skip_critic_grads = os.environ.get('HPVG_SKIP_CRITIC_GRADS', '1') != '0'
+        self.skip_critic_grads = bool(skip_critic_grads)
         self._side = self._wside = None
         if self.overlap:
             # parameters receive gradients from nodes on several streams by design; the engine synchronises them
@@ -191,7 +201,14 @@ class ScaleTrainer:
             self.optimizerD.step()
 
             rec_loss = F.mse_loss(generated, real)
-            errG = -D(fake).mean() * opt.disc_loss_weight
+            frozen = [p for p in D.parameters() if p.requires_grad] if self.skip_critic_grads else []
+            for p in frozen:
+                p.requires_grad_(False)
+            try:
+                errG = -D(fake).mean() * opt.disc_loss_weight
+            finally:
+                for p in frozen:
+                    p.requires_grad_(True)
             total_loss = opt.rec_weight * rec_loss + errG
             out.update(rec_loss=rec_loss.detach(), errG=errG.detach(), errD_real=errD_real.detach(), errD_fake=errD_fake.detach(),
                        gradient_penalty=gradient_penalty.detach())

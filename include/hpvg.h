@@ -55,6 +55,11 @@ long long hpvg_launch_count(void);
 /* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
 int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
+/* Programmatic dependent launch of the library's kernels (default on; environment HPVG_PDL=0 turns it off): each kernel is
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization and blocks in griddepcontrol.wait before it touches
+ * global memory, so consecutive launches of a stream overlap launch latency and set-up with the predecessor's tail.
+ * Returns the previous setting. */
+int hpvg_set_pdl(int on);
 int hpvg_profile_dump(double* rows, int max_rows);
 
 /* ---------------------------------------------------------------------------------------------------------------

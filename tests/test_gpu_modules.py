@@ -229,6 +229,42 @@ def test_generator_sg_parity(golden, monkeypatch):
     assert rel_err(fake, fx['rand']['fake']) < REF_OUT_TOL
 
 
+@pytest.mark.parametrize("nfc", [8, 64])
+def test_fused_lrelu_mask_backward_matches_unfused(monkeypatch, nfc):
+    """ops.ChainLink / ops._MaskLink: the critic's first-order backward and the gradient-penalty double backward with the
+    LeakyReLU derivative (and the bias sum) applied in the data-gradient epilogue, against the same backward through the
+    separate leaky_relu_backward launches.  The only arithmetic difference is one bf16 rounding less on the fused path."""
+    from hpvg import ops
+    from modules import networks_3d
+    from modules import utils as mutils
+    opt = port.Opt(nfc=nfc, latent_dim=8, num_layer=3)
+    d = networks_3d.WDiscriminator3D(opt)
+    port.det_fill(d.state_dict(), 11)
+    d.cuda()
+    real = port.det_tensor((1, 3, 5, 18, 20), 3).cuda()
+    fake = port.det_tensor((1, 3, 5, 18, 20), 4).cuda()
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: torch.full((1, 1), 0.3))
+    u0 = {k: b.clone() for k, b in d.named_buffers()}
+    results = []
+    for fuse in (False, True):
+        with torch.no_grad():
+            for k, b in d.named_buffers():
+                b.copy_(u0[k])                      # same power-iteration state for both runs
+        monkeypatch.setitem(ops._FUSE_MASK, 0, fuse)
+        d.zero_grad()
+        x = real.clone().requires_grad_(True)
+        n0 = ops.lib.launch_count()
+        loss = -d(x).mean() + d(fake).mean() + mutils.calc_gradient_penalty(d, real, fake, 0.1, 'cuda')
+        loss.backward()
+        torch.cuda.synchronize()
+        results.append((ops.lib.launch_count() - n0, x.grad.clone(), {k: p.grad.clone() for k, p in d.named_parameters()}))
+    (n_plain, gx_plain, g_plain), (n_fused, gx_fused, g_fused) = results
+    assert n_fused < n_plain                        # the leaky_relu_backward launches are gone
+    assert rel_err(gx_fused, gx_plain) < 5e-3
+    for k in g_plain:
+        assert rel_err(g_fused[k], g_plain[k]) < 5e-3, k
+
+
 def test_modules_refuse_cpu_tensors():
     from hpvg.lib import HpvgError
     from modules import networks_3d
