@@ -54,7 +54,7 @@ static inline int num_sms() {
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
-// Programmatic dependent launch (HPVG_PDL=0 turns it off): every libhpvg kernel is launched with the programmatic
+// Programmatic dependent launch (off by default, HPVG_PDL=1 / hpvg_set_pdl(1) turn it on): every libhpvg kernel is then launched with the programmatic
 // stream-serialization attribute and starts with pdl_enter() (or, in the tcgen05 kernels, runs its barrier / TMEM /
 // descriptor set-up first and then pdl_wait()).  The next kernel of the stream is scheduled while this one drains and
 // blocks in griddepcontrol.wait until this grid has completed and flushed, so a chain of dependent launches — a pyramid

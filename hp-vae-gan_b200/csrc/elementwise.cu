@@ -595,41 +595,50 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // ===============================================================================================================
 // spectral normalisation                   reference: nn.utils.spectral_norm as used at modules/networks_3d.py:63
 // ===============================================================================================================
-// v_raw[k] = sum_r W[r][k] u[r] ; norm2_v += v_raw[k]^2
+// The two vector norms are summed by ONE block in a fixed order (sn_norms_256) rather than accumulated with atomics: sigma
+// must be bit-reproducible, because a one-ulp change of W / sigma flips bf16 roundings of the packed weights and from there
+// LeakyReLU signs several layers on (measured: 1.6e-2 run-to-run scatter of the critic's input gradient with atomics).
+// v_raw[k] = sum_r W[r][k] u[r]
 __global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ v_raw,
-                                                     float* __restrict__ norm2_v, int Cout, int K) {
+                                                     int Cout, int K) {
   pdl_enter();
-  __shared__ float red[8];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
   float acc = 0.f;
-  if (k < K)
-    for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
-  if (k < K) v_raw[k] = acc;
-  const float s = block_sum_256(k < K ? acc * acc : 0.f, red);
-  if (threadIdx.x == 0) atomicAdd(norm2_v, s);
+  for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
+  v_raw[k] = acc;
 }
-// t_raw[r] = sum_k W[r][k] vec[k] ; norm2 += t_raw[r]^2
+// t_raw[r] = sum_k W[r][k] vec[k]
 __global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ vec, float* __restrict__ t_raw,
-                                                    float* __restrict__ norm2, int K) {
+                                                    int K) {
   pdl_enter();
   __shared__ float red[8];
   const int r = blockIdx.x;
   float acc = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) acc = fmaf(W[(size_t)r * K + k], vec[k], acc);
   const float s = block_sum_256(acc, red);
-  if (threadIdx.x == 0) {
-    t_raw[r] = s;
-    atomicAdd(norm2, s * s);
-  }
+  if (threadIdx.x == 0) t_raw[r] = s;
+}
+// sum of squares of p[0..n) by one 256-thread block, the same order on every run; result broadcast to all threads
+__device__ __forceinline__ float sn_norm2_256(const float* __restrict__ p, int n, float* red, float* bcast) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(p[i], p[i], acc);
+  const float s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) *bcast = s;
+  __syncthreads();
+  const float r = *bcast;
+  __syncthreads();
+  return r;
 }
 __global__ void __launch_bounds__(256) sn_finalize_kernel(float* __restrict__ u, float* __restrict__ v, float* __restrict__ sigma,
                                                           const float* __restrict__ v_raw, const float* __restrict__ t_raw,
-                                                          const float* __restrict__ norms, int Cout, int K, int update_uv, float eps) {
+                                                          int Cout, int K, int update_uv, float eps) {
   pdl_enter();
   __shared__ float red[8];
+  __shared__ float bcast;
   if (update_uv) {
-    const float nv = fmaxf(sqrtf(norms[0]), eps);
-    const float tn = sqrtf(norms[1]) / nv;  // || W v ||
+    const float nv = fmaxf(sqrtf(sn_norm2_256(v_raw, K, red, &bcast)), eps);
+    const float tn = sqrtf(sn_norm2_256(t_raw, Cout, red, &bcast)) / nv;  // || W v ||
     const float nu = fmaxf(tn, eps);
     for (int k = threadIdx.x; k < K; k += blockDim.x) v[k] = v_raw[k] / nv;
     for (int r = threadIdx.x; r < Cout; r += blockDim.x) u[r] = (t_raw[r] / nv) / nu;
@@ -646,18 +655,25 @@ __global__ void sn_scale_kernel(const float* __restrict__ w, const float* __rest
   const float inv = 1.f / sigma[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w_sn[i] = w[i] * inv;
 }
+// out[blockIdx.x] = this block's share of sum a*b (gridDim.x <= HPVG_SN_DOT_PARTS); the consumer adds the shares in order
 __global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
   pdl_enter();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(a[i], b[i], acc);
   const float s = block_sum_256(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+__device__ __forceinline__ float sn_ordered_sum(const float* __restrict__ parts, int n) {
+  float d = 0.f;
+  for (int i = 0; i < n; ++i) d += parts[i];
+  return d;
 }
 __global__ void sn_bwd_kernel(const float* __restrict__ gw_sn, const float* __restrict__ u, const float* __restrict__ v,
-                              const float* __restrict__ sigma, const float* __restrict__ dot, float* __restrict__ gw, int Cout, int K) {
+                              const float* __restrict__ sigma, const float* __restrict__ dot, int parts, float* __restrict__ gw, int Cout,
+                              int K) {
   pdl_enter();
-  const float inv = 1.f / sigma[0], d = dot[0];
+  const float inv = 1.f / sigma[0], d = sn_ordered_sum(dot, parts);
   const long long total = (long long)Cout * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % K), r = (int)(i / K);
@@ -683,18 +699,14 @@ struct SnBatch {
 
 __global__ void __launch_bounds__(256) snb_wtu_kernel(const SnBatch b) {
   pdl_enter();
-  __shared__ float red[8];
   const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= K) return;
+  if (k >= K) return;
   const float* W = b.w[l];
   const float* u = b.u[l];
   float acc = 0.f;
-  if (k < K)
-    for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
-  if (k < K) b.scratch[l][k] = acc;
-  const float s = block_sum_256(k < K ? acc * acc : 0.f, red);
-  if (threadIdx.x == 0) atomicAdd(b.scratch[l] + K + Cout, s);
+  for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
+  b.scratch[l][k] = acc;
 }
 __global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update_uv) {
   pdl_enter();
@@ -707,10 +719,7 @@ __global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update
   float acc = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) acc = fmaf(W[(size_t)r * K + k], vec[k], acc);
   const float s = block_sum_256(acc, red);
-  if (threadIdx.x == 0) {
-    b.scratch[l][K + r] = s;
-    atomicAdd(b.scratch[l] + K + Cout + 1, s * s);
-  }
+  if (threadIdx.x == 0) b.scratch[l][K + r] = s;
 }
 __global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int update_uv, float eps) {
   pdl_enter();
@@ -718,10 +727,10 @@ __global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int 
   const int l = blockIdx.x, K = b.k[l], Cout = b.cout[l];
   const float* v_raw = b.scratch[l];
   const float* t_raw = b.scratch[l] + K;
-  const float* norms = b.scratch[l] + K + Cout;
+  __shared__ float bcast;
   if (update_uv) {
-    const float nv = fmaxf(sqrtf(norms[0]), eps);
-    const float tn = sqrtf(norms[1]) / nv;  // || W v ||
+    const float nv = fmaxf(sqrtf(sn_norm2_256(v_raw, K, red, &bcast)), eps);
+    const float tn = sqrtf(sn_norm2_256(t_raw, Cout, red, &bcast)) / nv;  // || W v ||
     const float nu = fmaxf(tn, eps);
     for (int k = threadIdx.x; k < K; k += blockDim.x) b.v[l][k] = v_raw[k] / nv;
     for (int r = threadIdx.x; r < Cout; r += blockDim.x) b.u[l][r] = (t_raw[r] / nv) / nu;
@@ -753,13 +762,13 @@ __global__ void __launch_bounds__(256) snb_dot_kernel(const SnBatch b) {
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc = fmaf(a[i], w[i], acc);
   const float s = block_sum_256(acc, red);
-  if (threadIdx.x == 0) atomicAdd(b.scratch[l], s);
+  if (threadIdx.x == 0) b.scratch[l][blockIdx.x] = s;
 }
-__global__ void snb_bwd_kernel(const SnBatch b) {
+__global__ void snb_bwd_kernel(const SnBatch b, int parts) {
   pdl_enter();
   const int l = blockIdx.y, K = b.k[l];
   const long long total = (long long)b.cout[l] * K;
-  const float inv = 1.f / b.sigma[l][0], d = b.scratch[l][0];
+  const float inv = 1.f / b.sigma[l][0], d = sn_ordered_sum(b.scratch[l], parts);
   const float* g = b.gw_sn[l];
   const float* u = b.u[l];
   const float* v = b.v[l];
@@ -995,17 +1004,15 @@ int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, fl
   HPVG_CHECK_ARG(Cout > 0 && K > 0, "sn_power_iter: bad shape");
   float* v_raw = scratch;
   float* t_raw = scratch + K;
-  float* norms = scratch + K + Cout;
-  MEMSET0(norms, 4 * sizeof(float), ST(stream), "sn_power_iter");
   if (update_uv) {
-    launch_k(sn_wtu_kernel, (unsigned)cdiv(K, 256), 256, 0, ST(stream), w_orig, u, v_raw, norms, Cout, K);
+    launch_k(sn_wtu_kernel, (unsigned)cdiv(K, 256), 256, 0, ST(stream), w_orig, u, v_raw, Cout, K);
     HPVG_CHECK_LAUNCH("sn_wtu");
-    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v_raw, t_raw, norms + 1, K);
+    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v_raw, t_raw, K);
   } else {
-    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v, t_raw, norms + 1, K);
+    launch_k(sn_wv_kernel, Cout, 256, 0, ST(stream), w_orig, v, t_raw, K);
   }
   HPVG_CHECK_LAUNCH("sn_wv");
-  launch_k(sn_finalize_kernel, 1, 256, 0, ST(stream), u, v, sigma, v_raw, t_raw, norms, Cout, K, update_uv, eps);
+  launch_k(sn_finalize_kernel, 1, 256, 0, ST(stream), u, v, sigma, v_raw, t_raw, Cout, K, update_uv, eps);
   HPVG_CHECK_LAUNCH("sn_finalize");
   if (w_sn) {
     const long long n = (long long)Cout * K;
@@ -1018,10 +1025,10 @@ int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, fl
 int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, const float* v, const float* sigma, float* gw_orig,
                      float* scratch, int Cout, int K, void* stream) {
   const long long n = (long long)Cout * K;
-  MEMSET0(scratch, sizeof(float), ST(stream), "sn_backward");
-  launch_k(dot_kernel, (int)min((long long)num_sms(), cdiv(n, 256)), 256, 0, ST(stream), gw_sn, w_sn, scratch, n);
+  const int parts = (int)min((long long)HPVG_SN_DOT_PARTS, cdiv(n, 256));
+  launch_k(dot_kernel, parts, 256, 0, ST(stream), gw_sn, w_sn, scratch, n);
   HPVG_CHECK_LAUNCH("sn_dot");
-  launch_k(sn_bwd_kernel, ew_blocks(n, 256), 256, 0, ST(stream), gw_sn, u, v, sigma, scratch, gw_orig, Cout, K);
+  launch_k(sn_bwd_kernel, ew_blocks(n, 256), 256, 0, ST(stream), gw_sn, u, v, sigma, scratch, parts, gw_orig, Cout, K);
   HPVG_CHECK_LAUNCH("sn_bwd");
   return 0;
 }
@@ -1050,7 +1057,6 @@ int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* 
     b.w[l] = w_orig[l]; b.u[l] = u[l]; b.v[l] = v[l]; b.sigma[l] = sigma[l]; b.w_sn[l] = w_sn[l]; b.scratch[l] = scratch[l];
     maxk = max(maxk, k[l]); maxc = max(maxc, cout[l]);
     maxn = max(maxn, (long long)cout[l] * k[l]);
-    MEMSET0(scratch[l] + k[l] + cout[l], 4 * sizeof(float), ST(stream), "sn_power_iter_batched");
   }
   if (update_uv) {
     launch_k(snb_wtu_kernel, dim3((unsigned)cdiv(maxk, 256), n), 256, 0, ST(stream), b);
@@ -1075,12 +1081,11 @@ int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* cons
     b.gw_sn[l] = gw_sn[l]; b.w[l] = w_sn[l]; b.u[l] = const_cast<float*>(u[l]); b.v[l] = const_cast<float*>(v[l]);
     b.sigma[l] = const_cast<float*>(sigma[l]); b.gw[l] = gw_orig[l]; b.scratch[l] = scratch[l];
     maxn = max(maxn, (long long)cout[l] * k[l]);
-    MEMSET0(scratch[l], sizeof(float), ST(stream), "sn_backward_batched");
   }
-  const unsigned bx = (unsigned)min(cdiv(maxn, 256), 32LL);
+  const unsigned bx = (unsigned)min(cdiv(maxn, 256), (long long)HPVG_SN_DOT_PARTS);
   launch_k(snb_dot_kernel, dim3(bx, n), 256, 0, ST(stream), b);
   HPVG_CHECK_LAUNCH("snb_dot");
-  launch_k(snb_bwd_kernel, dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream), b);
+  launch_k(snb_bwd_kernel, dim3((unsigned)min(cdiv(maxn, 256), 64LL), n), 256, 0, ST(stream), b, (int)bx);
   HPVG_CHECK_LAUNCH("snb_bwd");
   return 0;
 }

@@ -97,6 +97,7 @@ def call(name, *args):
 
 
 SN_MAX_LAYERS = 8
+SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the spectral-norm backward
 
 
 def ptr_array(tensors):

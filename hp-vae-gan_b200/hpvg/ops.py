@@ -804,7 +804,7 @@ class SpectralWeight(Function):
         cout = w_sn.shape[0]
         k = w_sn.numel() // cout
         gw = torch.empty_like(w_sn)
-        scratch = torch.empty((4,), dtype=torch.float32, device=w_sn.device)
+        scratch = torch.empty((lib.SN_DOT_PARTS,), dtype=torch.float32, device=w_sn.device)
         lib.call("hpvg_sn_backward", _ptr(gw_sn.contiguous()), _ptr(w_sn), _ptr(u), _ptr(v), _ptr(sigma), _ptr(gw), _ptr(scratch),
                  cout, k, _stream())
         return gw, None, None, None, None
@@ -855,8 +855,8 @@ class SpectralWeights(Function):
             dev = sigmas.device
             gs = [grads[i].contiguous() for i in idx]
             gws = [torch.empty_like(outs[i]) for i in idx]
-            scratch_all = torch.empty((len(idx),), dtype=torch.float32, device=dev)
-            scratch = [scratch_all[j:j + 1] for j in range(len(idx))]
+            scratch_all = torch.empty((len(idx) * lib.SN_DOT_PARTS,), dtype=torch.float32, device=dev)
+            scratch = [scratch_all[j * lib.SN_DOT_PARTS:] for j in range(len(idx))]
             lib.call("hpvg_sn_backward_batched", len(idx), lib.ptr_array(gs), lib.ptr_array([outs[i] for i in idx]),
                      lib.ptr_array([us[i] for i in idx]), lib.ptr_array([vs[i] for i in idx]),
                      lib.ptr_array([sigmas[i:i + 1] for i in idx]), lib.ptr_array(gws), lib.ptr_array(scratch),

@@ -55,7 +55,7 @@ long long hpvg_launch_count(void);
 /* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
 int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
-/* Programmatic dependent launch of the library's kernels (default on; environment HPVG_PDL=0 turns it off): each kernel is
+/* Programmatic dependent launch of the library's kernels (default OFF — measured slower inside the multi-stream recorded iteration; environment HPVG_PDL=1 or this call turns it on): each kernel is
  * launched with cudaLaunchAttributeProgrammaticStreamSerialization and blocks in griddepcontrol.wait before it touches
  * global memory, so consecutive launches of a stream overlap launch latency and set-up with the predecessor's tail.
  * Returns the previous setting. */
@@ -200,15 +200,17 @@ int hpvg_frames_to_uint8(const float* video, uint8_t* out, int T, int H, int W, 
  * Spectral normalisation, one power iteration (nn.utils.spectral_norm as used by ConvBlock3DSN/2DSN,
  * networks_3d.py:63): w_mat = w_orig viewed [Cout][K].  In place: v <- normalize(W^T u), u <- normalize(W v);
  * sigma[0] = u^T W v.  `scratch` holds K + Cout + 4 floats.  Then w_sn = w_orig / sigma.
- * sn_backward: gw_orig = (gw_sn - (sum(gw_sn * w_sn)) * u v^T) / sigma    (u, v constants, as in torch)
+ * sn_backward: gw_orig = (gw_sn - (sum(gw_sn * w_sn)) * u v^T) / sigma    (u, v constants, as in torch); its `scratch`
+ * holds HPVG_SN_DOT_PARTS floats.  All reductions run in a fixed order (no atomics): sigma is bit-reproducible.
  * ------------------------------------------------------------------------------------------------------------- */
 int hpvg_sn_power_iter(const float* w_orig, float* u, float* v, float* sigma, float* w_sn, float* scratch, int Cout,
                        int K, int update_uv, float eps, void* stream);
 int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, const float* v, const float* sigma,
                      float* gw_orig, float* scratch, int Cout, int K, void* stream);
 /* the same for all spectral-norm layers of one network at once (n <= HPVG_SN_MAX_LAYERS): arrays of n device pointers
- * (the arrays themselves are host memory) and n shapes; scratch[l] holds K[l] + Cout[l] + 4 floats (forward) / 1 (backward) */
+ * (the arrays themselves are host memory) and n shapes; scratch[l] holds K[l] + Cout[l] + 4 floats (forward) / HPVG_SN_DOT_PARTS (backward) */
 #define HPVG_SN_MAX_LAYERS 8
+#define HPVG_SN_DOT_PARTS 32
 int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
                                float* const* w_sn, float* const* scratch, const int* Cout, const int* K, int update_uv,
                                float eps, void* stream);

@@ -246,23 +246,66 @@ def test_fused_lrelu_mask_backward_matches_unfused(monkeypatch, nfc):
     monkeypatch.setattr(torch, "rand", lambda *a, **k: torch.full((1, 1), 0.3))
     u0 = {k: b.clone() for k, b in d.named_buffers()}
     results = []
-    for fuse in (False, True):
-        with torch.no_grad():
-            for k, b in d.named_buffers():
-                b.copy_(u0[k])                      # same power-iteration state for both runs
-        monkeypatch.setitem(ops._FUSE_MASK, 0, fuse)
-        d.zero_grad()
-        x = real.clone().requires_grad_(True)
-        n0 = ops.lib.launch_count()
-        loss = -d(x).mean() + d(fake).mean() + mutils.calc_gradient_penalty(d, real, fake, 0.1, 'cuda')
-        loss.backward()
-        torch.cuda.synchronize()
-        results.append((ops.lib.launch_count() - n0, x.grad.clone(), {k: p.grad.clone() for k, p in d.named_parameters()}))
+    saved = ops._FUSE_MASK[0]
+    try:
+        for fuse in (False, True):
+            with torch.no_grad():
+                for k, b in d.named_buffers():
+                    b.copy_(u0[k])                      # same power-iteration state for both runs
+            ops._FUSE_MASK[0] = fuse
+            d.zero_grad()
+            x = real.clone().requires_grad_(True)
+            n0 = ops.lib.launch_count()
+            loss = -d(x).mean() + d(fake).mean() + mutils.calc_gradient_penalty(d, real, fake, 0.1, 'cuda')
+            loss.backward()
+            torch.cuda.synchronize()
+            results.append((ops.lib.launch_count() - n0, x.grad.clone(), {k: p.grad.clone() for k, p in d.named_parameters()}))
+    finally:
+        ops._FUSE_MASK[0] = saved
     (n_plain, gx_plain, g_plain), (n_fused, gx_fused, g_fused) = results
     assert n_fused < n_plain                        # the leaky_relu_backward launches are gone
     assert rel_err(gx_fused, gx_plain) < 5e-3
     for k in g_plain:
         assert rel_err(g_fused[k], g_plain[k]) < 5e-3, k
+
+
+def test_critic_passes_are_bit_reproducible():
+    """Spectral-norm sigma is reduced in a fixed order (no atomics), so two critic forwards from the same power-iteration
+    state — and the gradient-penalty value built on a second power iteration — are bit-identical.  (With atomics a one-ulp
+    change of W / sigma flipped bf16 roundings and, layers later, LeakyReLU signs: 1.6e-2 scatter of the input gradient.)"""
+    from modules import networks_3d
+    from modules import utils as mutils
+    opt = port.Opt(nfc=64, latent_dim=8, num_layer=3)
+    d = networks_3d.WDiscriminator3D(opt)
+    port.det_fill(d.state_dict(), 11)
+    d.cuda()
+    real = port.det_tensor((1, 3, 5, 18, 20), 3).cuda()
+    fake = port.det_tensor((1, 3, 5, 18, 20), 4).cuda()
+    saved = torch.rand
+    torch.rand = lambda *a, **k: torch.full((1, 1), 0.3)
+    u0 = {k: b.clone() for k, b in d.named_buffers()}
+    runs = []
+    try:
+        for _ in range(4):
+            with torch.no_grad():
+                for k, b in d.named_buffers():
+                    b.copy_(u0[k])
+            x = real.clone().requires_grad_(True)
+            out = d(x)
+            (gx,) = torch.autograd.grad(-out.mean(), x)
+            gp = mutils.calc_gradient_penalty(d, real, fake, 0.1, 'cuda')
+            d.zero_grad()
+            gp.backward()
+            torch.cuda.synchronize()
+            runs.append((out.detach().clone(), gx.clone(), d.head.conv.weight_orig.grad.clone(), {k: b.clone() for k, b in d.named_buffers()}))
+    finally:
+        torch.rand = saved
+    for out, gx, gw, bufs in runs[1:]:
+        assert torch.equal(out, runs[0][0])
+        assert torch.equal(gx, runs[0][1])
+        assert torch.equal(gw, runs[0][2])
+        for k, b in bufs.items():
+            assert torch.equal(b, runs[0][3][k]), k
 
 
 def test_modules_refuse_cpu_tensors():
