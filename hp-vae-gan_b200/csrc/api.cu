@@ -40,6 +40,22 @@ bool pdl_enabled() {
   }
   return v != 0;
 }
+static std::atomic<int> g_col_mode{-2};
+int conv_col_mode() {
+  int v = g_col_mode.load(std::memory_order_relaxed);
+  if (v == -2) {
+    const char* e = getenv("HPVG_TC_COL");
+    v = e ? atoi(e) : 0;      // default: brick kernel (measured faster at every BASELINE volume, see conv_col.cu)
+    if (v < -1 || v > 1) v = 0;
+    g_col_mode.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+int set_conv_col_mode(int mode) {
+  const int prev = conv_col_mode();
+  g_col_mode.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0), std::memory_order_relaxed);
+  return prev;
+}
 int set_pdl(int on) {
   const int prev = pdl_enabled() ? 1 : 0;
   g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
@@ -96,7 +112,7 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -115,7 +131,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
     if (i < rank - 1) gstrides[i] = stride;
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu %llu)", (int)r, rank,
@@ -149,6 +166,7 @@ int hpvg_debug_set_clock_buffer(long long* device_buffer) {
 }
 
 int hpvg_set_pdl(int on) { return hpvg::set_pdl(on); }
+int hpvg_set_conv_col_mode(int mode) { return hpvg::set_conv_col_mode(mode); }
 
 int hpvg_profile_enable(int on) {
   hpvg::g_prof_on.store(on ? 1 : 0);

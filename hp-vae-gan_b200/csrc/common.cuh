@@ -62,6 +62,10 @@ static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b;
 // attribute becomes a programmatic edge of the CUDA graph.
 bool pdl_enabled();
 int set_pdl(int on);
+// which tcgen05 kernel runs the 3-D 64-channel layers: 0 = brick kernel (conv_tc.cu) always (default), -1 = by size,
+// 1 = column-streaming kernel (conv_col.cu) whenever it supports the layer.  Environment HPVG_TC_COL sets the initial value.
+int conv_col_mode();
+int set_conv_col_mode(int mode);
 
 #ifdef __CUDACC__
 template <typename... P, typename... A>
@@ -280,7 +284,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_tiled();
 
 // bf16 tensor map over a dense [.. outer dims ..][C] array: dims[0] = C (innermost), box[0] = 64 channels (128 B),
-// 128-byte swizzle.  rank <= 5.
-int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+// 128-byte swizzle (swizzle_bytes = 64: box[0] = 32 channels, 64-byte swizzle).  rank <= 5.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace hpvg

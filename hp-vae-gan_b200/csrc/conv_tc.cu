@@ -633,9 +633,24 @@ bool conv_tc_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_pa
   return g.Cout <= 16 && g.Cin == 64;
 }
 
+// conv_col.cu
+bool conv_col_supported(int x_fmt, int y_fmt, const ConvGeom& g, const void* w_packed);
+long long conv_col_brick_units(const ConvGeom& g);
+int conv_col(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
+             const void* mask_src, cudaStream_t st);
+
 int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
             float* stats, const void* mask_src, cudaStream_t st) {
   const bool thin = y_fmt == HPVG_FMT_NCDHW_F32;
+  {
+    // column-streaming kernel (conv_col.cu) for volumes with few brick units per SM; HPVG_TC_COL = 0 never, 1 always (when
+    // supported), otherwise when the brick kernel would have at most HPVG_TC_COL_UNITS units per SM (default 2)
+    const int col_mode = conv_col_mode();
+    static const int col_units = getenv("HPVG_TC_COL_UNITS") ? atoi(getenv("HPVG_TC_COL_UNITS")) : 2;
+    if (col_mode != 0 && conv_col_supported(HPVG_FMT_NDHWC_BF16, y_fmt, g, w_packed) &&
+        (col_mode == 1 || conv_col_brick_units(g) <= (long long)col_units * num_sms()))
+      return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
+  }
   if (thin && (act != HPVG_ACT_NONE || stats || mask_src)) {
     set_error("conv_tc: the thin-output kernel supports bias only (no activation, statistics or mask)");
     return -1;

@@ -8,7 +8,8 @@ so construction consumes the RNG exactly like the reference, `state_dict()` has 
 
 Reference classes restated here: ConvBlock3D/2D (modules/networks_3d.py:48-56, networks_2d.py:53-61),
 ConvBlock3DSN/2DSN (:59-70 / :64-75), FeatureExtractor (:73-85 / :78-90), Encode3DVAE/Encode2DVAE (:88-107 / :93-112),
-WDiscriminator3D/2D (:163-181 / :168-185), GeneratorHPVAEGAN (:325-406 / :188-269), GeneratorSG (:272-322).
+WDiscriminator3D/2D (:163-181 / :168-185), GeneratorHPVAEGAN (:325-406 / :188-269), GeneratorSG (:272-322),
+GeneratorCSG (:213-269), WDiscriminatorBaselines (:184-210).
 """
 import copy
 
@@ -328,9 +329,87 @@ def make_family(dims):
                 x_prev_out = _run_stage(block, x_in, 0) + x_up
             return ops.TanhAdd.apply(x_prev_out, None)
 
+    class GeneratorCSG(nn.Module):
+        """Feature-space SinGAN baseline (reference modules/networks_3d.py:213-269, the default generator of
+        train_video_baselines.py): a BatchNorm head lifts the noise to nfc channels, every stage is num_layer valid (pad 0)
+        ConvBlocks on an input zero-padded by num_layer voxels, stages are chained in FEATURE space — trilinear resize of the
+        nfc-channel map, + noise_amp * noise, residual add — and one conv + tanh tail maps to the image.  3-D only."""
+
+        def __init__(self, opt):
+            super().__init__()
+            if dims != 3:
+                raise NotImplementedError("GeneratorCSG exists only in networks_3d")
+            self.opt = opt
+            nfc = int(opt.nfc)
+            self.margin = int(opt.num_layer)
+            self.p3d_once = (1,) * 6
+            self.p3d = (self.margin,) * 6
+            self.head = _ConvBlock(opt.nc_im, nfc, opt.ker_size, padding=0, stride=1)
+            self.body = nn.ModuleList([])
+            first = nn.Sequential()
+            for i in range(opt.num_layer):
+                first.add_module('block%d' % i, _ConvBlock(nfc, nfc, opt.ker_size, padding=0, stride=1))
+            self.body.append(first)
+            self.tail = nn.Sequential(Conv(nfc, opt.nc_im, kernel_size=opt.ker_size, padding=0, stride=1), nn.Tanh())
+            self.apply(weights_init)
+
+        def init_next_stage(self):
+            self.body.append(copy.deepcopy(self.body[-1]))
+
+        def forward(self, noise_init, noise_amp, mode='rand'):
+            _check_device(noise_init)
+            head, norm = self.head.conv, self.head.norm
+            # head(F.pad(noise, 1)) with a valid convolution == the same convolution with padding 1 (zero fill in the TMA box /
+            # halo loads); BatchNorm statistics run over the output, which is identical
+            x = ops.conv_bn_lrelu(noise_init.contiguous(), head.weight, head.bias, norm.weight, norm.bias, norm.running_mean,
+                                  norm.running_var, norm.num_batches_tracked, 1, momentum=norm.momentum, eps=norm.eps, slope=LRELU_SLOPE)
+            x_prev_out = _run_chain(self.body[0], ops.PadWide.apply(x, self.margin))
+            for idx, block in enumerate(self.body[1:], 1):
+                size = images.video_target_size(idx, self.opt)
+                x_up = ops.UpsampleWide.apply(x_prev_out, tuple(size), None, 0.0)
+                if mode == 'rand':
+                    big = tuple(s + 2 * self.margin for s in size)
+                    n, c = x_prev_out.shape[0], x_prev_out.shape[-1]
+                    noise = images.generate_noise(size=[n, c] + list(big), device=x_prev_out.device)
+                    x_in = ops.UpsampleWide.apply(x_prev_out, big, noise, float(noise_amp[idx]))
+                else:
+                    x_in = ops.PadWide.apply(x_up, self.margin)
+                x_prev_out = ops.AddWide.apply(_run_chain(block, x_in), x_up)
+            tail = self.tail[0]
+            out = ops.conv(x_prev_out, tail.weight, tail.bias, 1, False)      # tail(F.pad(x, 1)), valid conv == padding 1
+            return ops.TanhAdd.apply(out, None)
+
+    class WDiscriminatorBaselines(nn.Module):
+        """BatchNorm critic of the SinGAN-style baselines (reference modules/networks_3d.py:184-210): the input is zero-padded
+        by num_layer + 2 voxels, head = conv + LeakyReLU, num_layer ConvBlocks, plain tail conv.  Forward and first-order
+        backward run on the library's kernels; the WGAN-GP double backward through BatchNorm is not implemented (the
+        BatchNorm node is once-differentiable: calc_gradient_penalty(...).backward() raises) — the reference's default critic
+        for every script, WDiscriminator3D, has no BatchNorm and is fully covered.  3-D only."""
+
+        def __init__(self, opt):
+            super().__init__()
+            if dims != 3:
+                raise NotImplementedError("WDiscriminatorBaselines exists only in networks_3d")
+            self.opt = opt
+            nfc = int(opt.nfc)
+            self.p3d = (opt.num_layer + 2,) * 6
+            self.head = _ConvBlock(opt.nc_im, nfc, opt.ker_size, opt.padd_size, stride=1, bn=False, act='lrelu')
+            self.body = nn.Sequential()
+            for i in range(opt.num_layer):
+                self.body.add_module('block%d' % i, _ConvBlock(nfc, nfc, opt.ker_size, opt.padd_size, stride=1, bn=True, act='lrelu'))
+            self.tail = Conv(nfc, 1, kernel_size=opt.ker_size, padding=opt.padd_size, stride=1)
+            self.apply(weights_init)
+
+        def forward(self, x):
+            _check_device(x)
+            h = self.head.run(F.pad(x, self.p3d).contiguous())
+            h = _run_chain(self.body, h)
+            return ops.conv(h, self.tail.weight, self.tail.bias, int(self.opt.padd_size), False)
+
     return {
         'ConvBlock': _ConvBlock, 'ConvBlockSN': _ConvBlockSN, 'FeatureExtractor': FeatureExtractor, 'EncodeVAE': EncodeVAE,
         'WDiscriminator': WDiscriminator, 'GeneratorHPVAEGAN': GeneratorHPVAEGAN, 'GeneratorSG': GeneratorSG,
+        'GeneratorCSG': GeneratorCSG, 'WDiscriminatorBaselines': WDiscriminatorBaselines,
     }
 
 

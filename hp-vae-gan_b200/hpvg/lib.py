@@ -22,6 +22,7 @@ PROTOTYPES = {
     "hpvg_debug_set_clock_buffer": (c_int, [c_void_p]),
     "hpvg_profile_enable": (c_int, [c_int]),
     "hpvg_set_pdl": (c_int, [c_int]),
+    "hpvg_set_conv_col_mode": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -43,6 +44,11 @@ PROTOTYPES = {
     "hpvg_upsample_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),
     "hpvg_upsample_linear_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpvg_upsample_linear_wide_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_int, c_void_p]),
+    "hpvg_upsample_linear_wide_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpvg_pad_wide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpvg_add_wide": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "hpvg_tanh_add_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "hpvg_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "hpvg_reparam_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p]),
@@ -122,6 +128,12 @@ def get_conv_backend():
 
 
 PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow"}
+
+
+def set_conv_col_mode(mode):
+    """0 = brick tcgen05 kernel always (default), 1 = column-streaming kernel whenever supported, -1 = by volume;
+    returns the previous mode"""
+    return int(load().hpvg_set_conv_col_mode(int(mode)))
 
 
 def set_pdl(on):

@@ -615,6 +615,80 @@ class UpsampleLinear(Function):
         return gx, None, None, None
 
 
+class UpsampleWide(Function):
+    """the same resize on a wide tensor [N,D,H,W,C] (GeneratorCSG resizes its nfc-channel feature maps, reference
+    modules/networks_3d.py:252-261); `noise`: float32 [N,C,Do,Ho,Wo] as the reference draws it, or None"""
+
+    @staticmethod
+    def forward(ctx, x, size, noise, amp):
+        _require_cuda(x, noise)
+        if not is_wide(x):
+            raise TypeError("UpsampleWide takes a wide (bf16 NDHWC) tensor")
+        x = x.contiguous()
+        n, c, d, h, w = dims_of(x)
+        do, ho, wo = size
+        out = _empty(n, c, do, ho, wo, True, x.device)
+        if noise is not None:
+            noise = noise.contiguous()
+            if tuple(noise.shape) != (n, c, do, ho, wo) or noise.dtype != torch.float32:
+                raise ValueError("noise must be float32 of shape %s, got %s %s" % ((n, c, do, ho, wo), noise.dtype, tuple(noise.shape)))
+        lib.call("hpvg_upsample_linear_wide_fwd", _ptr(x), _ptr(out), _ptr(noise), float(amp), n, c, d, h, w, do, ho, wo, _stream())
+        ctx.geom = (n, c, d, h, w, do, ho, wo)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        n, c, d, h, w, do, ho, wo = ctx.geom
+        gout = gout.contiguous()
+        gx = _empty(n, c, d, h, w, True, gout.device)
+        lib.call("hpvg_upsample_linear_wide_bwd", _ptr(gout), _ptr(gx), n, c, d, h, w, do, ho, wo, _stream())
+        return gx, None, None, None
+
+
+def pad_wide_raw(x, pad):
+    n, c, d, h, w = dims_of(x)
+    out = _empty(n, c, d + 2 * pad, h + 2 * pad, w + 2 * pad, True, x.device)
+    lib.call("hpvg_pad_wide", _ptr(x.contiguous()), _ptr(out), n, c, d, h, w, int(pad), _stream())
+    return out
+
+
+class PadWide(Function):
+    """F.pad(x, (pad,) * 6) with zeros on a wide tensor (reference modules/networks_3d.py:205,248,264); the adjoint crops."""
+
+    @staticmethod
+    def forward(ctx, x, pad):
+        _require_cuda(x)
+        if not is_wide(x):
+            raise TypeError("PadWide takes a wide (bf16 NDHWC) tensor")
+        ctx.pad = int(pad)
+        return pad_wide_raw(x, ctx.pad)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return pad_wide_raw(g.contiguous(), -ctx.pad), None
+
+
+class AddWide(Function):
+    """a + b on wide tensors: the stage residual of GeneratorCSG (reference modules/networks_3d.py:265)"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        if not (is_wide(a) and is_wide(b)) or a.shape != b.shape:
+            raise ValueError("AddWide takes two wide tensors of equal shape")
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        lib.call("hpvg_add_wide", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return g, g
+
+
 class TanhAdd(Function):
     """tanh(a + b) (b optional) on thin tensors (reference modules/networks_3d.py:377,404)."""
 

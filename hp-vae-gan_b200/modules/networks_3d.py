@@ -26,6 +26,8 @@ Encode3DVAE = _export('EncodeVAE', 'Encode3DVAE')                      # referen
 WDiscriminator3D = _export('WDiscriminator', 'WDiscriminator3D')       # reference :163-181
 GeneratorHPVAEGAN = _export('GeneratorHPVAEGAN', 'GeneratorHPVAEGAN')  # reference :325-406
 GeneratorSG = _export('GeneratorSG', 'GeneratorSG')                    # reference :272-322
+GeneratorCSG = _export('GeneratorCSG', 'GeneratorCSG')                 # reference :213-269
+WDiscriminatorBaselines = _export('WDiscriminatorBaselines', 'WDiscriminatorBaselines')   # reference :184-210
 
 
 def get_activation(act):
@@ -63,6 +65,4 @@ def _out_of_scope(name, where):
 
 Encode3DVAE_nb = _out_of_scope('Encode3DVAE_nb', 'modules/networks_3d.py:110-138')
 Encode3DVAE1x1 = _out_of_scope('Encode3DVAE1x1', 'modules/networks_3d.py:141-160')
-WDiscriminatorBaselines = _out_of_scope('WDiscriminatorBaselines', 'modules/networks_3d.py:184-210')
-GeneratorCSG = _out_of_scope('GeneratorCSG', 'modules/networks_3d.py:213-269')
 GeneratorVAE_nb = _out_of_scope('GeneratorVAE_nb', 'modules/networks_3d.py:409-485')

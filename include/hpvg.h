@@ -60,6 +60,11 @@ int hpvg_profile_enable(int on);
  * global memory, so consecutive launches of a stream overlap launch latency and set-up with the predecessor's tail.
  * Returns the previous setting. */
 int hpvg_set_pdl(int on);
+/* Which tcgen05 kernel runs the 3-D 64-input-channel wide layers: 0 = brick kernel conv_tc.cu always (default: measured
+ * faster at every BASELINE volume), 1 = column-streaming kernel conv_col.cu whenever it supports the layer, -1 = column
+ * kernel when the brick kernel would have at most two units per SM.  Initial value from HPVG_TC_COL.  Returns the previous
+ * mode. */
+int hpvg_set_conv_col_mode(int mode);
 int hpvg_profile_dump(double* rows, int max_rows);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -152,6 +157,19 @@ int hpvg_upsample_linear_fwd(const float* x, float* out, const float* noise, flo
                              int Di, int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
 int hpvg_upsample_linear_bwd(const float* gout, float* gx, int NC, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                              void* stream);
+
+/* The same resize on NDHWC_BF16 tensors (C a multiple of 8) for GeneratorCSG, which resizes its nfc-channel feature maps
+ * between stages (networks_3d.py:252-261): out = resize(x) [+ noise_amp * noise], `noise` float32 NCDHW [N][C][Do][Ho][Wo]
+ * as the reference draws it (may be NULL); and the adjoint in gather form. */
+int hpvg_upsample_linear_wide_fwd(const void* x, void* out, const float* noise, float noise_amp, int N, int C, int Di,
+                                  int Hi, int Wi, int Do, int Ho, int Wo, void* stream);
+int hpvg_upsample_linear_wide_bwd(const void* gout, void* gx, int N, int C, int Di, int Hi, int Wi, int Do, int Ho,
+                                  int Wo, void* stream);
+/* F.pad(x, (pad,)*6) with zeros on an NDHWC_BF16 tensor (networks_3d.py:205,248,264); pad < 0 crops (its adjoint):
+ * x [N][D][H][W][C] -> out [N][D+2pad][H+2pad][W+2pad][C] */
+int hpvg_pad_wide(const void* x, void* out, int N, int C, int D, int H, int W, int pad, void* stream);
+/* out = a + b on NDHWC_BF16 tensors: the stage residual x_prev + x_prev_out_up of GeneratorCSG (networks_3d.py:265) */
+int hpvg_add_wide(const void* a, const void* b, void* out, long long numel, void* stream);
 
 /* out = tanh(a + b)  (b may be NULL) — torch.tanh(block(x) + x_up), torch.tanh(decoder(z))
  * (networks_3d.py:377,404).  bwd: g = gout * (1 - out^2). */

@@ -283,6 +283,46 @@ def generator_sg(sd, opt, noise_init, noise_amp, mode='rand', noises=None):
     return torch.tanh(x)
 
 
+def generator_csg(sd, opt, noise_init, noise_amp, mode='rand', noises=None):
+    """GeneratorCSG.forward (networks_3d.py:246-269): BatchNorm head on the noise padded by 1, stages of num_layer pad-0
+    ConvBlocks on inputs zero-padded by num_layer voxels, chained in feature space (resize, + noise, residual add), one
+    conv + tanh tail on the result padded by 1"""
+    m = opt.num_layer
+
+    def body(k, h):
+        for i in range(opt.num_layer):
+            h = conv_block(sd, 'body.%d.block%d.' % (k, i), h, 0)
+        return h
+
+    x = conv_block(sd, 'head.', F.pad(noise_init, (1,) * 6), 0)
+    x = body(0, F.pad(x, (m,) * 6))
+    k = 1
+    while 'body.%d.block0.conv.weight' % k in sd:
+        x_up = store(upscale(x, k, opt))
+        if mode == 'rand':
+            big = resize(x, [s + 2 * m for s in x_up.shape[-3:]])
+            noise = noises[k] if noises is not None else torch.zeros_like(big).normal_(0, 1)
+            x_in = store(big + noise * noise_amp[k])
+        else:
+            x_in = F.pad(x_up, (m,) * 6)
+        x = store(body(k, x_in) + x_up)
+        k += 1
+    return torch.tanh(conv(F.pad(x, (1,) * 6), mma_weight(sd['tail.0.weight']), sd['tail.0.bias'], 0))
+
+
+def discriminator_baselines(sd, opt, x):
+    """WDiscriminatorBaselines.forward (networks_3d.py:204-210): input zero-padded by num_layer + 2, conv + LeakyReLU head,
+    num_layer ConvBlocks (BatchNorm), plain tail conv, all with padding opt.padd_size"""
+    m = opt.num_layer + 2
+    x = F.pad(x, (m,) * 6)
+    w = sd['head.conv.weight']
+    h = conv(head_operand(x, w), head_operand(mma_weight(w), w), sd['head.conv.bias'], opt.padd_size)
+    h = store(F.leaky_relu(store_grad(h), SLOPE))
+    for i in range(opt.num_layer):
+        h = conv_block(sd, 'body.block%d.' % i, h, opt.padd_size)
+    return conv(h, mma_weight(sd['tail.weight']), sd['tail.bias'], opt.padd_size)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # deterministic weights and options (shared by the fixture generator, the CPU tests and the GPU tests)
 # ------------------------------------------------------------------------------------------------------------------

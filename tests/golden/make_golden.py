@@ -1,6 +1,8 @@
 """Generate the golden fixtures in this directory from the UNMODIFIED reference (run in the build container only):
 
     python tests/golden/make_golden.py            # needs /root/reference, writes tests/golden/*.pt
+    python tests/golden/make_golden.py train      # the training-loop fixtures
+    python tests/golden/make_golden.py baselines  # GeneratorCSG / WDiscriminatorBaselines fixtures
 
 Each fixture holds deterministic closed-form weights' *recipe* (oracle.port.det_fill seed), the inputs, and what the
 reference's own modules (modules/networks_3d.py, networks_2d.py, losses.py, utils.py) computed from them on CPU in
@@ -174,6 +176,59 @@ def sg_case(name, opt, stages):
     print(name, 'loss', fx['rec']['loss'], 'out', tuple(out.shape))
 
 
+def csg_case(name, opt, stages, full_grads):
+    """GeneratorCSG (the default generator of train_video_baselines.py): reconstruction pass + gradients, and a 'rand' pass
+    with the noise the reference draws under a fixed seed"""
+    g = networks_3d.GeneratorCSG(opt)
+    for _ in range(stages):
+        g.init_next_stage()
+    port.det_fill(g.state_dict(), seed=5)
+    s0, t0 = port.scale_size(0, opt), port.time_depth(0, opt)
+    z = port.det_tensor((1, 3, t0, s0, s0), 43)
+    amps = [1.0] + [0.1] * stages
+    fx = {'opt': dict(opt.__dict__), 'stages': stages, 'fill_seed': 5, 'z': z, 'amps': amps,
+          'state': [(k, tuple(v.shape)) for k, v in g.state_dict().items()]}
+    out = g(z, amps, mode='rec')
+    target = port.det_tensor(tuple(out.shape), 44)
+    loss = F.mse_loss(out, target)
+    g.zero_grad()
+    loss.backward()
+    fx['rec'] = {'out': out.detach().clone(), 'target': target, 'loss': loss.item(), 'grads': grads_of(g, full_grads),
+                 'buffers': buffers_of(g)}
+    import utils as ref_utils
+    m = opt.num_layer
+    torch.manual_seed(19)
+    noises = {}
+    x = torch.zeros(1, 3, t0, s0, s0)
+    for idx in range(1, stages + 1):
+        x = ref_utils.upscale(x, idx, opt)
+        noises[idx] = torch.zeros(1, opt.nfc, *[s + 2 * m for s in x.shape[-3:]]).normal_(0, 1)
+    torch.manual_seed(19)
+    with torch.no_grad():
+        fake = g(z, amps, mode='rand')
+    fx['rand'] = {'noises': noises, 'fake': fake.clone()}
+    torch.save(fx, os.path.join(HERE, name + '.pt'))
+    print(name, 'loss', fx['rec']['loss'], 'out', tuple(out.shape))
+
+
+def dbase_case(name, opt, shape, full_grads):
+    """WDiscriminatorBaselines: critic outputs and the first-order gradients of -D(real).mean() + D(fake).mean()"""
+    d = networks_3d.WDiscriminatorBaselines(opt)
+    port.det_fill(d.state_dict(), seed=9)
+    real = port.det_tensor(shape, 33)
+    fake = port.det_tensor(shape, 34, scale=0.8)
+    fx = {'opt': dict(opt.__dict__), 'fill_seed': 9, 'real': real, 'fake': fake,
+          'state': [(k, tuple(v.shape)) for k, v in d.state_dict().items()]}
+    d.zero_grad()
+    out_real = d(real)
+    out_fake = d(fake)
+    (-out_real.mean() + out_fake.mean()).backward()
+    fx.update({'out_real': out_real.detach().clone(), 'out_fake': out_fake.detach().clone(), 'grads': grads_of(d, full_grads),
+               'buffers': buffers_of(d)})
+    torch.save(fx, os.path.join(HERE, name + '.pt'))
+    print(name, 'out', tuple(out_real.shape))
+
+
 class DrawQueue(object):
     """feeds pre-generated draws to the reference's own normal_() / torch.rand() call sites, in call order, and records
     nothing else: the reference modules stay unmodified, only the source of randomness is replaced"""
@@ -311,6 +366,12 @@ def train_case(name, opt, scale_idx, iters, seed=0):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'baselines':
+        csg_case('csg3d_tiny', tiny_opt(num_layer=2), stages=2, full_grads=True)
+        csg_case('csg3d_wide', port.Opt(nfc=64, num_layer=3, img_size=20, min_size=12, sampling_rates=[4, 2, 1]), stages=1, full_grads=False)
+        dbase_case('dbase3d_tiny', tiny_opt(num_layer=2), (1, 3, 4, 12, 11), True)
+        dbase_case('dbase3d_wide', port.Opt(nfc=64, num_layer=3), (1, 3, 4, 14, 12), False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         train_case('train_vae_tiny', tiny_opt(), scale_idx=1, iters=12)
         train_case('train_gan_tiny', tiny_opt(), scale_idx=2, iters=8)

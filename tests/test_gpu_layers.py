@@ -339,3 +339,44 @@ def test_tcgen05_kernels_with_several_units_per_cta(cin, cout, vol, pad):
     if wide_out:
         assert rel_err(gx.float(), gx_ref.float()) < 3e-3
         assert rel_err(dw, dw_ref) < 1e-3
+
+
+@pytest.mark.parametrize("col_mode", [0, 1])
+@pytest.mark.parametrize("n,cout,vol,pad", [(1, 64, (16, 64, 64), 1), (2, 64, (5, 19, 21), 1), (1, 128, (7, 40, 24), 1), (1, 64, (11, 30, 17), 0),
+                                            (1, 64, (19, 16, 8), 1), (1, 64, (1, 9, 9), 1), (1, 64, (37, 64, 64), 1)])
+def test_both_tcgen05_conv_kernels_match_cuda_core(col_mode, n, cout, vol, pad):
+    """The brick kernel (conv_tc.cu, col_mode 0) and the column-streaming kernel (conv_col.cu, col_mode 1) on the same
+    64-input-channel layers — forward with bias + LeakyReLU + BatchNorm sums, data gradient with the fused LeakyReLU' mask —
+    against the library's CUDA-core kernels: ragged bricks, batch 2, Cout 128, valid (pad 0) convolution and its pad-2 data
+    gradient, columns longer than one 8-slice segment, a single d-slice, and the BASELINE config-2 volume."""
+    from hpvg import lib, ops
+    d, h, w = vol
+    x = _wide_randn((n, d, h, w, 64), 21)
+    gen = torch.Generator(device='cuda').manual_seed(22)
+    wt = (torch.randn((cout, 64, 3, 3, 3), device='cuda', generator=gen) * 0.02).bfloat16().float()
+    bias = torch.randn((cout,), device='cuda', generator=gen)
+    res = {}
+    prev = lib.set_conv_col_mode(col_mode)
+    try:
+        for backend in (lib.BACKEND_TCGEN05, lib.BACKEND_DIRECT):
+            lib.set_conv_backend(backend)
+            stats = torch.zeros(2 * cout, device='cuda')
+            y = ops.conv_raw(x, wt, bias, pad, False, True, act_slope=0.2, stats=stats)
+            y_plain = ops.conv_raw(x, wt, None, pad, False, True)
+            g = _wide_randn(tuple(y.shape), 23)
+            gx = ops.conv_raw(g, wt, None, 2 - pad, True, True)
+            res[backend] = (y, y_plain, stats, gx)
+            if cout == 64:
+                msrc = _wide_randn(tuple(x.shape), 24)
+                res[backend] += (ops.conv_raw(g, wt, None, 2 - pad, True, True, mask_src=msrc, mask_slope=0.2),)
+    finally:
+        lib.set_conv_backend(lib.BACKEND_AUTO)
+        lib.set_conv_col_mode(prev)
+    tc, ref = res[lib.BACKEND_TCGEN05], res[lib.BACKEND_DIRECT]
+    assert rel_err(tc[0].float(), ref[0].float()) < 3e-3
+    assert rel_err(tc[1].float(), ref[1].float()) < 3e-3
+    yf = tc[0].float().reshape(-1, cout)
+    assert rel_err(tc[2][:cout], yf.sum(0)) < 1e-4 and rel_err(tc[2][cout:], (yf * yf).sum(0)) < 1e-4
+    assert rel_err(tc[3].float(), ref[3].float()) < 3e-3
+    if cout == 64:
+        assert rel_err(tc[4].float(), ref[4].float()) < 3e-3

@@ -229,6 +229,99 @@ def test_generator_sg_parity(golden, monkeypatch):
     assert rel_err(fake, fx['rand']['fake']) < REF_OUT_TOL
 
 
+@pytest.mark.parametrize("name", ["csg3d_tiny", "csg3d_wide"])
+def test_generator_csg_parity(golden, monkeypatch, name):
+    """GeneratorCSG (reference modules/networks_3d.py:213-269, default generator of train_video_baselines.py): feature-space
+    pyramid — wide zero-pad, wide trilinear resize (+ noise), wide residual add (wide_ops.cu) around the pad-0 ConvBlocks"""
+    from hpvg import images
+    from modules import networks_3d
+    fx = golden(name)
+    opt = opt_from(fx)
+    g = _cuda_module(networks_3d.GeneratorCSG, opt, fx, stages=fx['stages'])
+    fam = _family(name)
+
+    sd = with_grad(state_from(fx))
+    with port.storage('bf16'):
+        e_out = port.generator_csg(sd, opt, fx['z'], fx['amps'], mode='rec')
+        F.mse_loss(e_out, fx['rec']['target']).backward()
+
+    out = g(fx['z'].cuda(), fx['amps'], mode='rec')
+    _REPORT[name + '/out'] = {'vs_emu': rel_err(out, e_out), 'vs_ref': rel_err(out, fx['rec']['out'])}
+    assert out.shape == fx['rec']['out'].shape and out.dtype == torch.float32
+    assert rel_err(out, e_out) < EMU_OUT_TOL
+    assert rel_err(out, fx['rec']['out']) < REF_OUT_TOL
+    loss = F.mse_loss(out, fx['rec']['target'].cuda())
+    assert abs(loss.item() - fx['rec']['loss']) < LOSS_TOL * fx['rec']['loss']
+    g.zero_grad()
+    loss.backward()
+    _check_grads(g, _oracle_grads(sd), 2 * EMU_GRAD_TOL[fam], 2e-3, name + '/grads_vs_emu')
+    _check_grads(g, fx['rec']['grads'], REF_GRAD_TOL[fam], 2e-3, name + '/grads_vs_ref')
+    bufs = dict(g.named_buffers())
+    for k, b in fx['rec']['buffers'].items():
+        if b.is_floating_point():
+            assert rel_err(bufs[k], b) < REF_OUT_TOL, k
+    noises = [fx['rand']['noises'][k] for k in sorted(fx['rand']['noises'])]
+    monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
+    with torch.no_grad():
+        fake = g(fx['z'].cuda(), fx['amps'], mode='rand')
+    assert rel_err(fake, fx['rand']['fake']) < REF_OUT_TOL
+
+
+@pytest.mark.parametrize("name", ["dbase3d_tiny", "dbase3d_wide"])
+def test_discriminator_baselines_parity(golden, name):
+    """WDiscriminatorBaselines (reference modules/networks_3d.py:184-210): outputs and first-order gradients; the gradient
+    penalty through its BatchNorm layers is refused loudly (once-differentiable node), never computed wrongly"""
+    from modules import networks_3d
+    from modules import utils as mutils
+    fx = golden(name)
+    opt = opt_from(fx)
+    d = _cuda_module(networks_3d.WDiscriminatorBaselines, opt, fx)
+    fam = _family(name)
+    sd = with_grad(state_from(fx))
+    with port.storage('bf16'):
+        e_real = port.discriminator_baselines(sd, opt, fx['real'])
+        e_fake = port.discriminator_baselines(sd, opt, fx['fake'])
+        (-e_real.mean() + e_fake.mean()).backward()
+    out_real, out_fake = d(fx['real'].cuda()), d(fx['fake'].cuda())
+    assert out_real.shape == fx['out_real'].shape
+    assert rel_err(out_real, e_real) < EMU_OUT_TOL and rel_err(out_fake, e_fake) < EMU_OUT_TOL
+    assert rel_err(out_real, fx['out_real']) < REF_OUT_TOL and rel_err(out_fake, fx['out_fake']) < REF_OUT_TOL
+    d.zero_grad()
+    (-out_real.mean() + out_fake.mean()).backward()
+    _check_grads(d, _oracle_grads(sd), 2 * EMU_GRAD_TOL[fam], 2e-3, name + '/grads_vs_emu')
+    _check_grads(d, fx['grads'], REF_GRAD_TOL[fam], 2e-3, name + '/grads_vs_ref')
+    with pytest.raises(RuntimeError):
+        mutils.calc_gradient_penalty(d, fx['real'].cuda(), fx['fake'].cuda(), 0.1, 'cuda').backward()
+
+
+def test_wide_resize_pad_add_match_torch():
+    """wide_ops.cu against torch on the same bf16 values: trilinear resize (align_corners) with and without the NCDHW float32
+    noise term, its adjoint, zero-pad and crop, residual add"""
+    from hpvg import ops
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    for c, (d, h, w), (do, ho, wo) in ((64, (3, 9, 11), (5, 14, 13)), (8, (2, 6, 6), (2, 16, 15)), (64, (6, 54, 54), (16, 64, 64))):
+        x = torch.randn((2, d, h, w, c), device='cuda', generator=gen).bfloat16().requires_grad_(True)
+        noise = torch.randn((2, c, do, ho, wo), device='cuda', generator=gen)
+        xt = x.detach().float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+        ref = F.interpolate(xt, size=[do, ho, wo], mode='trilinear', align_corners=True)
+        y = ops.UpsampleWide.apply(x, (do, ho, wo), None, 0.0)
+        assert rel_err(y.float().permute(0, 4, 1, 2, 3), ref) < 4e-3               # one bf16 rounding of the result
+        yn = ops.UpsampleWide.apply(x, (do, ho, wo), noise, 0.3)
+        assert rel_err(yn.float().permute(0, 4, 1, 2, 3), ref + 0.3 * noise) < 4e-3
+        g = torch.randn(tuple(y.shape), device='cuda', generator=gen).bfloat16()
+        y.backward(g)
+        ref.backward(g.float().permute(0, 4, 1, 2, 3))
+        assert rel_err(x.grad.float().permute(0, 4, 1, 2, 3), xt.grad) < 4e-3
+        p = ops.PadWide.apply(x, 2)
+        assert torch.equal(p.float().permute(0, 4, 1, 2, 3), F.pad(xt.detach(), (2,) * 6))
+        x.grad = None
+        gp = torch.randn(tuple(p.shape), device='cuda', generator=gen).bfloat16()
+        p.backward(gp)
+        assert torch.equal(x.grad, gp[:, 2:-2, 2:-2, 2:-2, :])
+        b = torch.randn(tuple(x.shape), device='cuda', generator=gen).bfloat16()
+        assert torch.equal(ops.AddWide.apply(x.detach(), b), (x.detach().float() + b.float()).bfloat16())
+
+
 @pytest.mark.parametrize("nfc", [8, 64])
 def test_fused_lrelu_mask_backward_matches_unfused(monkeypatch, nfc):
     """ops.ChainLink / ops._MaskLink: the critic's first-order backward and the gradient-penalty double backward with the

@@ -87,6 +87,40 @@ def test_generator_sg_matches_reference(golden):
     assert rel_err(fake, fx['rand']['fake']) < TOL
 
 
+@pytest.mark.parametrize("name", ["csg3d_tiny", "csg3d_wide"])
+def test_generator_csg_matches_reference(golden, name):
+    """GeneratorCSG (networks_3d.py:213-269), the default generator of train_video_baselines.py"""
+    fx = golden(name)
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    out = port.generator_csg(sd, opt, fx['z'], fx['amps'], mode='rec')
+    assert rel_err(out, fx['rec']['out']) < TOL
+    loss = F.mse_loss(out, fx['rec']['target'])
+    assert abs(loss.item() - fx['rec']['loss']) < TOL
+    loss.backward()
+    _check_grads(sd, fx['rec']['grads'], 5e-4)
+    for k, b in fx['rec']['buffers'].items():
+        assert rel_err(sd[k].float(), b.float()) < 1e-5, k
+    with torch.no_grad():
+        fake = port.generator_csg(sd, opt, fx['z'], fx['amps'], mode='rand', noises=fx['rand']['noises'])
+    assert rel_err(fake, fx['rand']['fake']) < TOL
+
+
+@pytest.mark.parametrize("name", ["dbase3d_tiny", "dbase3d_wide"])
+def test_discriminator_baselines_matches_reference(golden, name):
+    """WDiscriminatorBaselines (networks_3d.py:184-210): outputs and first-order gradients"""
+    fx = golden(name)
+    opt = opt_from(fx)
+    sd = with_grad(state_from(fx))
+    out_real = port.discriminator_baselines(sd, opt, fx['real'])
+    out_fake = port.discriminator_baselines(sd, opt, fx['fake'])
+    assert rel_err(out_real, fx['out_real']) < TOL and rel_err(out_fake, fx['out_fake']) < TOL
+    (-out_real.mean() + out_fake.mean()).backward()
+    _check_grads(sd, fx['grads'], 5e-4)
+    for k, b in fx['buffers'].items():
+        assert rel_err(sd[k].float(), b.float()) < 1e-5, k
+
+
 def test_scale_schedule(golden):
     fx = golden("hp3d_tiny")
     opt = opt_from(fx)
