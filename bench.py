@@ -318,13 +318,17 @@ def run_hpvg(args):
     # generation (BASELINE config 4): fresh z per draw through the whole pyramid, batch 1, draws split over ranks
     _, draws_rank = train.draws_for_rank(args.draws, world, rank)
     draws_rank = max(1, draws_rank)
-    sampler = train.Sampler(G, o, dev, batch=1, graph=use_graph, streams=args.gen_streams, static_weights=True)   # G is not trained during this leg
+    gen_batch = max(1, min(args.gen_batch, draws_rank))
+    gen_calls = max(1, draws_rank // gen_batch)
+    draws_rank = gen_calls * gen_batch
+    # batch > 1: every draw is normalised with its own BatchNorm statistics (ops.bn_per_sample), i.e. the reference's batch-1 draws
+    sampler = train.Sampler(G, o, dev, batch=gen_batch, graph=use_graph, streams=args.gen_streams, static_weights=True)   # G is not trained during this leg
     frames = [0]
 
     def gen_all():
         n = 0
         sampler.begin()
-        for _ in range(draws_rank):
+        for _ in range(gen_calls):
             n += sampler.frames_per_call(sampler.sample())
         sampler.wait()
         frames[0] = n
@@ -378,7 +382,8 @@ def run_hpvg(args):
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "model_tflops": value * (CONV_GFLOP_PER_ITER if WORKLOAD["name"] == "cfg2" else 12650.99) / 1e3 / world,
                 "generation": {"metric": "generated_frames_per_s", "value": world * frames[0] / (ms_gen * 1e-3), "unit": "frames/s",
-                               "draws": args.draws, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": 1,
+                               "draws": draws_rank * world, "frames_per_draw": level_shape(o, o.scale_idx)[2], "batch": gen_batch,
+                               "batchnorm": "per-draw statistics (each draw normalised as in a batch-1 forward)",
                                "ms_per_draw": ms_gen / draws_rank, "streams": sampler.nstreams,
                                "note": "draws split over ranks, no collective; rank 0's share timed x N (equal shares)"}}
         if distributed:
@@ -406,6 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
     ap.add_argument("--draws", type=int, default=256, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
+    ap.add_argument("--gen-batch", type=int, default=8, help="draws per forward of the generation leg; BatchNorm statistics stay per draw")
     ap.add_argument("--gen-streams", type=int, default=4, help="independent draws in flight on separate CUDA streams (generation leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")

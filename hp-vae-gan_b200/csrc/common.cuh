@@ -90,6 +90,7 @@ struct ConvGeom {
   int Di, Hi, Wi;  // input extents
   int Do, Ho, Wo;  // output extents = input + 2*pad - 2 on every filtered axis
   int KD, taps, pad, pad_d;
+  int stats_stride;  // floats between the BatchNorm-sum blocks of consecutive samples (0: one [2*Cout] block for the batch)
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ static int make_geom(ConvGeom& g, int N, int Cin, int Cout, int D, int H, int W,
   g.N = N; g.Cin = Cin; g.Cout = Cout;
   g.Di = D; g.Hi = H; g.Wi = W;
   g.KD = KD; g.taps = KD * 9; g.pad = pad; g.pad_d = (KD == 3) ? pad : 0;
+  g.stats_stride = 0;
   g.Do = D + 2 * g.pad_d - (KD - 1);
   g.Ho = H + 2 * pad - 2;
   g.Wo = W + 2 * pad - 2;
@@ -55,8 +56,16 @@ extern "C" {
 int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* w_packed, const float* bias, void* y, int y_fmt, int N,
                       int Cin, int Cout, int D, int H, int W, int KD, int pad, int transposed, int act, float lrelu_slope, float* stats,
                       const void* mask_src, void* stream) {
+  return hpvg_conv_forward_ex(x, x_fmt, w_f32, w_packed, bias, y, y_fmt, N, Cin, Cout, D, H, W, KD, pad, transposed, act, lrelu_slope,
+                              stats, 0, mask_src, stream);
+}
+
+int hpvg_conv_forward_ex(const void* x, int x_fmt, const float* w_f32, const void* w_packed, const float* bias, void* y, int y_fmt, int N,
+                         int Cin, int Cout, int D, int H, int W, int KD, int pad, int transposed, int act, float lrelu_slope,
+                         float* stats, int stats_per_sample, const void* mask_src, void* stream) {
   ConvGeom g;
   if (int rc = make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_forward")) return rc;
+  g.stats_stride = (stats && stats_per_sample) ? 2 * Cout : 0;
   HPVG_CHECK_ARG(x && y, "conv_forward: null tensor");
   HPVG_CHECK_ARG((x_fmt == 0 || x_fmt == 1) && (y_fmt == 0 || y_fmt == 1), "conv_forward: unknown tensor format");
   HPVG_CHECK_ARG(act == HPVG_ACT_NONE || act == HPVG_ACT_LRELU, "conv_forward: unknown activation %d", act);
@@ -84,6 +93,8 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
     prof_end(ph, st);
     return rc;
   }
+  HPVG_CHECK_ARG(g.stats_stride == 0, "conv_forward: per-sample statistics need the tcgen05 or the expand kernel (Cin=%d Cout=%d)", Cin,
+                 Cout);
   void* ph = prof_begin(HPVG_PROF_CONV_DIRECT, flops, st);
   int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
   prof_end(ph, st);

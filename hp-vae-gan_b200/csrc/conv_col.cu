@@ -373,8 +373,9 @@ conv_col_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         stg ^= 1;
       }
       if (p.stats) {
-        atomicAdd(p.stats + s.cb * NC + (et & 31), st_s);
-        atomicAdd(p.stats + g.Cout + s.cb * NC + (et & 31), st_s2);
+        float* sp = p.stats + (size_t)s.n * g.stats_stride;
+        atomicAdd(sp + s.cb * NC + (et & 31), st_s);
+        atomicAdd(sp + g.Cout + s.cb * NC + (et & 31), st_s2);
       }
       tc_fence_before();
       mbar_arrive(bar_hempty(half));

@@ -545,8 +545,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
       if (p.stats) {
-        atomicAdd(p.stats + nb * 64 + (et & 63), st_s);
-        atomicAdd(p.stats + g.Cout + nb * 64 + (et & 63), st_s2);
+        float* sp = p.stats + (size_t)n * g.stats_stride;      // per-sample statistics: a unit lies inside one sample
+        atomicAdd(sp + nb * 64 + (et & 63), st_s);
+        atomicAdd(sp + g.Cout + nb * 64 + (et & 63), st_s2);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty);

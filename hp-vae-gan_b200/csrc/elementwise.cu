@@ -276,6 +276,49 @@ __global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict_
   if (chsum) block_channel_sum(csum, (int)((threadIdx.x % (C >> 3)) << 3), C, red, chsum);
 }
 
+// BatchNorm (batch statistics) + LeakyReLU with statistics PER SAMPLE: stats is [N][2C] (hpvg_conv_forward_ex with
+// stats_per_sample), blockIdx.y = sample.  A batched forward then computes what N separate batch-1 forwards compute — the
+// reference generates every draw with batch size 1 (train_video.py:226-235), and G stays in train mode — without giving up
+// the larger launches.  Inference only: nothing is saved for a backward pass and running statistics are not advanced.
+__global__ void __launch_bounds__(256) bn_apply_lrelu_per_sample_kernel(const uint4* __restrict__ y, const float* __restrict__ stats,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                        float eps, long long count, uint4* __restrict__ out,
+                                                                        long long nvec, int C, float slope) {
+  pdl_enter();
+  extern __shared__ float ss[];  // scale[C], shift[C]
+  const int n = blockIdx.y;
+  const float* st = stats + (size_t)n * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double inv = 1.0 / (double)count;
+    const double mean = (double)st[c] * inv;
+    double var = (double)st[C + c] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    ss[c] = sc;
+    ss[C + c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int cvec = C >> 3;
+  const uint4* yn = y + (size_t)n * nvec;
+  uint4* on = out + (size_t)n * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) << 3;
+    uint4 v = __ldg(yn + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = unpack_bf16x2(w[k]);
+      float a = fmaf(f.x, ss[c0 + 2 * k], ss[C + c0 + 2 * k]);
+      float b = fmaf(f.y, ss[c0 + 2 * k + 1], ss[C + c0 + 2 * k + 1]);
+      a = a > 0.f ? a : a * slope;
+      b = b > 0.f ? b : b * slope;
+      w[k] = pack_bf16x2(a, b);
+    }
+    on[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // ===============================================================================================================
 // linear resize, align_corners=True      reference: utils/images.py:22-26 (F.interpolate trilinear), :9-19 (bilinear)
 // ===============================================================================================================
@@ -826,6 +869,19 @@ int hpvg_bn_finalize_apply_lrelu(const void* y, const float* stats, const float*
       reinterpret_cast<const uint4*>(y), stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, nvox, scale_shift,
       mean_invstd, reinterpret_cast<uint4*>(out), nvec, C, slope);
   HPVG_CHECK_LAUNCH("bn_finalize_apply_lrelu");
+  return 0;
+}
+
+int hpvg_bn_apply_lrelu_per_sample(const void* y, const float* stats, const float* gamma, const float* beta, float eps, void* out,
+                                   int N, long long nvox_per_sample, int C, float slope, void* stream) {
+  HPVG_CHECK_ARG(y && stats && gamma && beta && out, "bn_apply_lrelu_per_sample: null tensor");
+  HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && nvox_per_sample > 0 && N > 0 && N <= 65535,
+                 "bn_apply_lrelu_per_sample: C=%d must be a multiple of 8 (<= 256), 1 <= N <= 65535", C);
+  const long long nvec = nvox_per_sample * (C / 8);
+  const int bx = (int)max(1LL, min(cdiv(nvec, 256), cdiv((long long)num_sms() * 16, N)));
+  launch_k(bn_apply_lrelu_per_sample_kernel, dim3(bx, N), 256, 2 * C * sizeof(float), ST(stream), reinterpret_cast<const uint4*>(y), stats,
+           gamma, beta, eps, nvox_per_sample, reinterpret_cast<uint4*>(out), nvec, C, slope);
+  HPVG_CHECK_LAUNCH("bn_apply_lrelu_per_sample");
   return 0;
 }
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128, 3) expand_conv_kernel(const float* __rest
       }
     }
     __syncthreads();
-    atomicAdd(stats + tid, red[tid]);
+    atomicAdd(stats + (size_t)n * g.stats_stride + tid, red[tid]);
   }
 }
 
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, 2) expand_conv_mma_kernel(const float* __
     atomicAdd(red + 64 + 2 * lane, q0);
     atomicAdd(red + 64 + 2 * lane + 1, q1);
     __syncthreads();
-    if (tid < 128) atomicAdd(stats + tid, red[tid]);
+    if (tid < 128) atomicAdd(stats + (size_t)n * g.stats_stride + tid, red[tid]);
   }
 }
 

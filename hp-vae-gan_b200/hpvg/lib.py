@@ -26,6 +26,10 @@ PROTOTYPES = {
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "hpvg_conv_forward_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "hpvg_bn_apply_lrelu_per_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_longlong, c_int,
+                                               c_float, c_void_p]),
     "hpvg_conv_wgrad_workspace": (c_size_t, [c_int] * 10),
     "hpvg_conv_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_size_t, c_void_p]),

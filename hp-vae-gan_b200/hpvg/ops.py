@@ -154,11 +154,13 @@ def expand_image_for(w, cin, taps, transposed):
     return out
 
 
-def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None, mask_slope=None):
+def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, mask_src=None, mask_slope=None,
+             stats_per_sample=False):
     """One hpvg_conv_forward call.  `w` is the float32 weight of the *forward* convolution ([Cout_f, Cin_f, (3,)3,3]);
     transposed=True computes the data gradient form with it (input channels = Cout_f, output channels = Cin_f).
     mask_src / mask_slope: the epilogue multiplies the result by the LeakyReLU derivative read from `mask_src` (a wide
-    tensor of the output's extents): "dgrad then leaky_relu_backward" in one launch."""
+    tensor of the output's extents): "dgrad then leaky_relu_backward" in one launch.
+    stats_per_sample: `stats` is [N, 2*Cout] and every sample accumulates into its own row (tcgen05 / expand kernels only)."""
     _require_cuda(x, w)
     x = x.contiguous()
     w = w.contiguous()
@@ -188,10 +190,25 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
             raise ValueError("conv: mask_src needs a wide output of the same extents, a slope and no activation")
         mask_src = mask_src.contiguous()
     slope = act_slope if act_slope is not None else (mask_slope if mask_src is not None else 0.0)
-    lib.call("hpvg_conv_forward", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,
-             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE, float(slope), _ptr(stats), _ptr(mask_src),
-             _stream())
+    if stats_per_sample:
+        if stats is None or tuple(stats.shape) != (n, 2 * cout):
+            raise ValueError("per-sample statistics need a [N, 2*Cout] float32 accumulator")
+        if packed is None:
+            raise lib.HpvgError("per-sample statistics need the tcgen05 or the expand kernel (Cin=%d Cout=%d)" % (cin, cout))
+    lib.call("hpvg_conv_forward_ex", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,
+             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE, float(slope), _ptr(stats),
+             int(bool(stats_per_sample)), _ptr(mask_src), _stream())
     return y
+
+
+def per_sample_stats_supported(x, w):
+    """whether conv_raw(x, w, ..., out_wide=True, stats_per_sample=True) has a kernel: the tcgen05 and the thin -> wide layers"""
+    cout, cin = w.shape[0], w.shape[1]
+    if lib.get_conv_backend() == lib.BACKEND_DIRECT:
+        return False
+    if is_wide(x):
+        return cin in (64, 128) and cout % 64 == 0
+    return cin <= 4 and cout == 64
 
 
 def wgrad_raw(x, gy, pad, wshape, want_bias=False):
@@ -571,8 +588,56 @@ class ConvBnLrelu(Function):
         return gx, gw, gb, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
+_BN_PER_SAMPLE = [False]
+
+
+class bn_per_sample:
+    """`with bn_per_sample(True):` — BatchNorm blocks of a no-grad forward normalise every sample of the batch with its OWN
+    statistics, i.e. a batch-B forward computes what B batch-1 forwards compute (the reference generates each draw with batch
+    size 1 and keeps G in train mode, train_video.py:226-235).  Running statistics are not advanced in this mode."""
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = _BN_PER_SAMPLE[0]
+        _BN_PER_SAMPLE[0] = self.on
+
+    def __exit__(self, *a):
+        _BN_PER_SAMPLE[0] = self.prev
+
+
+def _conv_bn_lrelu_per_sample(x, w, bias, gamma, beta, pad, eps, slope):
+    _require_cuda(x, w, gamma, beta)
+    n = x.shape[0]
+    cout = w.shape[0]
+    if not per_sample_stats_supported(x, w):
+        # channel counts without a per-sample kernel: sample by sample through the same kernels
+        outs = []
+        for i in range(n):
+            stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
+            y = conv_raw(x[i:i + 1].contiguous(), w, bias, pad, False, True, stats=stats)
+            o = torch.empty_like(y)
+            _, c, d, h, wd = dims_of(y)
+            lib.call("hpvg_bn_apply_lrelu_per_sample", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), float(eps), _ptr(o), 1,
+                     d * h * wd, c, float(slope), _stream())
+            outs.append(o)
+        return torch.cat(outs, 0)
+    stats = torch.zeros((n, 2 * cout), dtype=torch.float32, device=x.device)
+    y = conv_raw(x, w, bias, pad, False, True, stats=stats, stats_per_sample=True)
+    _, c, d, h, wd = dims_of(y)
+    out = torch.empty_like(y)
+    lib.call("hpvg_bn_apply_lrelu_per_sample", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), float(eps), _ptr(out), n, d * h * wd, c,
+             float(slope), _stream())
+    return out
+
+
 def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum=0.1, eps=1e-5, slope=0.2):
     """ConvBlock3D/2D (reference modules/networks_3d.py:48-56) through the fused node"""
+    if _BN_PER_SAMPLE[0]:
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+            raise lib.HpvgError("per-sample BatchNorm statistics are an inference mode: run it under torch.no_grad()")
+        return _conv_bn_lrelu_per_sample(x, w, bias, gamma, beta, pad, eps, slope)
     token = None
     side = _WGRAD_STREAM[0]
     if side is not None and torch.is_grad_enabled() and w.requires_grad:

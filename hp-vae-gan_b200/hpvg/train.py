@@ -286,15 +286,20 @@ class Sampler:
     config 2: 20.8 k frames/s with 1 stream, 46 k with 4, 50.7 k with 6.  BatchNorm running statistics are not advanced in
     that mode (concurrent draws would race on them; nothing on the path reads them)."""
 
-    def __init__(self, netG, opt, device, batch=1, graph=True, streams=1, static_weights=False):
-        """static_weights=True: the bf16 weight images are packed once, outside the recordings (the generator is not
+    def __init__(self, netG, opt, device, batch=1, graph=True, streams=1, static_weights=False, per_sample_bn=None):
+        """per_sample_bn (default: on when batch > 1): BatchNorm normalises every draw of the batch with its own statistics
+        (ops.bn_per_sample), so `batch` draws per forward give what `batch` batch-1 forwards give — the reference's semantics —
+        in launches large enough to fill the GPU.  per_sample_bn=False with batch > 1 couples the draws through the batch
+        statistics, as the reference's modules would if they were called with a batch.
+        static_weights=True: the bf16 weight images are packed once, outside the recordings (the generator is not
         trained while this sampler is in use; build a new Sampler after its weights change).  Default: every recording
         repacks its images, so replays always read the generator's current weights."""
         self.netG, self.opt, self.device, self.batch = netG, opt, device, batch
         self.static_weights = static_weights
+        self.per_sample_bn = (batch > 1) if per_sample_bn is None else bool(per_sample_bn)
         self.size = [batch] + list(opt.Z_init_size[1:])
         self.nstreams = max(1, int(streams)) if graph else 1
-        self.track_bn = self.nstreams == 1
+        self.track_bn = self.nstreams == 1 and not self.per_sample_bn
         self.graphs, self.streams, self.static_fake = [], [], []
         self.next = 0
         if graph:
@@ -321,7 +326,7 @@ class Sampler:
             torch.cuda.synchronize()
 
     def _draw(self):
-        with ops.bn_running_stats(self.track_bn):
+        with ops.bn_running_stats(self.track_bn), ops.bn_per_sample(self.per_sample_bn):
             z = images.generate_noise(size=self.size, device=self.device)
             fake, _ = self.netG(z, self.opt.Noise_Amps, noise_init=z, mode="rand")
         return fake

@@ -89,6 +89,14 @@ int hpvg_conv_forward(const void* x, int x_fmt, const float* w_f32, const void* 
                       void* y, int y_fmt, int N, int Cin, int Cout, int D, int H, int W, int KD, int pad,
                       int transposed, int act, float lrelu_slope, float* stats, const void* mask_src, void* stream);
 
+/* The same call with BatchNorm sums kept PER SAMPLE: stats is [N][2*Cout] when stats_per_sample != 0 (tcgen05 and
+ * thin -> wide kernels only).  With hpvg_bn_apply_lrelu_per_sample a batched generation forward computes exactly what N
+ * batch-1 forwards compute (the reference draws every sample with batch size 1, train_video.py:226-235). */
+int hpvg_conv_forward_ex(const void* x, int x_fmt, const float* w_f32, const void* w_packed, const float* bias,
+                         void* y, int y_fmt, int N, int Cin, int Cout, int D, int H, int W, int KD, int pad,
+                         int transposed, int act, float lrelu_slope, float* stats, int stats_per_sample,
+                         const void* mask_src, void* stream);
+
 /* Weight gradient of the convolution above (aten::convolution_backward grad_weight, and the
  * "wgrad-as-conv" node of the WGAN-GP double backward, modules/utils.py:14-18):
  *   dw[co][ci][k] = sum_{n,o} gy[n,co,o] * x[n,ci,o+k-pad]        (float32, PyTorch layout, overwritten)
@@ -136,6 +144,10 @@ int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale
 int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
                             float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
                             float slope, int want_chsum, void* stream);
+/* inference-only BatchNorm(batch statistics of each sample) + LeakyReLU: y, out NDHWC_BF16 [N][nvox_per_sample][C],
+ * stats [N][2C] from hpvg_conv_forward_ex(stats_per_sample = 1); no running statistics, nothing saved for a backward */
+int hpvg_bn_apply_lrelu_per_sample(const void* y, const float* stats, const float* gamma, const float* beta, float eps,
+                                   void* out, int N, long long nvox_per_sample, int C, float slope, void* stream);
 int hpvg_bn_finalize_apply_lrelu(const void* y, const float* stats, const float* gamma, const float* beta,
                                  float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                                  float eps, float* scale_shift, float* mean_invstd, void* out, long long nvox, int C,

@@ -294,6 +294,45 @@ def test_discriminator_baselines_parity(golden, name):
         mutils.calc_gradient_penalty(d, fx['real'].cuda(), fx['fake'].cuda(), 0.1, 'cuda').backward()
 
 
+@pytest.mark.parametrize("nfc", [64, 8])
+def test_batched_generation_with_per_sample_batchnorm_equals_batch1_draws(monkeypatch, nfc):
+    """ops.bn_per_sample: a batch-3 'rand' forward of GeneratorHPVAEGAN with per-draw BatchNorm statistics against three
+    batch-1 forwards on the same latents and noise (the reference generates each draw with batch size 1,
+    train_video.py:226-235).  nfc 64: tcgen05 / expand kernels with [N, 2C] statistics; nfc 8: the per-sample fallback."""
+    from hpvg import images, ops
+    from modules import networks_3d
+    opt = port.Opt(nfc=nfc, latent_dim=128 if nfc == 64 else 8, num_layer=2, vae_levels=1, img_size=24, min_size=16, sampling_rates=[4, 2, 1])
+    g = networks_3d.GeneratorHPVAEGAN(opt)
+    g.init_next_stage()
+    g.init_next_stage()
+    port.det_fill(g.state_dict(), 3)
+    g.cuda()
+    b = 3
+    s0, t0 = port.scale_size(0, opt), port.time_depth(0, opt)
+    z = port.det_tensor((b, opt.latent_dim, t0, s0, s0), 71).cuda()
+    shapes = [(3, port.time_depth(i, opt), port.scale_size(i, opt), port.scale_size(i, opt)) for i in (1, 2)]
+    noises = [port.det_tensor((b,) + sh, 72 + i).cuda() for i, sh in enumerate(shapes)]
+    amps = [1.0, 0.1, 0.1]
+    singles = []
+    with torch.no_grad(), ops.bn_running_stats(False):
+        for i in range(b):
+            monkeypatch.setattr(images, "draw_normal", NoiseQueue([nz[i:i + 1] for nz in noises]))
+            fake, _ = g(z[i:i + 1], amps, noise_init=z[i:i + 1], mode='rand')
+            singles.append(fake)
+        monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
+        with ops.bn_per_sample(True):
+            batched, _ = g(z, amps, noise_init=z, mode='rand')
+        monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
+        coupled, _ = g(z, amps, noise_init=z, mode='rand')
+    ref = torch.cat(singles, 0)
+    assert batched.shape == ref.shape
+    assert rel_err(batched, ref) < 1e-2          # same arithmetic; BatchNorm sums are accumulated in a different order
+    assert rel_err(coupled, ref) > 3 * rel_err(batched, ref)      # batch statistics couple the draws: a different function
+    with pytest.raises(Exception):
+        with ops.bn_per_sample(True):
+            g(z, amps, noise_init=z.clone().requires_grad_(True), mode='rand')
+
+
 def test_wide_resize_pad_add_match_torch():
     """wide_ops.cu against torch on the same bf16 values: trilinear resize (align_corners) with and without the NCDHW float32
     noise term, its adjoint, zero-pad and crop, residual add"""
