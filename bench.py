@@ -272,6 +272,17 @@ def run_hpvg(args):
             last["rec_loss"] = out["rec_loss"].item()
         for _ in range(W):
             step_resident()
+    if args.profile_gen:
+        # for `ncu --profile-from-start off`: one forward of the generation leg (gen-batch draws, one stream) between Start/Stop
+        ps = train.Sampler(G, o, dev, batch=max(1, args.gen_batch), graph=use_graph, streams=1, static_weights=True)
+        ps.sample()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        ps.sample()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiled": "one generation forward", "batch": args.gen_batch, "graph": use_graph}), flush=True)
+        return
     if args.profile_one:
         # for `ncu --profile-from-start off`: exactly one replayed (or eager) iteration between cudaProfilerStart/Stop
         torch.cuda.synchronize()
@@ -410,11 +421,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hpvg", choices=["hpvg", "reference"])
-    ap.add_argument("--draws", type=int, default=256, help="noise draws of the generation leg (BASELINE config 4 uses 4096)")
-    ap.add_argument("--gen-batch", type=int, default=8, help="draws per forward of the generation leg; BatchNorm statistics stay per draw")
-    ap.add_argument("--gen-streams", type=int, default=4, help="independent draws in flight on separate CUDA streams (generation leg)")
+    ap.add_argument("--draws", type=int, default=4096, help="noise draws of the generation leg, all ranks together (BASELINE config 4: 4096)")
+    ap.add_argument("--gen-batch", type=int, default=32, help="draws per forward of the generation leg; BatchNorm statistics stay per draw")
+    ap.add_argument("--gen-streams", type=int, default=2, help="independent draws in flight on separate CUDA streams (generation leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")
+    ap.add_argument("--profile-gen", action="store_true", help="run one generation forward between cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
                     help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128)")

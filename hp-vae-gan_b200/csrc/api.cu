@@ -45,8 +45,8 @@ int conv_col_mode() {
   int v = g_col_mode.load(std::memory_order_relaxed);
   if (v == -2) {
     const char* e = getenv("HPVG_TC_COL");
-    v = e ? atoi(e) : 0;      // default: brick kernel (measured faster at every BASELINE volume, see conv_col.cu)
-    if (v < -1 || v > 1) v = 0;
+    v = e ? atoi(e) : -1;     // default: chosen per layer by how well the brick kernel's units fill the SMs (conv_tc.cu)
+    if (v < -1 || v > 1) v = -1;
     g_col_mode.store(v, std::memory_order_relaxed);
   }
   return v;

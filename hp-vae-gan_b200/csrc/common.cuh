@@ -62,8 +62,9 @@ static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b;
 // attribute becomes a programmatic edge of the CUDA graph.
 bool pdl_enabled();
 int set_pdl(int on);
-// which tcgen05 kernel runs the 3-D 64-channel layers: 0 = brick kernel (conv_tc.cu) always (default), -1 = by size,
-// 1 = column-streaming kernel (conv_col.cu) whenever it supports the layer.  Environment HPVG_TC_COL sets the initial value.
+// which tcgen05 kernel runs the 3-D 64-channel layers: -1 = per layer, by how well the brick kernel's units fill the SMs
+// (default, rule in conv_tc.cu), 0 = brick kernel (conv_tc.cu) always, 1 = column-streaming kernel (conv_col.cu) whenever it
+// supports the layer.  Environment HPVG_TC_COL sets the initial value.
 int conv_col_mode();
 int set_conv_col_mode(int mode);
 

@@ -644,17 +644,25 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
             float* stats, const void* mask_src, cudaStream_t st) {
   const bool thin = y_fmt == HPVG_FMT_NCDHW_F32;
   {
-    // column-streaming kernel (conv_col.cu) for volumes with few brick units per SM; HPVG_TC_COL = 0 never, 1 always (when
-    // supported), otherwise when the brick kernel would have at most HPVG_TC_COL_UNITS units per SM (default 2)
+    // Column-streaming kernel (conv_col.cu) or brick kernel?  The brick kernel is faster per unit of work (N = 192 MMAs) but
+    // deals work out in 4-slice x 128-voxel units, one round of at most num_sms() units at a time: a volume with 6 d-slices
+    // wastes half of every second unit, 54 x 54 wastes a fifth of its bricks, and 448 units on 148 SMs take four rounds.  The
+    // column kernel deals out single 128-voxel x 32-channel tiles in contiguous runs.  Measured (batch-8 generation, us per
+    // launch brick / column): 4x32x32 23.0 / 15.9, 4x39x39 23.7 / 21.4, 6x46x46 65.4 / 29.3, 6x54x54 85.3 / 41.0, 16x64x64
+    // 110.2 / 113.4; batch 1 at 16x64x64 22.6 / 24.6.  Rule (mode -1, the default): brick when the voxels it really computes
+    // fill at least HPVG_TC_COL_EFF (default 0.8) of the unit slots of its rounds.
     const int col_mode = conv_col_mode();
-    static const int col_units = getenv("HPVG_TC_COL_UNITS") ? atoi(getenv("HPVG_TC_COL_UNITS")) : 2;
-    if (col_mode != 0 && conv_col_supported(HPVG_FMT_NDHWC_BF16, y_fmt, g, w_packed) &&
-        (col_mode == 1 || conv_col_brick_units(g) <= (long long)col_units * num_sms()))
-      return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
-  }
-  if (thin && (act != HPVG_ACT_NONE || stats || mask_src)) {
-    set_error("conv_tc: the thin-output kernel supports bias only (no activation, statistics or mask)");
-    return -1;
+    static const double col_eff = getenv("HPVG_TC_COL_EFF") ? atof(getenv("HPVG_TC_COL_EFF")) : 0.8;
+    if (col_mode != 0 && conv_col_supported(HPVG_FMT_NDHWC_BF16, y_fmt, g, w_packed)) {
+      bool use_col = col_mode == 1;
+      if (!use_col) {
+        const long long units = conv_col_brick_units(g) / (g.Cout / 64);     // per 64-channel block
+        const long long rounds = cdiv(units * (g.Cout / 64), num_sms());
+        const double eff = (double)g.N * g.Do * g.Ho * g.Wo * (g.Cout / 64) / ((double)rounds * num_sms() * 512.0);
+        use_col = eff < col_eff;
+      }
+      if (use_col) return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
+    }
   }
   const int nout = thin ? 16 : 64;
   CUtensorMap mx, mw, my;

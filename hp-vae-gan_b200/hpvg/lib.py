@@ -135,8 +135,8 @@ PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 
 
 
 def set_conv_col_mode(mode):
-    """0 = brick tcgen05 kernel always (default), 1 = column-streaming kernel whenever supported, -1 = by volume;
-    returns the previous mode"""
+    """-1 = brick or column-streaming tcgen05 kernel per layer (default), 0 = brick kernel always, 1 = column kernel whenever
+    supported; returns the previous mode"""
     return int(load().hpvg_set_conv_col_mode(int(mode)))
 
 

@@ -60,10 +60,10 @@ int hpvg_profile_enable(int on);
  * global memory, so consecutive launches of a stream overlap launch latency and set-up with the predecessor's tail.
  * Returns the previous setting. */
 int hpvg_set_pdl(int on);
-/* Which tcgen05 kernel runs the 3-D 64-input-channel wide layers: 0 = brick kernel conv_tc.cu always (default: measured
- * faster at every BASELINE volume), 1 = column-streaming kernel conv_col.cu whenever it supports the layer, -1 = column
- * kernel when the brick kernel would have at most two units per SM.  Initial value from HPVG_TC_COL.  Returns the previous
- * mode. */
+/* Which tcgen05 kernel runs the 3-D 64-input-channel wide layers: -1 = chosen per layer (default): the brick kernel
+ * conv_tc.cu when its 4-slice x 128-voxel units fill at least 80 % of the unit slots of its rounds over the SMs, else the
+ * column-streaming kernel conv_col.cu (single-tile work units, no quantisation loss); 0 = brick kernel always; 1 = column
+ * kernel whenever it supports the layer.  Initial value from HPVG_TC_COL.  Returns the previous mode. */
 int hpvg_set_conv_col_mode(int mode);
 int hpvg_profile_dump(double* rows, int max_rows);
 
