@@ -207,30 +207,53 @@ __global__ void __launch_bounds__(256, 2) expand_conv_mma_kernel(const float* __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
 
   // filter: [K][64] fp32 image (hpvg_pack_weights_expand), 128-bit copies into rows of EM_BSTRIDE words; rows >= K are zero
-  for (int i = tid; i < EM_KMAX * 16; i += 256) {
-    const int k = i >> 4, c4 = i & 15;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (k < K) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(w_tco) + i);
-      v = make_uint4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
-    }
-    *reinterpret_cast<uint4*>(bs + k * EM_BSTRIDE + c4 * 4) = v;
+  // Every global load of the prologue is issued before the first one is consumed (fully unrolled register staging): the
+  // block is otherwise a chain of dependent DRAM / L2 round trips (ncu: 41 % of the warp stalls were long-scoreboard waits).
+  constexpr int F_ITERS = (EM_KMAX * 16 + 255) / 256;                  // filter: 6 x 128-bit loads per thread
+  constexpr int H_ITERS = (3 * KDT * EX_HH + 7) / 8;                   // halo rows per warp (Cin <= 3)
+  const size_t in_sp = (size_t)g.Di * g.Hi * g.Wi;
+  float4 fv[F_ITERS];
+#pragma unroll
+  for (int it = 0; it < F_ITERS; ++it) {
+    const int i = tid + it * 256;
+    fv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < EM_KMAX * 16 && (i >> 4) < K) fv[it] = __ldg(reinterpret_cast<const float4*>(w_tco) + i);
   }
   // halo tile: one warp per (ci, kd, row), lanes along w (no per-element index arithmetic)
-  const size_t in_sp = (size_t)g.Di * g.Hi * g.Wi;
-  for (int r = warp; r < g.Cin * KDT * EX_HH; r += 8) {
-    const int hh = r % EX_HH, kd = (r / EX_HH) % KDT, ci = r / (EX_HH * KDT);
-    const int id = od + kd - g.pad_d, ih = h0 + hh - g.pad;
-    const bool row_ok = id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi;
-    const float* src = x + ((size_t)n * g.Cin + ci) * in_sp + ((size_t)(row_ok ? id : 0) * g.Hi + (row_ok ? ih : 0)) * g.Wi;
+  float hv[H_ITERS][2];
+  const int hrows = g.Cin * KDT * EX_HH;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int ww = lane + 32 * half;
-      if (ww < EM_HW) {
+  for (int it = 0; it < H_ITERS; ++it) {
+    const int r = warp + 8 * it;
+    hv[it][0] = hv[it][1] = 0.f;
+    if (r < hrows) {
+      const int hh = r % EX_HH, kd = (r / EX_HH) % KDT, ci = r / (EX_HH * KDT);
+      const int id = od + kd - g.pad_d, ih = h0 + hh - g.pad;
+      const bool row_ok = id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi;
+      const float* src = x + ((size_t)n * g.Cin + ci) * in_sp + ((size_t)(row_ok ? id : 0) * g.Hi + (row_ok ? ih : 0)) * g.Wi;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ww = lane + 32 * half;
         const int iw = w0 + ww - g.pad;
-        const float v = (row_ok && iw >= 0 && iw < g.Wi) ? __ldg(src + iw) : 0.f;
-        xs[r * EM_HW + ww] = to_tf32(v);
+        if (ww < EM_HW && row_ok && iw >= 0 && iw < g.Wi) hv[it][half] = __ldg(src + iw);
       }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < F_ITERS; ++it) {
+    const int i = tid + it * 256;
+    if (i < EM_KMAX * 16) {
+      const int k = i >> 4, c4 = i & 15;
+      *reinterpret_cast<uint4*>(bs + k * EM_BSTRIDE + c4 * 4) =
+          make_uint4(to_tf32(fv[it].x), to_tf32(fv[it].y), to_tf32(fv[it].z), to_tf32(fv[it].w));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < H_ITERS; ++it) {
+    const int r = warp + 8 * it;
+    if (r < hrows) {
+      xs[r * EM_HW + lane] = to_tf32(hv[it][0]);
+      if (lane + 32 < EM_HW) xs[r * EM_HW + lane + 32] = to_tf32(hv[it][1]);
     }
   }
   if (tid < EM_KMAX) {
@@ -599,7 +622,8 @@ __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const Out
 
   const uint32_t s_wt = smem_u32(osm);
   // ldmatrix row address of this lane: voxel (lane & 7) + 8 * ((lane >> 3) & 1) of the k16 step, channels of n-tile (lane >> 4)
-  const uint32_t ld_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 128 + (lane >> 4) * 16);
+  const uint32_t ld_row = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 128);
+  const uint32_t ld_swz = (uint32_t)(lane & 7), ld_hi = (uint32_t)(lane >> 4);   // swizzle phase = voxel & 7 = lane & 7 at every k-step
   const size_t thin_sp = (size_t)p.Dt * p.Ht * p.Wt;
   for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     long long b = tile;
@@ -610,28 +634,54 @@ __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const Out
     const int d0 = (int)(b % p.Dw);
     const int n = (int)(b / p.Dw);
     __syncthreads();
-    for (int i = tid; i < OC_TH * OC_TW * 8; i += OM_THREADS) {
+    // all global loads of the tile are issued before the first shared-memory store (fully unrolled register staging): the
+    // tile used to be a chain of ~25 dependent global round trips per warp (ncu: 25 us per launch at 9.6 % issue activity)
+    constexpr int W_ITERS = (OC_TH * OC_TW * 8 + OM_THREADS - 1) / OM_THREADS;     // 11 x 128-bit loads per thread
+    constexpr int T_ITERS = (3 * KDT * OC_HH + OM_WARPS - 1) / OM_WARPS;           // thin halo rows per warp (J <= 3)
+    uint4 wv[W_ITERS];
+#pragma unroll
+    for (int it = 0; it < W_ITERS; ++it) {
+      const int i = tid + it * OM_THREADS;
       const int chunk = i & 7, vox = i >> 3;
       const int hh = vox / OC_TW, ww = vox % OC_TW;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (h0 + hh < p.Hw && w0 + ww < p.Ww)
-        v = __ldg(reinterpret_cast<const uint4*>(p.wide + ((((size_t)n * p.Dw + d0) * p.Hw + h0 + hh) * p.Ww + w0 + ww) * 64) + chunk);
-      reinterpret_cast<uint4*>(osm)[i] = v;
+      wv[it] = make_uint4(0, 0, 0, 0);
+      if (i < OC_TH * OC_TW * 8 && h0 + hh < p.Hw && w0 + ww < p.Ww)
+        wv[it] = __ldg(reinterpret_cast<const uint4*>(p.wide + ((((size_t)n * p.Dw + d0) * p.Hw + h0 + hh) * p.Ww + w0 + ww) * 64) + chunk);
     }
     const int od = d0 + p.shift_d - (KDT == 3 ? (p.sign > 0 ? 0 : 2) : 0);
     const int oh = h0 + p.shift - (p.sign > 0 ? 0 : 2), ow = w0 + p.shift - (p.sign > 0 ? 0 : 2);
-    for (int r = warp; r < p.J * KDT * OC_HH; r += OM_WARPS) {
-      const int hh = r % OC_HH, dd = (r / OC_HH) % KDT, j = r / (OC_HH * KDT);
-      const int id = od + dd, ih = oh + hh;
-      const bool row_ok = id >= 0 && id < p.Dt && ih >= 0 && ih < p.Ht;
-      const float* src = p.thin + ((size_t)n * p.J + j) * thin_sp + ((size_t)(row_ok ? id : 0) * p.Ht + (row_ok ? ih : 0)) * p.Wt;
+    const int trows = p.J * KDT * OC_HH;
+    float tv[T_ITERS][2];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int ww = lane + 32 * half;
-        if (ww < OC_HW) {
+    for (int it = 0; it < T_ITERS; ++it) {
+      const int r = warp + OM_WARPS * it;
+      tv[it][0] = tv[it][1] = 0.f;
+      if (r < trows) {
+        const int hh = r % OC_HH, dd = (r / OC_HH) % KDT, j = r / (OC_HH * KDT);
+        const int id = od + dd, ih = oh + hh;
+        const bool row_ok = id >= 0 && id < p.Dt && ih >= 0 && ih < p.Ht;
+        const float* src = p.thin + ((size_t)n * p.J + j) * thin_sp + ((size_t)(row_ok ? id : 0) * p.Ht + (row_ok ? ih : 0)) * p.Wt;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int ww = lane + 32 * half;
           const int iw = ow + ww;
-          th[r * OC_HW + ww] = (row_ok && iw >= 0 && iw < p.Wt) ? __ldg(src + iw) : 0.f;
+          if (ww < OC_HW && row_ok && iw >= 0 && iw < p.Wt) tv[it][half] = __ldg(src + iw);
         }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < W_ITERS; ++it) {
+      const int i = tid + it * OM_THREADS;
+      // 16-byte chunk index XOR (voxel & 7): the eight rows of an ldmatrix 8x8 tile (same chunk, consecutive voxels, 128 bytes
+      // apart) then fall into eight different bank groups instead of one (ncu counted 2.8 M shared-memory bank conflicts per launch)
+      if (i < OC_TH * OC_TW * 8) reinterpret_cast<uint4*>(osm)[(i & ~7) | ((i & 7) ^ ((i >> 3) & 7))] = wv[it];
+    }
+#pragma unroll
+    for (int it = 0; it < T_ITERS; ++it) {
+      const int r = warp + OM_WARPS * it;
+      if (r < trows) {
+        th[r * OC_HW + lane] = tv[it][0];
+        if (lane + 32 < OC_HW) th[r * OC_HW + lane + 32] = tv[it][1];
       }
     }
     __syncthreads();
@@ -648,11 +698,11 @@ __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const Out
         a[2] = pack_bf16x2(r0[8], r0[9]);
         a[3] = pack_bf16x2(r1[8], r1[9]);
       }
-      const uint32_t wrow = s_wt + (uint32_t)(ks * 16) * 128u + ld_lane;
+      const uint32_t wrow = s_wt + (uint32_t)(ks * 16) * 128u + ld_row;
 #pragma unroll
       for (int np = 0; np < 4; ++np) {                              // n-tile pairs (2 np, 2 np + 1)
         uint32_t bfrag[4];
-        ldmatrix_x4_trans(bfrag, wrow + np * 32);
+        ldmatrix_x4_trans(bfrag, wrow + (((uint32_t)(2 * np) + ld_hi) ^ ld_swz) * 16u);
         mma_bf16(acc[2 * np], a, bfrag[0], bfrag[1]);
         mma_bf16(acc[2 * np + 1], a, bfrag[2], bfrag[3]);
       }
