@@ -248,7 +248,11 @@ def run_hpvg(args):
         # the whole iteration (every libhpvg kernel, autograd glue, clipping, both Adam steps, the all-reduces) is
         # recorded once into a CUDA graph after W eager warm-up iterations and replayed per step
         c0 = lib.launch_count()
+        torch.cuda.synchronize()
+        reserved0 = torch.cuda.memory_reserved()
         trainer.capture(real, real_zero, warmup=W)
+        torch.cuda.synchronize()
+        last["pool_mb"] = (torch.cuda.memory_reserved() - reserved0) / 2**20
         launches_per_iter = (lib.launch_count() - c0) // (W + 1)
 
         def step_resident():
@@ -302,6 +306,9 @@ def run_hpvg(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     peak_mb = torch.cuda.max_memory_allocated() / 2**20
+    # working set of one iteration: the memory pool of the recorded graph (every activation saved for the backward passes,
+    # every gradient) when graphed, else the allocator's peak during the timed steps
+    work_mb = last.get("pool_mb") or peak_mb
 
     # roofline leg: the same steps again with CUDA events around every convolution launch (on the launching stream)
     prof_steps = min(args.steps, 3)
@@ -368,7 +375,11 @@ def run_hpvg(args):
             per_launch_ms = top["ms"] / top["launches"]
             achieved = top["work"] / (per_launch_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, 64->64 @ 16x64x64)",
-                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one 64->64 launch at 16x64x64 from the committed ncu --set full
+                        # capture (profiles/r01e_conv_tc_ncu.txt): 8.71 MB read (algorithmic 8.39 MB input + 0.22 MB weights), 0 written
+                        # before the kernel ends (the 8.39 MB output is still in L2); None for other workloads
+                        "traffic": 8711168 if WORKLOAD["name"] == "cfg2" else None, "traffic_unit": "bytes per launch",
                         "flops_per_launch": top["work"], "us_per_launch": per_launch_ms * 1e3, "launches_timed": top["launches"],
                         "peak_source": peak_src,
                         "share_of_step": (top["ms"] / prof_steps) / (ms / args.steps),
@@ -385,7 +396,8 @@ def run_hpvg(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat NCCL grad all-reduce)" % world if distributed else "single GPU",
-                           "l2": "no explicit flush: one iteration touches %.0f MB of activations (peak allocated), above the 126 MB L2" % peak_mb,
+                           "l2": "no explicit flush: one iteration writes and re-reads a %.0f MB working set (activations saved for the "
+                                 "backward passes, gradients), %s the 126 MB L2" % (work_mb, "above" if work_mb > 126 else "NOT above"),
                            "conv_gflop_per_iter": CONV_GFLOP_PER_ITER if WORKLOAD["name"] == "cfg2" else 12650.99,
                            "launch": ("one CUDA graph replay per iteration (%d libhpvg kernels recorded)" % launches_per_iter) if use_graph
                            else "eager launches"},

@@ -78,6 +78,54 @@ def _empty(n, c, d, h, w, wide, device):
     return torch.empty((n, c, d, h, w), dtype=torch.float32, device=device)
 
 
+class _Arena:
+    """bump allocator over ONE zero-filled float32 buffer: the small accumulators that kernels add into with atomics
+    (BatchNorm sums, fused bias-gradient sums) are carved from it, so an iteration pays one fill launch instead of ~80"""
+
+    def __init__(self, device, capacity):
+        self.buf = torch.zeros((int(capacity),), dtype=torch.float32, device=device)
+        self.used = 0
+        self.lock = threading.Lock()
+
+    def take(self, n):
+        n_al = (int(n) + 31) & ~31          # 128-byte granules: no two accumulators share a cache line
+        with self.lock:
+            if self.used + n_al > self.buf.numel():
+                return None
+            t = self.buf[self.used:self.used + n]
+            self.used += n_al
+        return t
+
+
+_ARENA = [None]
+
+
+class zero_arena:
+    """`with zero_arena(device, capacity_floats):` — zeros_small() inside the block hands out slices of one pre-zeroed buffer.
+    The buffer is created on the current stream when the block is entered: enter it BEFORE forking side streams."""
+
+    def __init__(self, device, capacity=16384):
+        self.device, self.capacity = device, capacity
+
+    def __enter__(self):
+        self.prev = _ARENA[0]
+        _ARENA[0] = _Arena(self.device, self.capacity)
+        return self
+
+    def __exit__(self, *a):
+        _ARENA[0] = self.prev
+
+
+def zeros_small(n, device):
+    """a zero-filled float32 vector of n elements for kernels that accumulate with atomics"""
+    a = _ARENA[0]
+    if a is not None and a.buf.device == torch.device(device):
+        t = a.take(n)
+        if t is not None:
+            return t
+    return torch.zeros((int(n),), dtype=torch.float32, device=device)
+
+
 def _kd_of(weight):
     return 3 if weight.dim() == 5 else 1
 
@@ -307,7 +355,7 @@ class ConvFwd(Function):
             if _FUSE_MASK[0] and plain and in_link is not None and is_wide(x) and is_wide(gz):
                 stats = None
                 if in_link.want_gb and not _input_only():
-                    stats = torch.zeros((2 * x.shape[-1],), dtype=torch.float32, device=x.device)
+                    stats = zeros_small(2 * x.shape[-1], x.device)
                 gx = conv_raw(gz, w, None, 2 - ctx.pad, True, True, stats=stats, mask_src=x, mask_slope=in_link.slope)
                 in_link.premasked = True
                 in_link.gb = stats[:x.shape[-1]] if stats is not None else None
@@ -543,7 +591,7 @@ class ConvBnLrelu(Function):
         _require_cuda(x, w, gamma, beta)
         ctx.token = token
         cout = w.shape[0]
-        stats = torch.zeros((2 * cout,), dtype=torch.float32, device=x.device)
+        stats = zeros_small(2 * cout, x.device)
         y = conv_raw(x, w, bias, pad, False, True, stats=stats)
         n, c, d, h, wd = dims_of(y)
         nvox = n * d * h * wd
@@ -623,7 +671,7 @@ def _conv_bn_lrelu_per_sample(x, w, bias, gamma, beta, pad, eps, slope):
                      d * h * wd, c, float(slope), _stream())
             outs.append(o)
         return torch.cat(outs, 0)
-    stats = torch.zeros((n, 2 * cout), dtype=torch.float32, device=x.device)
+    stats = zeros_small(n * 2 * cout, x.device).view(n, 2 * cout)
     y = conv_raw(x, w, bias, pad, False, True, stats=stats, stats_per_sample=True)
     _, c, d, h, wd = dims_of(y)
     out = torch.empty_like(y)

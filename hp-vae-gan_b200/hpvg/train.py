@@ -13,6 +13,8 @@ takes the same Adam step.  BatchNorm statistics stay per rank, as under the refe
 """
 import os
 
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
@@ -157,10 +159,13 @@ class ScaleTrainer:
         side = None
         if self.overlap and real.is_cuda and self._wside is None:
             self._wside = torch.cuda.Stream(device=real.device)
-        if self._wside is not None:
-            self._wside.wait_stream(torch.cuda.current_stream())     # fork (also makes it part of a graph capture)
-        with ops.wgrad_stream(self._wside):
-            out = self._iteration_body(real, real_zero, noise_init, out)
+        # one zero fill for every atomically-accumulated statistic of the iteration (created before the streams fork)
+        arena = ops.zero_arena(real.device, 32768) if real.is_cuda else contextlib.nullcontext()
+        with arena:
+            if self._wside is not None:
+                self._wside.wait_stream(torch.cuda.current_stream())     # fork (also makes it part of a graph capture)
+            with ops.wgrad_stream(self._wside):
+                out = self._iteration_body(real, real_zero, noise_init, out)
         if self._wside is not None:
             torch.cuda.current_stream().wait_stream(self._wside)     # join (the engine already did after each backward)
         return out
@@ -326,7 +331,8 @@ class Sampler:
             torch.cuda.synchronize()
 
     def _draw(self):
-        with ops.bn_running_stats(self.track_bn), ops.bn_per_sample(self.per_sample_bn):
+        # BatchNorm sums of the forward: ~35 layers x batch x 128 floats (x 32-float granules), zeroed by one fill
+        with ops.bn_running_stats(self.track_bn), ops.bn_per_sample(self.per_sample_bn), ops.zero_arena(self.device, 48 * 160 * max(1, self.batch)):
             z = images.generate_noise(size=self.size, device=self.device)
             fake, _ = self.netG(z, self.opt.Noise_Amps, noise_init=z, mode="rand")
         return fake
