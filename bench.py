@@ -170,7 +170,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": workload_name(o)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def fresh_states(o):
@@ -285,7 +285,7 @@ def run_hpvg(args):
         ps.sample()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-        print(json.dumps({"profiled": "one generation forward", "batch": args.gen_batch, "graph": use_graph}), flush=True)
+        _emit({"profiled": "one generation forward", "batch": args.gen_batch, "graph": use_graph})
         return
     if args.profile_one:
         # for `ncu --profile-from-start off`: exactly one replayed (or eager) iteration between cudaProfilerStart/Stop
@@ -294,7 +294,7 @@ def run_hpvg(args):
         step_resident()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-        print(json.dumps({"profiled": "one iteration", "graph": use_graph}), flush=True)
+        _emit({"profiled": "one iteration", "graph": use_graph})
         return
     torch.cuda.reset_peak_memory_stats()
     sampler = ClockSampler(local)
@@ -416,7 +416,7 @@ def run_hpvg(args):
             sec, done, cores = cpu_iteration_timer(o, sg, sd, budget_s=30.0, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d full iteration(s) of the same workload after 1 warm-up (oracle/train_ref.py, PyTorch-CPU fp32)" % done}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if distributed:
         # all ranks are done once rank 0 has printed; leave without tearing NCCL down: destroy_process_group() was seen
         # to hang while CUDA graphs holding captured all-reduces are alive
@@ -425,6 +425,19 @@ def run_hpvg(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+_REAL_STDOUT = [None]
+
+
+def _emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    fd = _REAL_STDOUT[0]
+    if fd is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(fd, data)
 
 
 def main():
@@ -444,6 +457,11 @@ def main():
                     help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128)")
     args = ap.parse_args()
     WORKLOAD["name"] = args.workload
+    # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version
+    # there when NCCL_DEBUG is VERSION or WARN) are sent to stderr, and only _emit() writes to the real stdout
+    sys.stdout.flush()
+    _REAL_STDOUT[0] = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
