@@ -282,6 +282,63 @@ def draws_for_rank(total, world, rank):
     return start, count
 
 
+class BaselineTrainer:
+    """One pyramid scale of train_video_baselines.py (:44-70 optimizers, :100-173 iteration) on the drop-in modules:
+    GeneratorSG / GeneratorCSG against WDiscriminator3D (the script's defaults), Dsteps = Gsteps = 1.  Eager launches."""
+
+    DEFAULTS = dict(lr_g=5e-4, lr_d=5e-4, beta1=0.5, lambda_grad=0.1, alpha=10.0, disc_loss_weight=1.0, lr_scale=0.2,
+                    train_depth=1, noise_amp_init=0.1, batch_size=1, Gsteps=1, Dsteps=1)
+
+    def __init__(self, opt, netG, netD):
+        for k, v in self.DEFAULTS.items():
+            if not hasattr(opt, k):
+                setattr(opt, k, v)
+        self.opt, self.netG, self.netD = opt, netG, netD
+        for block in netG.body[:-opt.train_depth]:
+            for p in block.parameters():
+                p.requires_grad = False
+        trained = netG.body[-opt.train_depth:]
+        groups = [{"params": b.parameters(), "lr": opt.lr_g * (opt.lr_scale ** (len(trained) - 1 - i))} for i, b in enumerate(trained)]
+        if hasattr(netG, 'head') and opt.scale_idx - opt.train_depth < 0:
+            groups.append({"params": netG.head.parameters(), "lr": opt.lr_g * (opt.lr_scale ** opt.scale_idx)})
+        if hasattr(netG, 'tail'):
+            groups.append({"params": netG.tail.parameters(), "lr": opt.lr_g})
+        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999))
+        self.optimizerG = torch.optim.Adam(groups, lr=opt.lr_g, betas=(opt.beta1, 0.999))
+        self.iterations = 0
+
+    def iteration(self, real, z_init):
+        from modules.utils import calc_gradient_penalty
+        opt, G, D = self.opt, self.netG, self.netD
+        noise_init = images.generate_noise(ref=z_init)
+        if self.iterations == 0:
+            if opt.scale_idx == 0:
+                opt.noise_amp = 1
+                opt.Noise_Amps.append(opt.noise_amp)
+            else:
+                opt.Noise_Amps.append(0)
+                z_rec = G(z_init, opt.Noise_Amps, mode="rec")
+                opt.noise_amp = opt.noise_amp_init * torch.sqrt(F.mse_loss(real, z_rec)).item() / opt.batch_size
+                opt.Noise_Amps[-1] = opt.noise_amp
+        with ops.zero_arena(real.device, 32768) if real.is_cuda else contextlib.nullcontext():
+            D.zero_grad()
+            errD_real = -D(real).mean()
+            fake = G(noise_init, opt.Noise_Amps, mode="rand")
+            errD_fake = D(fake.detach()).mean()
+            gradient_penalty = calc_gradient_penalty(D, real, fake, opt.lambda_grad, real.device)
+            (errD_real + errD_fake + gradient_penalty).backward()
+            self.optimizerD.step()
+            errG = -D(fake).mean() * opt.disc_loss_weight
+            generated = G(z_init, opt.Noise_Amps, mode="rec")
+            rec_loss = opt.alpha * F.mse_loss(generated, real)
+            G.zero_grad()
+            (errG + rec_loss).backward()
+            self.optimizerG.step()
+        self.iterations += 1
+        return dict(rec_loss=rec_loss.detach(), errG=errG.detach(), errD_real=errD_real.detach(), errD_fake=errD_fake.detach(),
+                    gradient_penalty=gradient_penalty.detach())
+
+
 class Sampler:
     """Diverse-sample generation (train_video.py:226-235) with the forward of one draw recorded into a CUDA graph: z is
     drawn by torch's generator inside the graph (graph-safe Philox offsets), so every replay is a fresh sample.

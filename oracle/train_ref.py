@@ -122,6 +122,79 @@ class ScaleTrainer(object):
         return out
 
 
+BASELINE_DEFAULTS = dict(lr_g=5e-4, lr_d=5e-4, beta1=0.5, lambda_grad=0.1, alpha=10.0, disc_loss_weight=1.0, lr_scale=0.2,
+                         train_depth=1, noise_amp_init=0.1, batch_size=1, Gsteps=1, Dsteps=1)
+
+
+def _num_stages(sd_g):
+    k = 0
+    while any(key.startswith('body.%d.' % k) for key in sd_g):
+        k += 1
+    return k
+
+
+def baseline_param_groups(opt, sd_g):
+    """train_video_baselines.py:53-70: the last train_depth stages, the head while scale_idx < train_depth, the tail always
+    (GeneratorSG has neither head nor tail attributes: its stages carry their own)"""
+    n = _num_stages(sd_g)
+    idxs = list(range(n))[-opt.train_depth:]
+    groups = [{"params": params_of(sd_g, 'body.%d.' % b), "lr": opt.lr_g * (opt.lr_scale ** (len(idxs) - 1 - i))} for i, b in enumerate(idxs)]
+    if any(k.startswith('head.') for k in sd_g) and opt.scale_idx - opt.train_depth < 0:
+        groups.append({"params": params_of(sd_g, 'head.'), "lr": opt.lr_g * (opt.lr_scale ** opt.scale_idx)})
+    if any(k.startswith('tail.') for k in sd_g):
+        groups.append({"params": params_of(sd_g, 'tail.'), "lr": opt.lr_g})
+    return groups
+
+
+class BaselineTrainer(object):
+    """One pyramid scale of train_video_baselines.py (:44-70 optimizers, :100-173 iteration) for GeneratorSG / GeneratorCSG
+    with the WDiscriminator3D critic (the script's default), Dsteps = Gsteps = 1."""
+
+    def __init__(self, opt, sd_g, sd_d, generator='GeneratorSG'):
+        for k, v in BASELINE_DEFAULTS.items():
+            if not hasattr(opt, k):
+                setattr(opt, k, v)
+        self.opt, self.sd_g, self.sd_d = opt, make_leaf(sd_g), make_leaf(sd_d)
+        self.gen = port.generator_sg if generator == 'GeneratorSG' else port.generator_csg
+        n = _num_stages(sd_g)
+        for b in range(n - opt.train_depth):                         # :55-57
+            for p in params_of(sd_g, 'body.%d.' % b):
+                p.requires_grad_(False)
+        self.optimizerD = torch.optim.Adam(params_of(sd_d), lr=opt.lr_d, betas=(opt.beta1, 0.999))
+        self.optimizerG = torch.optim.Adam(baseline_param_groups(opt, sd_g), lr=opt.lr_g, betas=(opt.beta1, 0.999))
+        self.iterations = 0
+
+    def iteration(self, real, z_init, noise_init=None, noises=None, alpha=None):
+        opt, sd_g, sd_d = self.opt, self.sd_g, self.sd_d
+        if noise_init is None:
+            noise_init = torch.zeros_like(z_init).normal_(0, 1)                              # :107
+        if self.iterations == 0:                                                             # :112-122
+            if opt.scale_idx == 0:
+                opt.noise_amp = 1
+                opt.Noise_Amps.append(opt.noise_amp)
+            else:
+                opt.Noise_Amps.append(0)
+                z_rec = self.gen(sd_g, opt, z_init, opt.Noise_Amps, mode='rec')
+                opt.noise_amp = opt.noise_amp_init * torch.sqrt(F.mse_loss(real, z_rec)).item() / opt.batch_size
+                opt.Noise_Amps[-1] = opt.noise_amp
+        ScaleTrainer._zero(sd_d)                                                             # :131
+        errD_real = -port.discriminator(sd_d, opt, real).mean()
+        fake = self.gen(sd_g, opt, noise_init, opt.Noise_Amps, mode='rand', noises=noises)
+        errD_fake = port.discriminator(sd_d, opt, fake.detach()).mean()
+        gradient_penalty = port.gradient_penalty(sd_d, opt, real, fake, opt.lambda_grad, alpha=alpha)
+        (errD_real + errD_fake + gradient_penalty).backward()
+        self.optimizerD.step()
+        errG = -port.discriminator(sd_d, opt, fake).mean() * opt.disc_loss_weight           # :158-160
+        generated = self.gen(sd_g, opt, z_init, opt.Noise_Amps, mode='rec')
+        rec_loss = opt.alpha * F.mse_loss(generated, real)
+        ScaleTrainer._zero(sd_g)
+        (errG + rec_loss).backward()
+        self.optimizerG.step()
+        self.iterations += 1
+        return dict(rec_loss=rec_loss.detach(), errG=errG.detach(), errD_real=errD_real.detach(), errD_fake=errD_fake.detach(),
+                    gradient_penalty=gradient_penalty.detach())
+
+
 @torch.no_grad()
 def generate(sd_g, opt, n_samples, batch=1):
     """train_video.py:226-235: fresh z per draw, G(z, amps, noise_init=z, mode='rand')"""

@@ -3,6 +3,7 @@
     python tests/golden/make_golden.py            # needs /root/reference, writes tests/golden/*.pt
     python tests/golden/make_golden.py train      # the training-loop fixtures
     python tests/golden/make_golden.py baselines  # GeneratorCSG / WDiscriminatorBaselines fixtures
+    python tests/golden/make_golden.py train_baselines   # train_video_baselines.py loop fixtures (BASELINE configs[2])
 
 Each fixture holds deterministic closed-form weights' *recipe* (oracle.port.det_fill seed), the inputs, and what the
 reference's own modules (modules/networks_3d.py, networks_2d.py, losses.py, utils.py) computed from them on CPU in
@@ -365,7 +366,102 @@ def train_case(name, opt, scale_idx, iters, seed=0):
     print(name, 'losses[0]', losses[0], 'losses[-1]', losses[-1], 'amps', opt.Noise_Amps)
 
 
+def train_baselines_case(name, gen_name, opt, scale_idx, iters, seed=0):
+    """K iterations of train_video_baselines.py:100-173 (restated here only as the DRIVER: every network and penalty call goes
+    to the reference's own modules) at pyramid level `scale_idx`, default critic WDiscriminator3D, Dsteps = Gsteps = 1."""
+    import torch.optim as optim
+    import utils as ref_utils
+    from oracle import train_ref
+    for k, v in train_ref.BASELINE_DEFAULTS.items():
+        setattr(opt, k, v)
+    opt.scale_idx = scale_idx
+    opt.device = 'cpu'
+    g = getattr(networks_3d, gen_name)(opt)
+    for _ in range(scale_idx):
+        g.init_next_stage()
+    port.det_fill(g.state_dict(), seed=6)
+    d = networks_3d.WDiscriminator3D(opt)
+    port.det_fill(d.state_dict(), seed=8)
+    s0, t0 = port.scale_size(0, opt), port.time_depth(0, opt)
+    sN, tN = port.scale_size(scale_idx, opt), port.time_depth(scale_idx, opt)
+    z_init = port.det_tensor((1, 3, t0, s0, s0), 53)
+    real = port.det_tensor((1, 3, tN, sN, sN), 54)
+    opt.Noise_Amps = [1.0] + [0.1] * (scale_idx - 1) if scale_idx > 0 else []
+    fx = {'opt': {k: v for k, v in opt.__dict__.items() if k != 'Noise_Amps'}, 'generator': gen_name, 'stages': scale_idx,
+          'fill_seed': 6, 'fill_seed_d': 8, 'real': real, 'z_init': z_init, 'amps_before': list(opt.Noise_Amps), 'iters': iters,
+          'state': [(k, tuple(v.shape)) for k, v in g.state_dict().items()],
+          'state_d': [(k, tuple(v.shape)) for k, v in d.state_dict().items()]}
+    optimizerD = optim.Adam(d.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999))
+    for block in g.body[:-opt.train_depth]:
+        for param in block.parameters():
+            param.requires_grad = False
+    parameter_list = [{"params": block.parameters(), "lr": opt.lr_g * (opt.lr_scale ** (len(g.body[-opt.train_depth:]) - 1 - idx))}
+                      for idx, block in enumerate(g.body[-opt.train_depth:])]
+    if hasattr(g, 'head'):
+        if opt.scale_idx - opt.train_depth < 0:
+            parameter_list += [{"params": g.head.parameters(), "lr": opt.lr_g * (opt.lr_scale ** opt.scale_idx)}]
+    if hasattr(g, 'tail'):
+        parameter_list += [{"params": g.tail.parameters(), "lr": opt.lr_g}]
+    optimizerG = optim.Adam(parameter_list, lr=opt.lr_g, betas=(opt.beta1, 0.999))
+    # shapes of the per-stage noise of a 'rand' pass
+    margin = opt.num_layer + 2 if gen_name == 'GeneratorSG' else opt.num_layer
+    chans = 3 if gen_name == 'GeneratorSG' else opt.nfc
+    noise_shapes = {}
+    x = torch.zeros(1, 3, t0, s0, s0)
+    for idx in range(1, scale_idx + 1):
+        x = ref_utils.upscale(x, idx, opt)
+        noise_shapes[idx] = (1, chans) + tuple(s + 2 * margin for s in x.shape[-3:])
+    gen = torch.Generator().manual_seed(2000 + seed)
+    draws, losses = [], []
+    mse = torch.nn.MSELoss()
+    for it in range(iters):
+        dr = {'noise_init': torch.randn(tuple(z_init.shape), generator=gen),
+              'noises': {lvl: torch.randn(shape, generator=gen) for lvl, shape in sorted(noise_shapes.items())},
+              'alpha': float(torch.rand(1, generator=gen))}
+        draws.append(dr)
+        with DrawQueue() as q:
+            q.normals = [dr['noise_init']] + [dr['noises'][lvl] for lvl in sorted(dr['noises'])]
+            q.rands = [dr['alpha']]
+            noise_init = ref_utils.generate_noise(ref=z_init)
+            if it == 0:
+                if scale_idx == 0:
+                    opt.noise_amp = 1
+                    opt.Noise_Amps.append(opt.noise_amp)
+                else:
+                    opt.Noise_Amps.append(0)
+                    z_reconstruction = g(z_init, opt.Noise_Amps, mode="rec")
+                    RMSE = torch.sqrt(F.mse_loss(real, z_reconstruction))
+                    opt.noise_amp = opt.noise_amp_init * RMSE.item() / opt.batch_size
+                    opt.Noise_Amps[-1] = opt.noise_amp
+            d.zero_grad()
+            errD_real = -d(real).mean()
+            fake = g(noise_init, opt.Noise_Amps, mode="rand")
+            errD_fake = d(fake.detach()).mean()
+            gradient_penalty = calc_gradient_penalty(d, real, fake, opt.lambda_grad, 'cpu')
+            (errD_real + errD_fake + gradient_penalty).backward()
+            optimizerD.step()
+            errG = -d(fake).mean() * opt.disc_loss_weight
+            generated = g(z_init, opt.Noise_Amps, mode="rec")
+            rec_loss = opt.alpha * mse(generated, real)
+            g.zero_grad()
+            (errG + rec_loss).backward()
+            optimizerG.step()
+        losses.append(dict(rec_loss=rec_loss.item(), errG=errG.item(), errD_real=errD_real.item(), errD_fake=errD_fake.item(),
+                           gradient_penalty=gradient_penalty.item()))
+    last_key = [k for k in g.state_dict() if k.startswith('body.%d.' % scale_idx) and k.endswith('conv.weight')][-1]
+    fx.update({'draws': draws, 'losses': losses, 'noise_amps_after': list(opt.Noise_Amps), 'final_key': last_key,
+               'final_weight': g.state_dict()[last_key].clone()})
+    torch.save(fx, os.path.join(HERE, name + '.pt'))
+    print(name, 'losses[0]', losses[0], 'losses[-1]', losses[-1], 'amps', opt.Noise_Amps)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'train_baselines':
+        train_baselines_case('train_sg_tiny', 'GeneratorSG', tiny_opt(num_layer=2), scale_idx=1, iters=8)
+        train_baselines_case('train_csg_tiny', 'GeneratorCSG', tiny_opt(num_layer=2), scale_idx=1, iters=8)
+        train_baselines_case('train_sg_wide', 'GeneratorSG', port.Opt(nfc=64, num_layer=3, img_size=20, min_size=12, sampling_rates=[4, 2, 1]),
+                             scale_idx=1, iters=4)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'baselines':
         csg_case('csg3d_tiny', tiny_opt(num_layer=2), stages=2, full_grads=True)
         csg_case('csg3d_wide', port.Opt(nfc=64, num_layer=3, img_size=20, min_size=12, sampling_rates=[4, 2, 1]), stages=1, full_grads=False)

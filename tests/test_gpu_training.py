@@ -67,3 +67,41 @@ def test_reconstruction_loss_after_k_iterations(golden, monkeypatch, name):
         assert abs(history[-1]['gradient_penalty'] - ref[-1]['gradient_penalty']) <= 0.1 * scale
     else:
         assert abs(history[-1]['kl_loss'] - ref[-1]['kl_loss']) <= 5e-2 * abs(ref[-1]['kl_loss'])
+
+
+@pytest.mark.parametrize("name", ["train_sg_tiny", "train_csg_tiny", "train_sg_wide"])
+def test_baselines_reconstruction_loss_after_k_iterations(golden, monkeypatch, name):
+    """BASELINE configs[2]: the train_video_baselines.py loop (GeneratorSG / GeneratorCSG against WDiscriminator3D,
+    train-depth 1) on the drop-in modules; reconstruction loss within 1 % of the reference after every iteration"""
+    from hpvg import images, train
+    from modules import networks_3d
+    fx = golden(name)
+    opt = train_opt_from(fx)
+    g = getattr(networks_3d, fx['generator'])(opt)
+    for _ in range(fx['stages']):
+        g.init_next_stage()
+    g.load_state_dict(state_from(fx), strict=True)
+    g.cuda()
+    d = networks_3d.WDiscriminator3D(opt)
+    d.load_state_dict(state_d_from(fx), strict=True)
+    d.cuda()
+    tr = train.BaselineTrainer(opt, g, d)
+    q = DrawQueue()
+    monkeypatch.setattr(images, "draw_normal", q)
+    alphas = []
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: torch.full((1, 1), alphas.pop(0)))
+    real, z_init = fx['real'].cuda(), fx['z_init'].cuda()
+    history = []
+    for it in range(fx['iters']):
+        dr = fx['draws'][it]
+        q.tensors = [dr['noise_init']] + [dr['noises'][lvl] for lvl in sorted(dr['noises'])]
+        alphas.append(dr['alpha'])
+        out = tr.iteration(real, z_init)
+        assert not q.tensors and not alphas, "the CUDA path draws in a different order than the reference"
+        history.append({k: v.item() for k, v in out.items()})
+    ref = fx['losses']
+    for it in range(fx['iters']):
+        assert abs(history[it]['rec_loss'] - ref[it]['rec_loss']) <= REC_TOL * abs(ref[it]['rec_loss']), (it, history[it], ref[it])
+    assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) <= REC_TOL * abs(fx['noise_amps_after'][-1])
+    scale = max(abs(ref[-1]['gradient_penalty']), 1e-3)
+    assert abs(history[-1]['gradient_penalty'] - ref[-1]['gradient_penalty']) <= 0.1 * scale

@@ -178,6 +178,25 @@ def test_training_loop_matches_reference(golden, name):
     assert rel_err(sd_g[key], fx['final_tail_weight']) < 1e-3
 
 
+@pytest.mark.parametrize("name", ["train_sg_tiny", "train_csg_tiny", "train_sg_wide"])
+def test_baselines_training_loop_matches_reference(golden, name):
+    """oracle/train_ref.py::BaselineTrainer (train_video_baselines.py:44-70, :100-173; BASELINE configs[2]: GeneratorSG,
+    train-depth 1) against the losses recorded from the unmodified reference modules stepping the same loop"""
+    from helpers import state_d_from, train_opt_from
+    from oracle import train_ref
+    fx = golden(name)
+    opt = train_opt_from(fx)
+    sd_g, sd_d = state_from(fx), state_d_from(fx)
+    tr = train_ref.BaselineTrainer(opt, sd_g, sd_d, generator=fx['generator'])
+    for it in range(fx['iters']):
+        dr = fx['draws'][it]
+        out = tr.iteration(fx['real'], fx['z_init'], noise_init=dr['noise_init'], noises=dr['noises'], alpha=dr['alpha'])
+        for k, v in fx['losses'][it].items():
+            assert abs(out[k].item() - v) <= 2e-3 * abs(v) + 2e-5, (it, k, out[k].item(), v)
+    assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) < 1e-4 * abs(fx['noise_amps_after'][-1])
+    assert rel_err(sd_g[fx['final_key']], fx['final_weight']) < 1e-3
+
+
 def test_numpy_primitives_match_torch():
     """oracle/np_ops.py (independent float64 numpy definitions) against the torch CPU operators oracle/port.py calls"""
     import numpy as np
