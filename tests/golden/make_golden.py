@@ -256,7 +256,7 @@ class DrawQueue(object):
         assert not self.normals and not self.rands, "unconsumed draws: the loop does not draw in the assumed order"
 
 
-def train_case(name, opt, scale_idx, iters, seed=0):
+def train_case(name, opt, scale_idx, iters, seed=0, three_d=True):
     """K iterations of the reference's per-scale loop (train_video.py:111-202, restated here only as the DRIVER: every
     network, loss and penalty call goes to the reference's own modules) at pyramid level `scale_idx`."""
     import torch.optim as optim
@@ -265,13 +265,19 @@ def train_case(name, opt, scale_idx, iters, seed=0):
         setattr(opt, k, v)
     opt.scale_idx = scale_idx
     opt.device = 'cpu'
-    g = make_generator(networks_3d, opt, scale_idx, seed=3)
+    nets = networks_3d if three_d else networks_2d
+    g = make_generator(nets, opt, scale_idx, seed=3)
     gan = opt.vae_levels < scale_idx + 1
     s0, t0 = port.scale_size(0, opt), port.time_depth(0, opt)
     sN, tN = port.scale_size(scale_idx, opt), port.time_depth(scale_idx, opt)
-    real_zero = port.det_tensor((1, 3, t0, s0, s0), 51)
-    real = port.det_tensor((1, 3, tN, sN, sN), 52) if scale_idx > 0 else real_zero
-    opt.Z_init_size = [1, opt.latent_dim, t0, s0, s0]
+    if three_d:
+        real_zero = port.det_tensor((1, 3, t0, s0, s0), 51)
+        real = port.det_tensor((1, 3, tN, sN, sN), 52) if scale_idx > 0 else real_zero
+        opt.Z_init_size = [1, opt.latent_dim, t0, s0, s0]
+    else:       # train_image.py: 4-D tensors, Z_init_size without the time axis (train_image.py:106-108)
+        real_zero = port.det_tensor((1, 3, s0, s0), 51)
+        real = port.det_tensor((1, 3, sN, sN), 52) if scale_idx > 0 else real_zero
+        opt.Z_init_size = [1, opt.latent_dim, s0, s0]
     opt.Noise_Amps = [1.0] + [0.1] * (scale_idx - 1) if scale_idx > 0 else []
     amps_before = list(opt.Noise_Amps)
     fx = {'opt': {k: v for k, v in opt.__dict__.items() if k != 'Noise_Amps'}, 'stages': scale_idx, 'fill_seed': 3, 'fill_seed_d': 7,
@@ -279,10 +285,11 @@ def train_case(name, opt, scale_idx, iters, seed=0):
           'state': [(k, tuple(v.shape)) for k, v in g.state_dict().items()]}
     d = None
     if gan:
-        d = networks_3d.WDiscriminator3D(opt)
+        d = networks_3d.WDiscriminator3D(opt) if three_d else networks_2d.WDiscriminator2D(opt)
         port.det_fill(d.state_dict(), seed=7)
         fx['state_d'] = [(k, tuple(v.shape)) for k, v in d.state_dict().items()]
         optimizerD = optim.Adam(d.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999))
+    fx['three_d'] = three_d
     # parameter groups exactly as train_video.py:57-88 builds them for the default flags (train_all False)
     if gan:
         depth = min(opt.train_depth, len(g.body) - opt.vae_levels + 1)
@@ -298,10 +305,10 @@ def train_case(name, opt, scale_idx, iters, seed=0):
     # shapes of the per-level noise of a 'rand' pass
     import utils as ref_utils
     noise_shapes = {}
-    x = torch.zeros(1, 3, t0, s0, s0)
+    x = torch.zeros(1, 3, t0, s0, s0) if three_d else torch.zeros(1, 3, s0, s0)
     for idx in range(scale_idx):
-        x = ref_utils.upscale(x, idx + 1, opt)
-        if opt.vae_levels <= idx + 1:
+        x = ref_utils.upscale(x, idx + 1, opt) if three_d else ref_utils.upscale_2d(x, idx + 1, opt)
+        if opt.vae_levels <= idx + 1 or not three_d:        # the 2-D generator adds noise at every level (networks_2d.py:261-263)
             noise_shapes[idx + 1] = tuple(x.shape)
     gen = torch.Generator().manual_seed(1000 + seed)
 
@@ -467,6 +474,11 @@ if __name__ == '__main__':
         csg_case('csg3d_wide', port.Opt(nfc=64, num_layer=3, img_size=20, min_size=12, sampling_rates=[4, 2, 1]), stages=1, full_grads=False)
         dbase_case('dbase3d_tiny', tiny_opt(num_layer=2), (1, 3, 4, 12, 11), True)
         dbase_case('dbase3d_wide', port.Opt(nfc=64, num_layer=3), (1, 3, 4, 14, 12), False)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'train2d':
+        # BASELINE configs[0]: train_image.py, 2-D HP-VAE-GAN (the same loop on networks_2d), a VAE level and a GAN level
+        train_case('train_vae2d_tiny', tiny_opt(), scale_idx=1, iters=8, three_d=False)
+        train_case('train_gan2d_tiny', tiny_opt(), scale_idx=2, iters=8, three_d=False)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         train_case('train_vae_tiny', tiny_opt(), scale_idx=1, iters=12)

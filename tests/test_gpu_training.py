@@ -24,20 +24,23 @@ class DrawQueue:
         return t.to(device=device, dtype=dtype)
 
 
-@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide"])
+@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide", "train_vae2d_tiny", "train_gan2d_tiny"])
 def test_reconstruction_loss_after_k_iterations(golden, monkeypatch, name):
+    """3-D fixtures: train_video.py's loop; *2d*: train_image.py's (BASELINE configs[0]: the same loop on networks_2d)"""
     from hpvg import images, train
-    from modules import networks_3d
+    from modules import networks_2d, networks_3d
     fx = golden(name)
     opt = train_opt_from(fx)
-    g = networks_3d.GeneratorHPVAEGAN(opt)
+    three_d = fx.get('three_d', True)
+    nets = networks_3d if three_d else networks_2d
+    g = nets.GeneratorHPVAEGAN(opt)
     for _ in range(fx['stages']):
         g.init_next_stage()
     g.load_state_dict(state_from(fx), strict=True)
     g.cuda()
     d = None
     if 'state_d' in fx:
-        d = networks_3d.WDiscriminator3D(opt)
+        d = networks_3d.WDiscriminator3D(opt) if three_d else networks_2d.WDiscriminator2D(opt)
         d.load_state_dict(state_d_from(fx), strict=True)
         d.cuda()
     tr = train.ScaleTrainer(opt, g, d)

@@ -155,7 +155,7 @@ def test_bf16_storage_emulation_stays_close_to_fp32(golden, name, bound):
             assert (mine - g.double()).norm().item() <= bound * g.double().norm().item() + 2e-3 * big, k
 
 
-@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide"])
+@pytest.mark.parametrize("name", ["train_vae_tiny", "train_gan_tiny", "train_gan_wide", "train_vae2d_tiny", "train_gan2d_tiny"])
 def test_training_loop_matches_reference(golden, name):
     """oracle/train_ref.py (optimizer groups + iteration body of train_video.py:44-202) against the losses recorded from
     the unmodified reference modules stepping the same loop on the same draws"""
