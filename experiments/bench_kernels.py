@@ -120,7 +120,10 @@ if which == "clk":
         print("rep", rep, "per-CTA clocks [mma loop, wait weights, wait slabs, epilogue total, epilogue wait acc]")
         for b in (0, 1, 64, 127):
             print("  cta", b, d[b, :5].tolist())
-        print("  mean", [int(v) for v in d[:128, :8].float().mean(0).tolist()])
+        print("  mean", [int(v) for v in d[:128, :5].float().mean(0).tolist()])
+        g0, g1 = d[:128, 5], d[:128, 6]
+        print("  globaltimer (ns): kernel span first CTA start -> last CTA end %d, CTA start spread %d, per-CTA duration mean %d max %d"
+              % (int(g1.max() - g0.min()), int(g0.max() - g0.min()), int((g1 - g0).float().mean()), int((g1 - g0).max())))
     print("thin 64->3")
     packed_t = ops.pack_weights(w_tail, 3, 64, 27, False, rows=16)
     b3 = torch.zeros(3, device=dev)

@@ -133,15 +133,20 @@ conv_col_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_y);
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
   pdl_trigger();
   pdl_wait();
+  __syncthreads();                       // barriers initialised and visible to every warp
+  // the producer warp starts its TMA loads at once; TMEM allocation and the bias fetch of the other warps overlap their flight
   float* bias_s = reinterpret_cast<float*>(sgen + OFF_BIAS);
-  for (int i = threadIdx.x; i < MAX_COUT; i += THREADS) bias_s[i] = (p.bias && i < g.Cout) ? p.bias[i] : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base = 0;
+  if (warp != 0) {
+    if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+    for (int i = threadIdx.x - 32; i < MAX_COUT; i += THREADS - 32) bias_s[i] = (p.bias && i < g.Cout) ? p.bias[i] : 0.f;
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(THREADS - 32) : "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
 
   // this CTA's run of tiles
   const long long t_begin = p.tiles * blockIdx.x / gridDim.x;

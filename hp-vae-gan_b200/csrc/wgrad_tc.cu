@@ -70,13 +70,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_gy);
   }
-  if (warp == 1) tmem_alloc<WG_TMEM_COLS>(smem_u32(tmem_slot));
   pdl_trigger();      // see conv_tc.cu: set-up above overlaps the previous kernel's tail, operands are read after the wait
   pdl_wait();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  __syncthreads();    // barriers initialised and visible
+  // the producer warp starts its TMA loads at once; the TMEM allocation of warp 1 overlaps their flight (see conv_tc.cu)
+  uint32_t tmem_base = 0;
+  if (warp != 0) {
+    if (warp == 1) tmem_alloc<WG_TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(WG_THREADS - 32) : "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
 
   long long t_d0 = 0, t_d1 = 0;   // drain-phase clocks (development aid)
   const long long b_begin = (long long)split * p.bricks_per_split;
