@@ -248,15 +248,41 @@ def run_hpvg(args):
         # the whole iteration (every libhpvg kernel, autograd glue, clipping, both Adam steps, the all-reduces) is
         # recorded once into a CUDA graph after W eager warm-up iterations and replayed per step
         c0 = lib.launch_count()
+        trainer.capture(real, real_zero, warmup=W, candidates=args.graph_candidates)
         torch.cuda.synchronize()
-        reserved0 = torch.cuda.memory_reserved()
-        trainer.capture(real, real_zero, warmup=W)
-        torch.cuda.synchronize()
-        last["pool_mb"] = (torch.cuda.memory_reserved() - reserved0) / 2**20
-        launches_per_iter = (lib.launch_count() - c0) // (W + 1)
+        last["pool_mb"] = getattr(trainer, "pool_bytes", 0) / 2**20
+        sys.stderr.write("graph recordings, ms per replay: %s\n" % ", ".join("%.3f" % t for t in getattr(trainer, "capture_trials", [])))
+        # launches counted per recorded iteration: W eager warm-up iterations + the recording pass of the first candidate, then
+        # 1 warm-up + 1 recording pass per further candidate (replays launch nothing through the library's host side)
+        launches_per_iter = (lib.launch_count() - c0) // (W + 1 + 2 * (max(1, args.graph_candidates) - 1))
 
         def step_resident():
             trainer.replay()
+
+        if args.recapture < 0:
+            # diagnostic: per-replay GPU time (events) and host enqueue time of 48 consecutive replays of one recording
+            import time as _time
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(49)]
+            host = []
+            torch.cuda.synchronize()
+            evs[0].record()
+            for k in range(48):
+                t0 = _time.perf_counter()
+                step_resident()
+                host.append((_time.perf_counter() - t0) * 1e3)
+                evs[k + 1].record()
+            torch.cuda.synchronize()
+            sys.stderr.write("per-replay ms (gpu): %s\n" % " ".join("%.2f" % evs[k].elapsed_time(evs[k + 1]) for k in range(48)))
+            sys.stderr.write("per-replay ms (host enqueue): %s\n" % " ".join("%.2f" % h for h in host))
+        if args.recapture > 0:
+            # diagnostic: replay time of several recordings of the same iteration in ONE process (how much of the run-to-run
+            # spread of ms_per_step is the schedule the graph instantiation happens to pick)
+            for k in range(args.recapture + 1):
+                for _ in range(3):
+                    step_resident()
+                sys.stderr.write("recording %d: %.3f ms per replay\n" % (k, timed(step_resident, 10) / 10))
+                if k < args.recapture:
+                    trainer.capture(real, real_zero, warmup=1)
 
         def step_e2e():
             out = trainer.replay(real_h, real_zero_h)          # H2D of the clip into the graph's input buffers
@@ -452,6 +478,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true", help="run one iteration between cudaProfilerStart/Stop and exit (for ncu)")
     ap.add_argument("--profile-gen", action="store_true", help="run one generation forward between cudaProfilerStart/Stop and exit (for ncu)")
+    ap.add_argument("--graph-candidates", type=int, default=1,
+                    help="record the iteration this many times and keep the recording that replays fastest (ScaleTrainer.capture)")
+    ap.add_argument("--recapture", type=int, default=0, help="diagnostic: re-record the iteration this many times and time each recording")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
                     help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128)")
