@@ -279,6 +279,7 @@ class ScaleTrainer:
         # in the warm-up steps); frozen stages keep the images cached before the capture, which stay valid for the lifetime
         # of this trainer because nothing else writes those weights.  Re-capture after load_state_dict().
         ops._GpAlpha.external = True
+        torch.cuda.empty_cache()      # torch.cuda.graph() does the same on entry: take the baseline after it
         reserved0 = torch.cuda.memory_reserved()
         try:
             with torch.cuda.graph(self.graph):
