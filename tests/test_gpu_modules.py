@@ -294,12 +294,13 @@ def test_discriminator_baselines_parity(golden, name):
         mutils.calc_gradient_penalty(d, fx['real'].cuda(), fx['fake'].cuda(), 0.1, 'cuda').backward()
 
 
-@pytest.mark.parametrize("nfc", [64, 8])
-def test_batched_generation_with_per_sample_batchnorm_equals_batch1_draws(monkeypatch, nfc):
+@pytest.mark.parametrize("nfc,col_mode", [(64, 0), (64, 1), (8, -1)])
+def test_batched_generation_with_per_sample_batchnorm_equals_batch1_draws(monkeypatch, nfc, col_mode):
     """ops.bn_per_sample: a batch-3 'rand' forward of GeneratorHPVAEGAN with per-draw BatchNorm statistics against three
     batch-1 forwards on the same latents and noise (the reference generates each draw with batch size 1,
-    train_video.py:226-235).  nfc 64: tcgen05 / expand kernels with [N, 2C] statistics; nfc 8: the per-sample fallback."""
-    from hpvg import images, ops
+    train_video.py:226-235).  nfc 64: tcgen05 (brick kernel / column kernel) and expand kernels with [N, 2C] statistics;
+    nfc 8: the per-sample fallback."""
+    from hpvg import images, lib, ops
     from modules import networks_3d
     opt = port.Opt(nfc=nfc, latent_dim=128 if nfc == 64 else 8, num_layer=2, vae_levels=1, img_size=24, min_size=16, sampling_rates=[4, 2, 1])
     g = networks_3d.GeneratorHPVAEGAN(opt)
@@ -314,16 +315,20 @@ def test_batched_generation_with_per_sample_batchnorm_equals_batch1_draws(monkey
     noises = [port.det_tensor((b,) + sh, 72 + i).cuda() for i, sh in enumerate(shapes)]
     amps = [1.0, 0.1, 0.1]
     singles = []
-    with torch.no_grad(), ops.bn_running_stats(False):
-        for i in range(b):
-            monkeypatch.setattr(images, "draw_normal", NoiseQueue([nz[i:i + 1] for nz in noises]))
-            fake, _ = g(z[i:i + 1], amps, noise_init=z[i:i + 1], mode='rand')
-            singles.append(fake)
-        monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
-        with ops.bn_per_sample(True):
-            batched, _ = g(z, amps, noise_init=z, mode='rand')
-        monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
-        coupled, _ = g(z, amps, noise_init=z, mode='rand')
+    prev_mode = lib.set_conv_col_mode(col_mode)
+    try:
+        with torch.no_grad(), ops.bn_running_stats(False):
+            for i in range(b):
+                monkeypatch.setattr(images, "draw_normal", NoiseQueue([nz[i:i + 1] for nz in noises]))
+                fake, _ = g(z[i:i + 1], amps, noise_init=z[i:i + 1], mode='rand')
+                singles.append(fake)
+            monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
+            with ops.bn_per_sample(True):
+                batched, _ = g(z, amps, noise_init=z, mode='rand')
+            monkeypatch.setattr(images, "draw_normal", NoiseQueue(noises))
+            coupled, _ = g(z, amps, noise_init=z, mode='rand')
+    finally:
+        lib.set_conv_col_mode(prev_mode)
     ref = torch.cat(singles, 0)
     assert batched.shape == ref.shape
     assert rel_err(batched, ref) < 1e-2          # same arithmetic; BatchNorm sums are accumulated in a different order
