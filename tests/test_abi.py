@@ -42,7 +42,7 @@ def test_host_only_entry_points():
 def test_drop_in_modules_expose_the_reference_names():
     from modules import losses, networks_2d, networks_3d, utils
     for name in ("ConvBlock3D", "ConvBlock3DSN", "FeatureExtractor", "Encode3DVAE", "WDiscriminator3D", "GeneratorHPVAEGAN",
-                 "GeneratorSG", "reparameterize", "weights_init", "get_activation"):
+                 "GeneratorSG", "GeneratorCSG", "WDiscriminatorBaselines", "reparameterize", "weights_init", "get_activation"):
         assert hasattr(networks_3d, name), name
     for name in ("ConvBlock2D", "ConvBlock2DSN", "FeatureExtractor", "Encode2DVAE", "WDiscriminator2D", "GeneratorHPVAEGAN",
                  "reparameterize"):
@@ -65,3 +65,50 @@ def test_state_dict_keys_match_the_reference_contract(golden):
     fd = golden("d3d_wide")
     d = networks_3d.WDiscriminator3D(opt_from(fd))
     assert [(k, tuple(v.shape)) for k, v in d.state_dict().items()] == [(k, tuple(s)) for k, s in fd["state"]]
+
+
+def test_state_dict_keys_of_the_baseline_networks(golden):
+    """GeneratorCSG / GeneratorSG / WDiscriminatorBaselines: same keys, shapes and construction-time RNG consumption as the
+    reference (weights_init draws N(0, 0.02) / N(1, 0.02) in module order, networks_3d.py:9-15,202,241,293)"""
+    import torch
+    from helpers import opt_from
+    from modules import networks_3d
+    for name, cls, stages in (("csg3d_tiny", networks_3d.GeneratorCSG, None), ("sg3d_tiny", networks_3d.GeneratorSG, None),
+                              ("dbase3d_tiny", networks_3d.WDiscriminatorBaselines, 0)):
+        fx = golden(name)
+        m = cls(opt_from(fx))
+        for _ in range(fx["stages"] if stages is None else stages):
+            m.init_next_stage()
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in fx["state"]], name
+    # the same seed gives the same initial weights as the reference's constructor would: weights_init overwrites every conv
+    # weight with N(0, 0.02), so the standard deviation is the check that does not need the reference here
+    torch.manual_seed(0)
+    g = networks_3d.GeneratorCSG(opt_from(golden("csg3d_wide")))
+    w = g.body[0].block0.conv.weight
+    assert abs(w.std().item() - 0.02) < 2e-3 and abs(g.head.norm.weight.mean().item() - 1.0) < 2e-2
+
+
+def test_zero_arena_and_per_sample_switch_host_logic():
+    """host-side state of hpvg.ops that needs no GPU: the bump allocator behind zeros_small() and the per-draw BatchNorm switch"""
+    import torch
+    from hpvg import ops
+    dev = torch.device("cpu")
+    a = ops.zeros_small(10, dev)
+    assert a.shape == (10,) and float(a.abs().sum()) == 0.0           # no arena: plain zeros
+    with ops.zero_arena(dev, 128):
+        x = ops.zeros_small(40, dev)
+        y = ops.zeros_small(40, dev)
+        assert x.untyped_storage().data_ptr() == y.untyped_storage().data_ptr()          # slices of one buffer
+        assert y.data_ptr() - x.data_ptr() == 64 * 4                                      # 32-float granules
+        z = ops.zeros_small(100, dev)                                                     # does not fit any more: falls back
+        assert z.untyped_storage().data_ptr() != x.untyped_storage().data_ptr()
+        x += 1.0
+        assert float(y.sum()) == 0.0
+    assert ops._ARENA[0] is None
+    assert ops._BN_PER_SAMPLE[0] is False
+    with ops.bn_per_sample(True):
+        assert ops._BN_PER_SAMPLE[0] is True
+        with ops.bn_per_sample(False):
+            assert ops._BN_PER_SAMPLE[0] is False
+        assert ops._BN_PER_SAMPLE[0] is True
+    assert ops._BN_PER_SAMPLE[0] is False
