@@ -635,6 +635,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// Both bf16 operand images (forward and data-gradient form) of up to HPVG_SN_MAX_LAYERS wide layers in ONE launch
+// (blockIdx.y = layer): the critic repacks W / sigma in every pass, 2 launches per layer otherwise.  Reads are coalesced in
+// the PyTorch layout [Cout][Cin][taps]; each element goes to fwd[t][co][ci] and tr[taps-1-t][ci][co], exactly the values
+// pack_weights_kernel writes for transposed = 0 / 1.
+struct PackBatch {
+  const float* w[HPVG_SN_MAX_LAYERS];
+  __nv_bfloat16* fwd[HPVG_SN_MAX_LAYERS];
+  __nv_bfloat16* tr[HPVG_SN_MAX_LAYERS];
+  int cout[HPVG_SN_MAX_LAYERS], cin[HPVG_SN_MAX_LAYERS], taps[HPVG_SN_MAX_LAYERS];
+};
+__global__ void __launch_bounds__(256) pack_pair_batched_kernel(const PackBatch b) {
+  pdl_enter();
+  const int l = blockIdx.y;
+  const int Cout = b.cout[l], Cin = b.cin[l], taps = b.taps[l];
+  const long long total = (long long)Cout * Cin * taps;
+  const float* w = b.w[l];
+  __nv_bfloat16* fwd = b.fwd[l];
+  __nv_bfloat16* tr = b.tr[l];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((long long)taps * Cin));
+    const __nv_bfloat16 v = f2bf(w[i]);
+    if (fwd) fwd[((size_t)t * Cout + co) * Cin + ci] = v;
+    if (tr) tr[((size_t)(taps - 1 - t) * Cin + ci) * Cout + co] = v;
+  }
+}
+
 // ===============================================================================================================
 // spectral normalisation                   reference: nn.utils.spectral_norm as used at modules/networks_3d.py:63
 // ===============================================================================================================
@@ -1052,6 +1080,24 @@ int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int
   launch_k(pack_weights_kernel, ew_blocks(total, 256), 256, 0, ST(stream), w_f32, reinterpret_cast<__nv_bfloat16*>(w_packed), Cout, Cin, taps,
                                                                      transposed, inv_scale_of, rows_per_tap);
   HPVG_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+int hpvg_pack_weights_pair_batched(int n, const float* const* w_f32, void* const* packed_fwd, void* const* packed_tr, const int* Cout,
+                                   const int* Cin, const int* taps, void* stream) {
+  HPVG_CHECK_ARG(n > 0 && n <= HPVG_SN_MAX_LAYERS, "pack_weights_pair_batched: %d layers (max %d)", n, HPVG_SN_MAX_LAYERS);
+  PackBatch b;
+  long long maxn = 0;
+  for (int l = 0; l < n; ++l) {
+    HPVG_CHECK_ARG(w_f32[l] && Cout[l] > 0 && Cin[l] > 0 && (taps[l] == 9 || taps[l] == 27), "pack_weights_pair_batched: bad layer %d", l);
+    b.w[l] = w_f32[l];
+    b.fwd[l] = reinterpret_cast<__nv_bfloat16*>(packed_fwd[l]);
+    b.tr[l] = reinterpret_cast<__nv_bfloat16*>(packed_tr[l]);
+    b.cout[l] = Cout[l]; b.cin[l] = Cin[l]; b.taps[l] = taps[l];
+    maxn = max(maxn, (long long)Cout[l] * Cin[l] * taps[l]);
+  }
+  launch_k(pack_pair_batched_kernel, dim3((unsigned)min(cdiv(maxn, 256), 128LL), n), 256, 0, ST(stream), b);
+  HPVG_CHECK_LAUNCH("pack_weights_pair_batched");
   return 0;
 }
 

@@ -128,6 +128,7 @@ def _run_sn_chain(blocks, x):
     the reference where every forward pre-hook runs on its own weight), then the convolutions"""
     blocks = list(blocks)
     weights = ops.spectral_weights([b.conv for b in blocks])
+    ops.prepack_pairs(weights)       # one launch for the bf16 operand images of all layers (forward + data-gradient form)
     # each block's output feeds exactly the next block, so in the first-order backward the next block's data-gradient launch
     # can apply this block's LeakyReLU derivative (and sum its bias gradient) in its epilogue: see ops.ChainLink
     link = None

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "hpvg_conv_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "hpvg_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "hpvg_pack_weights_pair_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hpvg_pack_weights_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hpvg_channel_sum": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_longlong, c_void_p]),
     "hpvg_bn_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_longlong,

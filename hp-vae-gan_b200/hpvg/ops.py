@@ -181,6 +181,37 @@ def packed_for(w, cout, cin, taps, transposed, rows):
     return packed
 
 
+def prepack_pairs(weights):
+    """Pack the forward and the data-gradient operand image of every tcgen05-eligible weight in `weights` (float32,
+    [Cout, Cin, (3,)3,3], e.g. the W / sigma tensors of one critic pass) in ONE launch and plant them in the per-weight cache,
+    so that the packed_for() calls of the convolutions that follow hit.  Same values as pack_weights()."""
+    if lib.get_conv_backend() == lib.BACKEND_DIRECT:
+        return
+    todo = [w for w in weights if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() in (4, 5)
+            and w.shape[1] in (64, 128) and w.shape[0] % 64 == 0 and w._base is None]
+    for i in range(0, len(todo), lib.SN_MAX_LAYERS):
+        chunk = todo[i:i + lib.SN_MAX_LAYERS]
+        fwd, tr, couts, cins, taps = [], [], [], [], []
+        for w in chunk:
+            cout, cin = w.shape[0], w.shape[1]
+            t = _kd_of(w) * 9
+            fwd.append(torch.empty((t, cout, cin), dtype=torch.bfloat16, device=w.device))
+            tr.append(torch.empty((t, cin, cout), dtype=torch.bfloat16, device=w.device))
+            couts.append(cout); cins.append(cin); taps.append(t)
+        lib.call("hpvg_pack_weights_pair_batched", len(chunk), lib.ptr_array(chunk), lib.ptr_array(fwd), lib.ptr_array(tr),
+                 lib.int_array(couts), lib.int_array(cins), lib.int_array(taps), _stream())
+        for w, f, r, cout, cin in zip(chunk, fwd, tr, couts, cins):
+            stamp = (w._version, _PACK_GEN[0], w.data_ptr())
+            cache = getattr(w, '_hpvg_packs', None)
+            if cache is None:
+                try:
+                    w._hpvg_packs = cache = {}
+                except (AttributeError, RuntimeError):
+                    continue
+            cache[(False, cout)] = (stamp, f)        # packed_for(w, cout, cin, taps, False, rows=cout)
+            cache[(True, cin)] = (stamp, r)          # packed_for(w, cin, cout, taps, True, rows=cin): the data-gradient form
+
+
 def expand_image_for(w, cin, taps, transposed):
     """float32 [taps][cin][64] filter image for the thin -> wide kernel, cached on the weight like packed_for()"""
     key = ('expand', bool(transposed))

@@ -114,6 +114,12 @@ int hpvg_conv_wgrad(const void* x, int x_fmt, const void* gy, int gy_fmt, float*
 int hpvg_pack_weights(const float* w_f32, void* w_packed, int Cout, int Cin, int taps, int transposed,
                       const float* inv_scale_of, int rows_per_tap, void* stream);
 
+/* Both images (transposed == 0 into packed_fwd[l], transposed == 1 into packed_tr[l]; either may be NULL) of n <=
+ * HPVG_SN_MAX_LAYERS layers with rows_per_tap = Cout, no scaling, in one launch: the critic's spectral-norm weights change in
+ * every pass, so every pass repacks all of them.  Arrays of n device pointers / shapes live in host memory. */
+int hpvg_pack_weights_pair_batched(int n, const float* const* w_f32, void* const* packed_fwd, void* const* packed_tr,
+                                   const int* Cout, const int* Cin, const int* taps, void* stream);
+
 /* float32 [taps][Cin][64] image of the filter of a thin -> wide layer (Cin <= 4, 64 output channels; `transposed` as in
  * hpvg_conv_forward), passed as `w_packed` to hpvg_conv_forward for NCDHW_F32 -> NDHWC_BF16 calls: optional, but lets every
  * block of the kernel copy the filter instead of gathering it from the PyTorch layout. */
