@@ -410,9 +410,9 @@ def run_hpvg(args):
             roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, 64->64 @ 16x64x64)",
                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         # dram__bytes_read.sum + dram__bytes_write.sum of one 64->64 launch at 16x64x64 from the committed ncu --set full
-                        # capture (profiles/r01e_conv_tc_ncu.txt): 8.71 MB read (algorithmic 8.39 MB input + 0.22 MB weights), 0 written
+                        # capture (profiles/r01g_conv_tc_ncu.txt): 8.71 MB read (algorithmic 8.39 MB input + 0.22 MB weights), 0 written
                         # before the kernel ends (the 8.39 MB output is still in L2); None for other workloads
-                        "traffic": 8711168 if WORKLOAD["name"] == "cfg2" else None, "traffic_unit": "bytes per launch",
+                        "traffic": 8705024 if WORKLOAD["name"] == "cfg2" else None, "traffic_unit": "bytes per launch",
                         "flops_per_launch": top["work"], "us_per_launch": per_launch_ms * 1e3, "launches_timed": top["launches"],
                         "peak_source": peak_src,
                         "share_of_step": (top["ms"] / prof_steps) / (ms / args.steps),
