@@ -712,6 +712,10 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
   p.w_img_bytes = (unsigned)((size_t)g.taps * (thin ? 16 : g.Cout) * g.Cin * 2);
   static const int variant = getenv("HPVG_TC_VARIANT") ? atoi(getenv("HPVG_TC_VARIANT")) : 0;   // tuning knob: 1 = unstacked, 2 = unstacked two groups, 3 = stacked two groups (measured: 24.5 us vs 22.4 us for the default)
   if (thin) {
+    // 2-slice units when the depth is even but not a multiple of 4 (the 6-slice pyramid levels): every unit is then full.
+    // A 4-slice unit with only two valid output slices takes the run-time-range path of the issue loop — measured 39.5 us
+    // per launch at 6 x 46 x 46 and 6 x 54 x 54 against 17.6 us for the (larger) 16 x 64 x 64 volume.
+    if (g.KD == 3 && variant != 1 && g.Do % 4 != 0 && g.Do % 2 == 0) return launch_tc<1, 2, 3, 1, 16, true>(mx, mw, my, p, st);
     if (g.KD == 3) return variant == 1 ? launch_tc<1, 4, 3, 1, 16>(mx, mw, my, p, st) : launch_tc<1, 4, 3, 1, 16, true>(mx, mw, my, p, st);
     return launch_tc<1, 4, 1, 1, 16>(mx, mw, my, p, st);
   }

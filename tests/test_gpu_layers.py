@@ -310,7 +310,8 @@ def test_full_size_batchnorm_statistics():
 
 
 @pytest.mark.parametrize("cin,cout,vol,pad", [(64, 64, (37, 64, 64), 1), (64, 64, (9, 130, 70), 1), (128, 64, (12, 48, 40), 1),
-                                              (64, 64, (22, 50, 50), 0), (64, 3, (37, 64, 64), 1)])
+                                              (64, 64, (22, 50, 50), 0), (64, 3, (37, 64, 64), 1), (64, 3, (6, 46, 46), 1),
+                                              (64, 1, (2, 20, 33), 1), (64, 3, (10, 30, 30), 0)])
 def test_tcgen05_kernels_with_several_units_per_cta(cin, cout, vol, pad):
     """volumes with more work units than SMs (every CTA loops over several units, with different zero-padding patterns per
     unit: BASELINE configs[4], 32 x 128 x 128, is such a case): tcgen05 kernels against the library's CUDA-core kernels"""
