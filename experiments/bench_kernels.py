@@ -7,7 +7,7 @@ from hpvg import ops, lib
 dev = "cuda"
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-D, H, W = (32, 128, 128) if os.environ.get('BENCH_BIG') == '1' else (16, 64, 64)     # BASELINE config 5 / config 2 finest volume
+D, H, W = (32, 128, 128) if os.environ.get('BENCH_BIG') == '1' else (int(os.environ.get('BENCH_D', '16')), 64, 64)     # BASELINE config 5 / config 2 finest volume
 V = D * H * W
 flush = torch.empty(256 * 2**20 // 4, device=dev)
 

@@ -673,7 +673,10 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
         const long long units = conv_col_brick_units(g) / (g.Cout / 64);     // per 64-channel block
         const long long rounds = cdiv(units * (g.Cout / 64), num_sms());
         const double eff = (double)g.N * g.Do * g.Ho * g.Wo * (g.Cout / 64) / ((double)rounds * num_sms() * 512.0);
-        use_col = eff < col_eff;
+        // ... or when its last d-unit would be partial (Do % 4 != 0, e.g. the 13 / 7 / 5-frame levels of the reference's default
+        // sampling rates): a partial unit takes the run-time-range issue path, ~2x the time of a full unit, and with one unit
+        // per CTA it sets the kernel time
+        use_col = eff < col_eff || (g.Do % 4 != 0);
       }
       if (use_col) return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
     }
