@@ -326,7 +326,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                   } else {
                     const uint64_t bd = bs + (uint64_t)((klo * Cfg::BTILE_BYTES + ks * 32) >> 4);
                     const uint32_t tacc = tmem_base + acc_col(j - klo);
-                    if (n == 3)
+                    if constexpr (!FULL) {
+                      // run-time ranges: ONE instruction with the N field computed, not three predicated copies with three
+                      // descriptor sets (the issue loop of a partial unit was instruction-bound, ~2x the time of a full unit)
+                      umma_bf16_acc(tacc, ad, bd, umma_idesc_bf16(128, n * NOUT, 0, 0));
+                    } else if (n == 3)
                       umma_bf16_acc(tacc, ad, bd, umma_idesc_bf16(128, 3 * NOUT, 0, 0));
                     else if (n == 2)
                       umma_bf16_acc(tacc, ad, bd, umma_idesc_bf16(128, 2 * NOUT, 0, 0));
