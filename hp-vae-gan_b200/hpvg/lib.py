@@ -1,7 +1,7 @@
 """ctypes binding of libhpvg.so.  Signatures mirror include/hpvg.h one to one."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpvg.so")
@@ -73,6 +73,9 @@ PROTOTYPES = {
                                            c_int, c_float, c_void_p]),
     "hpvg_sn_backward_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p]),
+    "hpvg_grad_clip_coef": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "hpvg_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double,
+                               c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -107,6 +110,9 @@ def call(name, *args):
         raise HpvgError("%s failed (%d): %s" % (name, rc, lib.hpvg_last_error().decode(errors="replace")))
 
 
+OPT_MAX_TENSORS = 32      # HPVG_OPT_MAX_TENSORS: tensors per hpvg_adam_step / hpvg_grad_clip_coef call
+OPT_BLOCKS = 16           # HPVG_OPT_BLOCKS: partial sums per tensor
+OPT_STATE_FLOATS = 8
 SN_MAX_LAYERS = 8
 SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the spectral-norm backward
 
@@ -114,6 +120,10 @@ SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the sp
 def ptr_array(tensors):
     """host array of device pointers (for the *_batched entry points)"""
     return (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def longlong_array(values):
+    return (c_longlong * len(values))(*[int(v) for v in values])
 
 
 def int_array(values):

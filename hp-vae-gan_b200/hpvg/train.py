@@ -18,7 +18,7 @@ import contextlib
 import torch
 import torch.nn.functional as F
 
-from . import images, ops
+from . import images, ops, optim
 
 
 def _train_defaults(opt):
@@ -104,10 +104,16 @@ class ScaleTrainer:
         if self.gan and netD is None:
             raise ValueError("scale %d is a GAN scale (vae_levels=%d): a discriminator is required" % (opt.scale_idx, opt.vae_levels))
         self.capturable = capturable
-        # capturable mode uses torch's fused multi-tensor Adam kernel (one launch per parameter group, same update rule)
-        extra = dict(capturable=True, fused=True) if capturable else {}
-        self.optimizerG = torch.optim.Adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999), **extra)
-        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999), **extra) if self.gan else None
+        # CUDA parameters: clipping + Adam on the library's multi-tensor kernels (hpvg/optim.py; device-side step count, so
+        # the pair records into the CUDA graph).  CPU parameters (host-logic tests) or HPVG_TORCH_ADAM=1: torch's Adam, in
+        # capturable mode its fused multi-tensor kernel (same update rule).
+        if optim.use_library_optimizer(netG.parameters()):
+            adam = optim.Adam
+        else:
+            extra = dict(capturable=True, fused=True) if capturable else {}
+            adam = lambda params, **kw: torch.optim.Adam(params, **kw, **extra)
+        self.optimizerG = adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999))
+        self.optimizerD = adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999)) if self.gan else None
         self.distributed = distributed
         self.bucketG, self.bucketD = GradBucket(), GradBucket()
         self.allreduce_bytes = 0
@@ -221,8 +227,11 @@ class ScaleTrainer:
         total_loss.backward()
         if self.distributed:
             self.allreduce_bytes += self.bucketG.average(list(G.parameters()))
-        torch.nn.utils.clip_grad_norm_(G.parameters(), opt.grad_clip)
-        self.optimizerG.step()
+        if isinstance(self.optimizerG, optim.Adam):
+            self.optimizerG.step(clip_params=list(G.parameters()), max_norm=opt.grad_clip)      # clip_grad_norm_ + step, 2 launches
+        else:
+            torch.nn.utils.clip_grad_norm_(G.parameters(), opt.grad_clip)
+            self.optimizerG.step()
         out['total_loss'] = total_loss.detach()
         self.iterations += 1
         return out
@@ -347,8 +356,9 @@ class BaselineTrainer:
             groups.append({"params": netG.head.parameters(), "lr": opt.lr_g * (opt.lr_scale ** opt.scale_idx)})
         if hasattr(netG, 'tail'):
             groups.append({"params": netG.tail.parameters(), "lr": opt.lr_g})
-        self.optimizerD = torch.optim.Adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999))
-        self.optimizerG = torch.optim.Adam(groups, lr=opt.lr_g, betas=(opt.beta1, 0.999))
+        adam = optim.Adam if optim.use_library_optimizer(netG.parameters()) else torch.optim.Adam
+        self.optimizerD = adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999))
+        self.optimizerG = adam(groups, lr=opt.lr_g, betas=(opt.beta1, 0.999))
         self.iterations = 0
 
     def iteration(self, real, z_init):

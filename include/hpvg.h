@@ -254,6 +254,32 @@ int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* cons
                              const float* const* v, const float* const* sigma, float* const* gw_orig, float* const* scratch,
                              const int* Cout, const int* K, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * End of an iteration: gradient clipping + Adam over all tensors of an optimizer.  Replaces
+ * torch.nn.utils.clip_grad_norm_(G_curr.parameters(), opt.grad_clip) (train_video.py:201, train_image.py:216) and
+ * optim.Adam(...).step() (train_video.py:55,88,183,202; train_video_baselines.py:51,70: betas (beta1, 0.999), eps 1e-8,
+ * no weight decay, no amsgrad).  All tensors are contiguous float32; the pointer / size / lr arrays are HOST arrays of n
+ * entries (n <= HPVG_OPT_MAX_TENSORS per call; more tensors = more calls).
+ * `state`: HPVG_OPT_STATE_FLOATS device floats owned by the optimizer, zero-initialised once:
+ *   [0] step count t   [1] clip coefficient   [2] total gradient norm   [4],[5] block tickets (self-resetting)
+ * grad_clip_coef: partials[slot_base + i*HPVG_OPT_BLOCKS + b] = per-block sums of squares of grads[i]; the call with
+ *   finalize != 0 (the last one of a sequence covering total_slots slots) reduces all partials in index order and sets
+ *   state[1] = min(1, max_norm / (sqrt(sum) + 1e-6)), state[2] = sqrt(sum).  No atomically accumulated floats.
+ * adam_step: g <- g*state[1] (when use_clip; written back, as clip_grad_norm_ scales .grad in place), m <- lerp(m, g, 1-beta1),
+ *   v <- beta2 v + (1-beta2) g^2, p <- p - lr[i]/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps) with t = state[0] + 1.
+ *   exp_avg[i] == NULL: tensor i is not owned by the optimizer, only its gradient is scaled.  advance_step != 0 (the last
+ *   call of a step): state[0] <- t when the grid has finished.  The step count lives on the device so that a recorded CUDA
+ *   graph advances it at every replay.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define HPVG_OPT_MAX_TENSORS 32
+#define HPVG_OPT_BLOCKS 16
+#define HPVG_OPT_STATE_FLOATS 8
+int hpvg_grad_clip_coef(int n, const float* const* grads, const long long* numel, float* partials, int slot_base,
+                        int total_slots, int finalize, float max_norm, float* state, void* stream);
+int hpvg_adam_step(int n, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const long long* numel, const float* lr, double beta1, double beta2, double eps, int use_clip,
+                   int advance_step, float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

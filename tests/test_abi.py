@@ -112,3 +112,20 @@ def test_zero_arena_and_per_sample_switch_host_logic():
             assert ops._BN_PER_SAMPLE[0] is False
         assert ops._BN_PER_SAMPLE[0] is True
     assert ops._BN_PER_SAMPLE[0] is False
+
+
+def test_library_optimizer_refuses_cpu_parameters_and_keeps_torch_state_layout():
+    """hpvg.optim.Adam has no CPU path; its param_groups carry torch.optim.Adam's keys (checkpoint compatibility)"""
+    import torch
+    from hpvg import optim
+    from hpvg.lib import HpvgError
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    o = optim.Adam([{"params": [p], "lr": 1e-4}], lr=5e-4, betas=(0.5, 0.999))
+    with pytest.raises(HpvgError):
+        o.step()
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3))], lr=5e-4, betas=(0.5, 0.999)).state_dict()['param_groups'][0]
+    mine = o.state_dict()['param_groups'][0]
+    assert {'lr', 'betas', 'eps', 'weight_decay', 'amsgrad', 'maximize', 'params'} <= set(mine) <= set(ref)
+    assert mine['lr'] == 1e-4 and mine['betas'] == (0.5, 0.999) and mine['eps'] == ref['eps']
+    assert not optim.use_library_optimizer([p])

@@ -108,3 +108,37 @@ def test_baselines_reconstruction_loss_after_k_iterations(golden, monkeypatch, n
     assert abs(opt.Noise_Amps[-1] - fx['noise_amps_after'][-1]) <= REC_TOL * abs(fx['noise_amps_after'][-1])
     scale = max(abs(ref[-1]['gradient_penalty']), 1e-3)
     assert abs(history[-1]['gradient_penalty'] - ref[-1]['gradient_penalty']) <= 0.1 * scale
+
+
+def test_recorded_iteration_replays_with_the_library_optimizer(golden):
+    """ScaleTrainer.capture / replay: the whole GAN-level iteration, clipping and both Adam steps included,
+    replays from one CUDA graph; every replay is a training step (device-side step count, moving weights, finite losses that
+    stay on the scale of the eager iterations)"""
+    from hpvg import optim, train
+    from modules import networks_3d
+    fx = golden("train_gan_tiny")
+    opt = train_opt_from(fx)
+    g = networks_3d.GeneratorHPVAEGAN(opt)
+    for _ in range(fx['stages']):
+        g.init_next_stage()
+    g.load_state_dict(state_from(fx), strict=True)
+    g.cuda()
+    d = networks_3d.WDiscriminator3D(opt)
+    d.load_state_dict(state_d_from(fx), strict=True)
+    d.cuda()
+    torch.manual_seed(0)
+    tr = train.ScaleTrainer(opt, g, d, capturable=True)
+    assert isinstance(tr.optimizerG, optim.Adam) and isinstance(tr.optimizerD, optim.Adam)
+    real, real_zero = fx['real'].cuda(), fx['real_zero'].cuda()
+    tr.capture(real, real_zero, warmup=2)
+    tail = [p for p in g.body[-1].parameters()][0]
+    before = tail.detach().clone()
+    rec = []
+    for _ in range(3):
+        out = tr.replay()
+        rec.append(out['rec_loss'].item())
+        assert all(torch.isfinite(v).all() for v in out.values())
+    assert not torch.equal(before, tail.detach())
+    assert float(tr.optimizerG.state[tail]['step']) == 5.0 and float(tr.optimizerD.state[next(d.parameters())]['step']) == 5.0
+    ref = fx['losses'][min(4, fx['iters'] - 1)]['rec_loss']
+    assert 0.5 * ref < rec[-1] < 2.0 * ref, (rec, ref)
