@@ -56,6 +56,21 @@ int set_conv_col_mode(int mode) {
   g_col_mode.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0), std::memory_order_relaxed);
   return prev;
 }
+static std::atomic<int> g_wgrad_mode{-1};
+int wgrad_mode() {
+  int v = g_wgrad_mode.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HPVG_WGRAD_STACK");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+    g_wgrad_mode.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+int set_wgrad_mode(int mode) {
+  const int prev = wgrad_mode();
+  g_wgrad_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 int set_pdl(int on) {
   const int prev = pdl_enabled() ? 1 : 0;
   g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
@@ -167,6 +182,7 @@ int hpvg_debug_set_clock_buffer(long long* device_buffer) {
 
 int hpvg_set_pdl(int on) { return hpvg::set_pdl(on); }
 int hpvg_set_conv_col_mode(int mode) { return hpvg::set_conv_col_mode(mode); }
+int hpvg_set_wgrad_mode(int mode) { return hpvg::set_wgrad_mode(mode); }
 
 int hpvg_profile_enable(int on) {
   hpvg::g_prof_on.store(on ? 1 : 0);

@@ -67,6 +67,8 @@ int set_pdl(int on);
 // supports the layer.  Environment HPVG_TC_COL sets the initial value.
 int conv_col_mode();
 int set_conv_col_mode(int mode);
+int wgrad_mode();               // 0 = one kd per CTA (default), 1 = kd-stacked N = 192 form where KD == 3 (wgrad_tc.cu)
+int set_wgrad_mode(int mode);
 
 #ifdef __CUDACC__
 template <typename... P, typename... A>

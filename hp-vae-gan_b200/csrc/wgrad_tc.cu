@@ -202,6 +202,173 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 1) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// kd-stacked form (KD == 3 only; OFF by default: hpvg_set_wgrad_mode(1) / HPVG_WGRAD_STACK=1).  NOT YET RUN ON A GPU —
+// written at the end of round 1 after the GPU budget was spent; experiments/check_wgrad_stack.py is its parity check.
+//
+// Measured cost model: an M = 128, K = 16 MMA with both operands in shared memory costs max(64, N/2)
+// cycles, so the N = 64 instructions above run the tensor pipe at half rate by construction (5 x 64 = 320 clk per
+// k-step and brick for 9 taps).  Here the work item is one INPUT slab (slice d); the gy bricks of the three output
+// slices it feeds, od = d + pad_d - kd, are loaded side by side and read as ONE MN-major B operand of N = 192 whose three
+// 64-column N-atoms lie WG_GY_BYTES apart (descriptor LBO — the same mechanism the A operand uses for its two taps):
+//     D[ci][kd*64 + co] += X_d(kh,kw)^T[ci][voxel] * [GY_{d+p} | GY_{d+p-1} | GY_{d+p-2}][voxel][kd*64 + co]
+// One instruction serves the three kd taps of a (kh,kw) position.  A CTA owns one kh (blockIdx.z): taps kw = 0,1 share an
+// M = 128 instruction, kw = 2 takes a second one (upper half duplicated and ignored): 2 x 96 = 192 clk per k-step and
+// slab for the same 9 taps.  TMEM: 2 accumulators x 192 columns.  gy slices outside the volume are fetched as fully
+// out-of-bounds TMA boxes (zero fill, full byte count) — the first thing to confirm on the GPU.
+// Partials keep the layout [split][tap][ci][co]; the reduction kernel is shared.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WK_STAGE_BYTES = WG_SLAB_STRIDE + 3 * WG_GY_BYTES;   // 72704 (multiple of 1024)
+constexpr int WK_STAGES = 3;
+constexpr int WK_NACC = 2;
+constexpr int WK_ACC_COLS = 192;
+constexpr int WK_SMEM_BYTES = WK_STAGES * WK_STAGE_BYTES + (2 * WK_STAGES + 1) * 8 + 16 + 1024;
+static_assert(WK_STAGE_BYTES % 1024 == 0, "stage bases must keep the 1024-byte swizzle alignment");
+static_assert(WK_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(WK_NACC * WK_ACC_COLS <= WG_TMEM_COLS, "TMEM budget");
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_gy, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const uint32_t s_bar = sbase + WK_STAGES * WK_STAGE_BYTES;
+  auto bar_full = [&](int i) { return s_bar + 8u * i; };
+  auto bar_empty = [&](int i) { return s_bar + 8u * (WK_STAGES + i); };
+  const uint32_t bar_acc = s_bar + 8u * (2 * WK_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + WK_STAGES * WK_STAGE_BYTES + (2 * WK_STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  const int split = blockIdx.x;
+  const int cblocks_in = g.Cin / 64;
+  const int ci_blk = blockIdx.y % cblocks_in, co_blk = blockIdx.y / cblocks_in;
+  const int kh = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WK_STAGES; ++i) {
+      mbar_init(bar_full(i), 1);
+      mbar_init(bar_empty(i), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_gy);
+  }
+  pdl_trigger();
+  pdl_wait();
+  __syncthreads();
+  uint32_t tmem_base = 0;
+  if (warp != 0) {
+    if (warp == 1) tmem_alloc<WG_TMEM_COLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(WG_THREADS - 32) : "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
+
+  // work items = input slabs: num_bricks = N * Di * bricks_h * bricks_w here
+  const long long b_begin = (long long)split * p.bricks_per_split;
+  const long long b_end = min(p.num_bricks, b_begin + p.bricks_per_split);
+  auto decode = [&](long long b, int& n, int& d, int& h0, int& w0) {
+    w0 = (int)(b % p.bricks_w) * WG_BW;
+    b /= p.bricks_w;
+    h0 = (int)(b % p.bricks_h) * WG_BH;
+    b /= p.bricks_h;
+    d = (int)(b % g.Di);
+    n = (int)(b / g.Di);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (long long b = b_begin; b < b_end; ++b) {
+        int n, d, h0, w0;
+        decode(b, n, d, h0, w0);
+        mbar_wait(bar_empty(stage), phase ^ 1u);
+        mbar_expect_tx(bar_full(stage), WG_SLAB_BYTES + 3 * WG_GY_BYTES);
+        const uint32_t sa = sbase + stage * WK_STAGE_BYTES;
+        tma_load_5d(sa, &tmap_x, bar_full(stage), ci_blk * 64, w0 - g.pad, h0 - g.pad, d, n);
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)      // N-atom kd = the gy slice that meets this slab through tap kd
+          tma_load_5d(sa + WG_SLAB_STRIDE + kd * WG_GY_BYTES, &tmap_gy, bar_full(stage), co_blk * 64, w0, h0, d + g.pad_d - kd, n);
+        if (++stage == WK_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(128, WK_ACC_COLS, 1, 1);   // A and B MN-major, N = 3 atoms of 64
+      const uint32_t a_kh = (uint32_t)kh * WG_SLAB_W * 128u;
+      uint32_t stage = 0, phase = 0;
+      uint32_t first = 1;
+      long long t_start = clock64(), t_wait = 0;
+      for (long long b = b_begin; b < b_end; ++b) {
+        if (p.dbg) t_wait -= clock64();
+        mbar_wait(bar_full(stage), phase);
+        if (p.dbg) t_wait += clock64();
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * WK_STAGE_BYTES;
+        const uint64_t b_base = umma_desc(sa + WG_SLAB_STRIDE, WG_GY_BYTES, 1024, 2);
+#pragma unroll
+        for (int pr = 0; pr < WK_NACC; ++pr) {
+          // pr 0: taps kw = 0 (lanes 0-63) and kw = 1 (lanes 64-127), one slab row apart; pr 1: kw = 2 twice
+          const uint64_t a_base = umma_desc(sa + a_kh + (uint32_t)(2 * pr) * 128u, pr == 0 ? 128u : 0u, WG_SLAB_W * 128, 2);
+          const uint32_t tacc = tmem_base + pr * WK_ACC_COLS;
+          umma_bf16(tacc, a_base, b_base, IDESC, first ^ 1u);
+#pragma unroll
+          for (int ks = 1; ks < 8; ++ks)
+            umma_bf16_acc(tacc, a_base + (uint64_t)((2 * ks * WG_SLAB_W * 128) >> 4), b_base + (uint64_t)((ks * 2048) >> 4), IDESC);
+        }
+        umma_commit(bar_empty(stage));
+        first = 0;
+        if (++stage == WK_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_acc);
+      if (p.dbg) {
+        const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.dbg[cta * 8 + 0] = clock64() - t_start;
+        p.dbg[cta * 8 + 1] = t_wait;
+      }
+    }
+    __syncwarp();
+  } else {
+    // drain: TMEM [lane = half*64 + ci][pr*192 + kd*64 + co] -> partial[split][kd*9 + kh*3 + kw][ci][co], kw = 2*pr + half
+    const bool any = b_begin < b_end;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ci = ci_blk * 64 + (m & 63);
+    for (int pr = 0; pr < WK_NACC; ++pr) {
+      const int kw = 2 * pr + (m >> 6);
+      for (int kd = 0; kd < 3; ++kd) {
+        uint32_t r[64];
+        if (any) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + pr * WK_ACC_COLS + kd * 64;
+          tmem_ld32(taddr, r);
+          tmem_ld32(taddr + 32, r + 32);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) r[j] = 0u;
+        }
+        if (kw <= 2) {
+          const int tap = kd * 9 + kh * 3 + kw;
+          float4* dst = reinterpret_cast<float4*>(p.partial + (((size_t)split * g.taps + tap) * g.Cin + ci) * g.Cout + co_blk * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
+}
+
 // dw[co][ci][tap] = sum_s partial[s][tap][ci][co]: 4 consecutive co per thread (128-bit loads), splits walked by 4
 // threads per output quad and combined through shared memory
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partial, float* __restrict__ dw, int splits,
@@ -252,17 +419,40 @@ static void wgrad_plan(const ConvGeom& g, int& bricks_h, int& bricks_w, long lon
   splits = (int)cdiv(num_bricks, per_split);
 }
 
+// kd-stacked form: work items are input slabs (N * Di * bricks), grid.z = kh
+static bool wgrad_kdstack_ok(const ConvGeom& g) { return g.KD == 3 && g.taps == 27; }
+static void wgrad_plan_kdstack(const ConvGeom& g, int& bricks_h, int& bricks_w, long long& num_items, int& splits, long long& per_split) {
+  bricks_h = (int)cdiv(g.Ho, WG_BH);
+  bricks_w = (int)cdiv(g.Wo, WG_BW);
+  num_items = (long long)g.N * g.Di * bricks_h * bricks_w;
+  const int others = 3 * (g.Cin / 64) * (g.Cout / 64);
+  long long want = max(1LL, (long long)num_sms() / others);
+  want = min(want, num_items);
+  per_split = cdiv(num_items, want);
+  splits = (int)cdiv(num_items, per_split);
+}
+
+// large enough for either form, so that the mode can change between the workspace query and the call
 size_t wgrad_tc_workspace(const ConvGeom& g) {
   int bh, bw, splits;
   long long nb, per;
   wgrad_plan(g, bh, bw, nb, splits, per);
+  if (wgrad_kdstack_ok(g)) {
+    int s2;
+    wgrad_plan_kdstack(g, bh, bw, nb, s2, per);
+    splits = max(splits, s2);
+  }
   return (size_t)splits * g.taps * g.Cin * g.Cout * sizeof(float);
 }
 
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
   WgParams p;
   p.g = g;
-  wgrad_plan(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
+  const bool stacked = wgrad_mode() == 1 && wgrad_kdstack_ok(g);
+  if (stacked)
+    wgrad_plan_kdstack(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
+  else
+    wgrad_plan(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
   const size_t need = (size_t)p.splits * g.taps * g.Cin * g.Cout * sizeof(float);
   if (ws_bytes < need || workspace == nullptr) {
     set_error("wgrad_tc: workspace too small (%zu < %zu bytes)", ws_bytes, need);
@@ -284,15 +474,23 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_tc_kdstack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("wgrad_tc: cannot opt in to %d bytes of shared memory: %s", WG_SMEM_BYTES, cudaGetErrorString(e));
+      set_error("wgrad_tc: cannot opt in to %d bytes of shared memory: %s", max(WG_SMEM_BYTES, WK_SMEM_BYTES), cudaGetErrorString(e));
       return -2;
     }
     attr_done = true;
   }
-  dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), (unsigned)g.KD);
-  launch_k(wgrad_tc_kernel, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
-  HPVG_CHECK_LAUNCH("wgrad_tc_kernel");
+  if (stacked) {
+    dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), 3u);
+    launch_k(wgrad_tc_kdstack_kernel, grid, WG_THREADS, WK_SMEM_BYTES, st, mx, mg, p);
+    HPVG_CHECK_LAUNCH("wgrad_tc_kdstack_kernel");
+  } else {
+    dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), (unsigned)g.KD);
+    launch_k(wgrad_tc_kernel, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
+    HPVG_CHECK_LAUNCH("wgrad_tc_kernel");
+  }
   const long long total4 = (long long)g.taps * g.Cin * g.Cout / 4;
   launch_k(wgrad_reduce_kernel, (unsigned)cdiv(total4, 64), 256, 0, st, reinterpret_cast<const float4*>(p.partial), dw, p.splits, g.taps,
                                                                  g.Cin, g.Cout);

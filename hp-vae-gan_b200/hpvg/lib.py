@@ -23,6 +23,7 @@ PROTOTYPES = {
     "hpvg_profile_enable": (c_int, [c_int]),
     "hpvg_set_pdl": (c_int, [c_int]),
     "hpvg_set_conv_col_mode": (c_int, [c_int]),
+    "hpvg_set_wgrad_mode": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
@@ -149,6 +150,11 @@ def set_conv_col_mode(mode):
     """-1 = brick or column-streaming tcgen05 kernel per layer (default), 0 = brick kernel always, 1 = column kernel whenever
     supported; returns the previous mode"""
     return int(load().hpvg_set_conv_col_mode(int(mode)))
+
+
+def set_wgrad_mode(mode):
+    """0 = measured weight-gradient kernel (default), 1 = kd-stacked N = 192 form (experimental); returns the previous mode"""
+    return int(load().hpvg_set_wgrad_mode(int(mode)))
 
 
 def set_pdl(on):
