@@ -56,6 +56,26 @@ int set_conv_col_mode(int mode) {
   g_col_mode.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0), std::memory_order_relaxed);
   return prev;
 }
+static std::atomic<int> g_carveout{-1};
+bool carveout_enabled() {
+  int v = g_carveout.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HPVG_CARVEOUT");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+    g_carveout.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void prefer_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::map<const void*, bool> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  if (seen.count(kernel)) return;
+  seen[kernel] = true;
+  // a hint: failure (or a driver that ignores it) changes nothing about correctness
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+    cudaGetLastError();
+}
 static std::atomic<int> g_wgrad_mode{-1};
 int wgrad_mode() {
   int v = g_wgrad_mode.load(std::memory_order_relaxed);

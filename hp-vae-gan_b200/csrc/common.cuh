@@ -67,6 +67,11 @@ int set_pdl(int on);
 // supports the layer.  Environment HPVG_TC_COL sets the initial value.
 int conv_col_mode();
 int set_conv_col_mode(int mode);
+// HPVG_CARVEOUT=1 (experimental, unmeasured): every libhpvg kernel asks for the maximum shared-memory carve-out, so that SMs
+// do not have to drain and re-partition L1 / shared memory between the small-footprint kernels and the 220 KB tcgen05 kernels
+// (kernels with different carve-outs cannot share an SM, which also limits the overlap of the iteration's streams)
+bool carveout_enabled();
+void prefer_max_smem(const void* kernel);
 int wgrad_mode();               // 0 = one kd per CTA (default), 1 = kd-stacked N = 192 form where KD == 3 (wgrad_tc.cu)
 int set_wgrad_mode(int mode);
 
@@ -83,6 +88,7 @@ static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (carveout_enabled()) prefer_max_smem(reinterpret_cast<const void*>(kernel));
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 #endif
