@@ -75,3 +75,21 @@ def kl(mu, logvar):
 def gp_penalty(grads, lam):
     """modules/utils.py:18: L2 norm over the CHANNEL axis per voxel"""
     return np.mean((np.sqrt((grads ** 2).sum(1)) - 1) ** 2) * lam
+
+
+def clip_grad_norm(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_(G_curr.parameters(), opt.grad_clip) (train_video.py:201, train_image.py:216):
+    total = 2-norm over ALL gradients, every gradient scaled by min(1, max_norm / (total + 1e-6)); returns (scaled, total)"""
+    total = np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads))
+    coef = min(1.0, max_norm / (total + 1e-6))
+    return [g * coef for g in grads], total
+
+
+def adam_step(p, g, m, v, step, lr, beta1, beta2=0.999, eps=1e-8):
+    """optim.Adam(lr, betas=(opt.beta1, 0.999)).step() (train_video.py:55,88,183,202; eps 1e-8, no weight decay, no amsgrad):
+    `step` is the count BEFORE this update; returns (p, m, v) after it"""
+    t = step + 1
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    denom = np.sqrt(v) / np.sqrt(1 - beta2 ** t) + eps
+    return p - (lr / (1 - beta1 ** t)) * m / denom, m, v

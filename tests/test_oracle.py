@@ -252,3 +252,33 @@ def test_data_path_restatement():
     assert torch.equal(flipped, clip.flip(-1))
     video = np.array([-1.0, -0.5, 0.0, 0.5, 1.0, 0.999], dtype=np.float32).reshape(1, 1, 1, 6).repeat(3, 0)
     assert data_ref.frames_to_uint8(video)[0, 0, :, 0].tolist() == [0, 63, 127, 191, 255, 254]
+
+
+def test_numpy_clip_and_adam_match_torch():
+    """oracle/np_ops.py clip_grad_norm / adam_step (the definition hpvg.optim.Adam's kernels are held to on the GPU, SURVEY.md
+    §8f-1) against torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on the CPU, in float64, over several steps"""
+    import numpy as np
+    from oracle import np_ops
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(4, 3, 3, 3, 3), (4,), (7, 5)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=gen, dtype=torch.float64)) for s in shapes]
+    opt = torch.optim.Adam([{"params": params[:1], "lr": 1e-4}, {"params": params[1:], "lr": 5e-4}], lr=5e-4, betas=(0.5, 0.999))
+    lrs = [1e-4, 5e-4, 5e-4]
+    p_np = [p.detach().numpy().copy() for p in params]
+    m_np = [np.zeros_like(a) for a in p_np]
+    v_np = [np.zeros_like(a) for a in p_np]
+    for step in range(5):
+        grads = [torch.randn(s, generator=gen, dtype=torch.float64) * 10.0 ** (step - 2) for s in shapes]
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_(params, 5.0)
+        scaled, total_np = np_ops.clip_grad_norm([g.numpy() for g in grads], 5.0)
+        assert abs(total_np - total.item()) <= 1e-12 * total.item()
+        for p, s_ in zip(params, scaled):
+            assert np.allclose(p.grad.numpy(), s_, rtol=1e-12, atol=0)
+        opt.step()
+        for i in range(len(params)):
+            p_np[i], m_np[i], v_np[i] = np_ops.adam_step(p_np[i], scaled[i], m_np[i], v_np[i], step, lrs[i], 0.5)
+            assert np.allclose(params[i].detach().numpy(), p_np[i], rtol=1e-10, atol=1e-14)
+            assert np.allclose(opt.state[params[i]]['exp_avg'].numpy(), m_np[i], rtol=1e-10, atol=1e-300)
+            assert np.allclose(opt.state[params[i]]['exp_avg_sq'].numpy(), v_np[i], rtol=1e-10, atol=1e-300)
