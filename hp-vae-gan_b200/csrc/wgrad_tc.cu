@@ -353,13 +353,25 @@ wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
           for (int j = 0; j < 64; ++j) r[j] = 0u;
         }
-        if (kw <= 2) {
+        if (kw <= 2) {      // warp-uniform: m >> 6 is the same for the 32 lanes of a quadrant
+          // A thread holds one 256-byte row (its ci): written straight to global memory, every store instruction would touch
+          // 32 different lines.  The 32 x 256-byte tile of the warp goes through a private staging tile instead (the pipeline
+          // stages are dead once bar_acc has completed; 16-byte chunks XOR-swizzled by row: conflict-free both ways) and
+          // leaves as 512 contiguous bytes per instruction.
           const int tap = kd * 9 + kh * 3 + kw;
-          float4* dst = reinterpret_cast<float4*>(p.partial + (((size_t)split * g.taps + tap) * g.Cin + ci) * g.Cout + co_blk * 64);
+          uint8_t* stg = sgen + (warp - 2) * 8192;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3]));
+            *reinterpret_cast<uint4*>(stg + lane * 256 + ((j ^ (lane & 15)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          float* tile = p.partial + (((size_t)split * g.taps + tap) * g.Cin + (ci - lane)) * g.Cout + co_blk * 64;   // row 0 = lane 0's ci
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int c = it * 32 + lane, row = c >> 4, col = c & 15;
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 256 + ((col ^ (row & 15)) << 4));
+            *reinterpret_cast<uint4*>(tile + (size_t)row * g.Cout + col * 4) = v;
+          }
+          __syncwarp();     // the next tile reuses the staging area
         }
       }
     }
