@@ -13,6 +13,7 @@ timeout 90 python experiments/check_wgrad_stack.py > ${O}_wgrad_stack.txt 2>&1; 
 timeout 200 python bench.py > ${O}_bench_default.json 2> ${O}_bench_default.err
 HPVG_CARVEOUT=1 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_carveout.json 2> ${O}_bench_carveout.err
 if grep -q "ALL OK" ${O}_wgrad_stack.txt; then
+  HPVG_WGRAD_STACK=2 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_wgrad_staged.json 2> ${O}_bench_wgrad_staged.err
   HPVG_WGRAD_STACK=1 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_wgrad_stack.json 2> ${O}_bench_wgrad_stack.err
   HPVG_WGRAD_STACK=1 timeout 120 python -m pytest tests/test_gpu_layers.py tests/test_gpu_training.py -m gpu -q > ${O}_tests_wgrad_stack.txt 2>&1
   tail -2 ${O}_tests_wgrad_stack.txt

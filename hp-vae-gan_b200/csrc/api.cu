@@ -80,15 +80,16 @@ static std::atomic<int> g_wgrad_mode{-1};
 int wgrad_mode() {
   int v = g_wgrad_mode.load(std::memory_order_relaxed);
   if (v < 0) {
-    const char* e = getenv("HPVG_WGRAD_STACK");
-    v = (e && atoi(e) != 0) ? 1 : 0;
+    const char* e = getenv("HPVG_WGRAD_STACK");      // 1 = kd-stacked kernel, 2 = measured kernel with the staged drain
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
     g_wgrad_mode.store(v, std::memory_order_relaxed);
   }
   return v;
 }
 int set_wgrad_mode(int mode) {
   const int prev = wgrad_mode();
-  g_wgrad_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  g_wgrad_mode.store((mode < 0 || mode > 2) ? 0 : mode, std::memory_order_relaxed);
   return prev;
 }
 int set_pdl(int on) {

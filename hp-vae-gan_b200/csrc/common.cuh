@@ -72,7 +72,7 @@ int set_conv_col_mode(int mode);
 // (kernels with different carve-outs cannot share an SM, which also limits the overlap of the iteration's streams)
 bool carveout_enabled();
 void prefer_max_smem(const void* kernel);
-int wgrad_mode();               // 0 = one kd per CTA (default), 1 = kd-stacked N = 192 form where KD == 3 (wgrad_tc.cu)
+int wgrad_mode();               // 0 = one kd per CTA (default), 1 = kd-stacked N = 192 form where KD == 3, 2 = default kernel with the staged drain (wgrad_tc.cu)
 int set_wgrad_mode(int mode);
 
 #ifdef __CUDACC__

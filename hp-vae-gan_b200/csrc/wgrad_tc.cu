@@ -41,6 +41,9 @@ struct WgParams {
   long long* dbg;             // optional per-CTA phase clocks (development aid)
 };
 
+// STAGED (hpvg_set_wgrad_mode(2), unmeasured): the drain writes its partials through a swizzled shared-memory tile so that every
+// store instruction covers 512 contiguous bytes (see wgrad_tc_kdstack_kernel); <false> is the measured kernel, unchanged.
+template <bool STAGED>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_gy, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -184,11 +187,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
       if (tap9 <= 8) {
         const int tap = kd * 9 + tap9;
-        float4* dst = reinterpret_cast<float4*>(p.partial + (((size_t)split * g.taps + tap) * g.Cin + ci) * g.Cout + co_blk * 64);
+        if constexpr (STAGED) {
+          uint8_t* stg = sgen + (warp - 2) * 8192;      // pipeline stage 0 is dead once bar_acc has completed
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 16; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 256 + ((j ^ (lane & 15)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          float* tile = p.partial + (((size_t)split * g.taps + tap) * g.Cin + (ci - lane)) * g.Cout + co_blk * 64;
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int c = it * 32 + lane, row = c >> 4, col = c & 15;
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 256 + ((col ^ (row & 15)) << 4));
+            *reinterpret_cast<uint4*>(tile + (size_t)row * g.Cout + col * 4) = v;
+          }
+          __syncwarp();
+        } else {
+          float4* dst = reinterpret_cast<float4*>(p.partial + (((size_t)split * g.taps + tap) * g.Cin + ci) * g.Cout + co_blk * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+        }
       }
     }
   }
@@ -485,7 +504,8 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(wgrad_tc_kdstack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -500,7 +520,10 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
     HPVG_CHECK_LAUNCH("wgrad_tc_kdstack_kernel");
   } else {
     dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), (unsigned)g.KD);
-    launch_k(wgrad_tc_kernel, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
+    if (wgrad_mode() == 2)
+      launch_k(wgrad_tc_kernel<true>, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
+    else
+      launch_k(wgrad_tc_kernel<false>, grid, WG_THREADS, WG_SMEM_BYTES, st, mx, mg, p);
     HPVG_CHECK_LAUNCH("wgrad_tc_kernel");
   }
   const long long total4 = (long long)g.taps * g.Cin * g.Cout / 4;

@@ -66,9 +66,10 @@ int hpvg_set_pdl(int on);
  * kernel whenever it supports the layer.  Initial value from HPVG_TC_COL.  Returns the previous mode. */
 int hpvg_set_conv_col_mode(int mode);
 /* Weight-gradient kernel of the 3-D wide layers: 0 = one kd tap plane per CTA, N = 64 MMAs (default, measured);
- * 1 = kd-stacked form, one N = 192 MMA per (kh,kw) position serves the three kd taps (wgrad_tc.cu; EXPERIMENTAL: written
- * after round 1's GPU budget was spent, not yet run — experiments/check_wgrad_stack.py).  Initial value from
- * HPVG_WGRAD_STACK.  Returns the previous mode. */
+ * 1 = kd-stacked form, one N = 192 MMA per (kh,kw) position serves the three kd taps; 2 = the measured kernel with its fp32
+ * partials written through a swizzled shared-memory tile (coalesced stores).  Modes 1 and 2 are EXPERIMENTAL: written after
+ * round 1's GPU budget was spent, not yet run — experiments/check_wgrad_stack.py.  Initial value from HPVG_WGRAD_STACK.
+ * Returns the previous mode. */
 int hpvg_set_wgrad_mode(int mode);
 int hpvg_profile_dump(double* rows, int max_rows);
 
