@@ -129,3 +129,47 @@ def test_library_optimizer_refuses_cpu_parameters_and_keeps_torch_state_layout()
     assert {'lr', 'betas', 'eps', 'weight_decay', 'amsgrad', 'maximize', 'params'} <= set(mine) <= set(ref)
     assert mine['lr'] == 1e-4 and mine['betas'] == (0.5, 0.999) and mine['eps'] == ref['eps']
     assert not optim.use_library_optimizer([p])
+
+
+def test_library_optimizer_call_tables(monkeypatch):
+    """host logic of hpvg.optim.Adam.step on CPU tensors with the library calls recorded instead of executed: tensors per call
+    (<= 32), partial-sum slots, finalize / advance flags on the last chunk only, NULL moments for clipped-but-not-owned tensors,
+    per-group learning rates, and the refusal of a changing gradient set"""
+    import ctypes
+    import torch
+    from hpvg import lib, optim
+    calls = []
+    monkeypatch.setattr(optim.Adam, "_check", staticmethod(lambda t, what: None))
+    monkeypatch.setattr(optim, "_stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(lib, "call", lambda name, *a: calls.append((name, a)))
+    owned = [torch.nn.Parameter(torch.zeros(3 + i)) for i in range(40)]
+    extra = [torch.nn.Parameter(torch.zeros(2)) for _ in range(5)]
+    for p in owned + extra:
+        p.grad = torch.ones_like(p)
+    opt = optim.Adam([{"params": owned[:10], "lr": 1e-4}, {"params": owned[10:]}], lr=5e-4, betas=(0.5, 0.999))
+    opt.step(clip_params=owned + extra, max_norm=5.0)
+    clip = [a for n, a in calls if n == "hpvg_grad_clip_coef"]
+    adam = [a for n, a in calls if n == "hpvg_adam_step"]
+    assert [a[0] for a in clip] == [32, 13] and [a[0] for a in adam] == [32, 13]
+    slots = 45 * lib.OPT_BLOCKS
+    assert [(a[4], a[5], a[6]) for a in clip] == [(0, slots, 0), (32 * lib.OPT_BLOCKS, slots, 1)]      # slot_base, total, finalize
+    assert [a[7] for a in clip] == [5.0, 5.0]
+    assert [(a[10], a[11]) for a in adam] == [(1, 0), (1, 1)]                                          # use_clip, advance_step
+    assert (adam[0][7], adam[0][8], adam[0][9]) == (0.5, 0.999, 1e-8)
+    lrs = list(adam[0][6]) + list(adam[1][6])
+    assert lrs[:10] == [pytest.approx(1e-4)] * 10 and lrs[10:40] == [pytest.approx(5e-4)] * 30 and lrs[40:] == [0.0] * 5
+    numel = list(adam[0][5]) + list(adam[1][5])
+    assert numel == [3 + i for i in range(40)] + [2] * 5
+    moments = list(adam[1][3])
+    assert all(m is not None for m in moments[:8]) and moments[8:] == [None] * 5                      # extra tensors: scaled only
+    assert list(adam[1][1])[8:] == [None] * 5 and list(adam[1][2])[8:] == [e.grad.data_ptr() for e in extra]
+    assert all(p._version == 1 for p in owned) and opt.last_launches == 4
+    # no clipping: one kind of call, the extra tensors are not touched
+    calls.clear()
+    opt.step()
+    assert [n for n, _ in calls] == ["hpvg_adam_step", "hpvg_adam_step"] and [a[0] for _, a in calls] == [32, 8]
+    assert [(a[10], a[11]) for _, a in calls] == [(0, 0), (0, 1)]
+    # one shared step count: a parameter that skips a step is refused
+    owned[3].grad = None
+    with pytest.raises(lib.HpvgError):
+        opt.step()
