@@ -17,6 +17,7 @@ bool narrow_wgrad_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g);
 int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbias_wide, const ConvGeom& g, void* workspace,
                  size_t ws_bytes, cudaStream_t st);
+bool conv_tc_picks_column(int y_fmt, const ConvGeom& g, const void* w_packed);
 bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
@@ -99,6 +100,15 @@ int hpvg_conv_forward_ex(const void* x, int x_fmt, const float* w_f32, const voi
   int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
   prof_end(ph, st);
   return rc;
+}
+
+int hpvg_conv_kernel_choice(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int y_fmt) {
+  ConvGeom g;
+  if (int rc = make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_kernel_choice")) return rc;
+  const void* packed = reinterpret_cast<const void*>(uintptr_t(1));      // "a packed weight image exists": only compared with NULL
+  if (conv_tc_supported(x_fmt, y_fmt, g, packed)) return conv_tc_picks_column(y_fmt, g, packed) ? HPVG_KERNEL_TC_COLUMN : HPVG_KERNEL_TC_BRICK;
+  if (expand_conv_supported(x_fmt, y_fmt, g, nullptr)) return HPVG_KERNEL_EXPAND;
+  return HPVG_KERNEL_DIRECT;
 }
 
 int hpvg_pack_weights_expand(const float* w_f32, float* w_tco, int Cin, int taps, int transposed, void* stream) {

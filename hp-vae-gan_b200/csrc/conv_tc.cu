@@ -658,33 +658,32 @@ long long conv_col_brick_units(const ConvGeom& g);
 int conv_col(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
              const void* mask_src, cudaStream_t st);
 
+// Column-streaming kernel (conv_col.cu) or brick kernel?  The brick kernel is faster per unit of work (N = 192 MMAs) but
+// deals work out in 4-slice x 128-voxel units, one round of at most num_sms() units at a time: a volume with 6 d-slices
+// wastes half of every second unit, 54 x 54 wastes a fifth of its bricks, and 448 units on 148 SMs take four rounds.  The
+// column kernel deals out single 128-voxel x 32-channel tiles in contiguous runs.  Measured (batch-8 generation, us per
+// launch brick / column): 4x32x32 23.0 / 15.9, 4x39x39 23.7 / 21.4, 6x46x46 65.4 / 29.3, 6x54x54 85.3 / 41.0, 16x64x64
+// 110.2 / 113.4; batch 1 at 16x64x64 22.6 / 24.6.  Rule (mode -1, the default): brick when the voxels it really computes
+// fill at least HPVG_TC_COL_EFF (default 0.8) of the unit slots of its rounds.  (Host logic only: hpvg_conv_kernel_choice
+// exposes it to the CPU tests.)
+bool conv_tc_picks_column(int y_fmt, const ConvGeom& g, const void* w_packed) {
+  const int col_mode = conv_col_mode();
+  static const double col_eff = getenv("HPVG_TC_COL_EFF") ? atof(getenv("HPVG_TC_COL_EFF")) : 0.8;
+  if (col_mode == 0 || !conv_col_supported(HPVG_FMT_NDHWC_BF16, y_fmt, g, w_packed)) return false;
+  if (col_mode == 1) return true;
+  const long long units = conv_col_brick_units(g) / (g.Cout / 64);     // per 64-channel block
+  const long long rounds = cdiv(units * (g.Cout / 64), num_sms());
+  const double eff = (double)g.N * g.Do * g.Ho * g.Wo * (g.Cout / 64) / ((double)rounds * num_sms() * 512.0);
+  // ... or when its last d-unit would be partial (Do % 4 != 0, e.g. the 13 / 7 / 5-frame levels of the reference's default
+  // sampling rates): a partial unit takes the run-time-range issue path, ~2x the time of a full unit, and with one unit
+  // per CTA it sets the kernel time
+  return eff < col_eff || (g.Do % 4 != 0);
+}
+
 int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int y_fmt, const ConvGeom& g, int act, float slope,
             float* stats, const void* mask_src, cudaStream_t st) {
   const bool thin = y_fmt == HPVG_FMT_NCDHW_F32;
-  {
-    // Column-streaming kernel (conv_col.cu) or brick kernel?  The brick kernel is faster per unit of work (N = 192 MMAs) but
-    // deals work out in 4-slice x 128-voxel units, one round of at most num_sms() units at a time: a volume with 6 d-slices
-    // wastes half of every second unit, 54 x 54 wastes a fifth of its bricks, and 448 units on 148 SMs take four rounds.  The
-    // column kernel deals out single 128-voxel x 32-channel tiles in contiguous runs.  Measured (batch-8 generation, us per
-    // launch brick / column): 4x32x32 23.0 / 15.9, 4x39x39 23.7 / 21.4, 6x46x46 65.4 / 29.3, 6x54x54 85.3 / 41.0, 16x64x64
-    // 110.2 / 113.4; batch 1 at 16x64x64 22.6 / 24.6.  Rule (mode -1, the default): brick when the voxels it really computes
-    // fill at least HPVG_TC_COL_EFF (default 0.8) of the unit slots of its rounds.
-    const int col_mode = conv_col_mode();
-    static const double col_eff = getenv("HPVG_TC_COL_EFF") ? atof(getenv("HPVG_TC_COL_EFF")) : 0.8;
-    if (col_mode != 0 && conv_col_supported(HPVG_FMT_NDHWC_BF16, y_fmt, g, w_packed)) {
-      bool use_col = col_mode == 1;
-      if (!use_col) {
-        const long long units = conv_col_brick_units(g) / (g.Cout / 64);     // per 64-channel block
-        const long long rounds = cdiv(units * (g.Cout / 64), num_sms());
-        const double eff = (double)g.N * g.Do * g.Ho * g.Wo * (g.Cout / 64) / ((double)rounds * num_sms() * 512.0);
-        // ... or when its last d-unit would be partial (Do % 4 != 0, e.g. the 13 / 7 / 5-frame levels of the reference's default
-        // sampling rates): a partial unit takes the run-time-range issue path, ~2x the time of a full unit, and with one unit
-        // per CTA it sets the kernel time
-        use_col = eff < col_eff || (g.Do % 4 != 0);
-      }
-      if (use_col) return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
-    }
-  }
+  if (conv_tc_picks_column(y_fmt, g, w_packed)) return conv_col(x, w_packed, bias, y, g, act, slope, stats, mask_src, st);
   const int nout = thin ? 16 : 64;
   CUtensorMap mx, mw, my;
   {

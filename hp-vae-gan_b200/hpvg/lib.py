@@ -25,6 +25,7 @@ PROTOTYPES = {
     "hpvg_set_conv_col_mode": (c_int, [c_int]),
     "hpvg_set_wgrad_mode": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
+    "hpvg_conv_kernel_choice": (c_int, [c_int] * 10),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "hpvg_conv_forward_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -150,6 +151,15 @@ def set_conv_col_mode(mode):
     """-1 = brick or column-streaming tcgen05 kernel per layer (default), 0 = brick kernel always, 1 = column kernel whenever
     supported; returns the previous mode"""
     return int(load().hpvg_set_conv_col_mode(int(mode)))
+
+
+KERNEL_DIRECT, KERNEL_EXPAND, KERNEL_TC_BRICK, KERNEL_TC_COLUMN = 0, 1, 2, 3
+
+
+def conv_kernel_choice(n, cin, cout, d, h, w, kd=3, pad=1, x_wide=True, y_wide=True):
+    """which kernel hpvg_conv_forward picks for this layer (host logic only: works without a GPU)"""
+    return int(load().hpvg_conv_kernel_choice(n, cin, cout, d, h, w, kd, pad, FMT_NDHWC_BF16 if x_wide else FMT_NCDHW_F32,
+                                              FMT_NDHWC_BF16 if y_wide else FMT_NCDHW_F32))
 
 
 def set_wgrad_mode(mode):

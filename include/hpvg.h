@@ -72,6 +72,13 @@ int hpvg_set_conv_col_mode(int mode);
  * Returns the previous mode. */
 int hpvg_set_wgrad_mode(int mode);
 int hpvg_profile_dump(double* rows, int max_rows);
+/* Which kernel hpvg_conv_forward picks for a layer with the AUTO backend, a packed weight image available, plain epilogue
+ * (host logic only, no launch; negative = invalid geometry).  COLUMN vs BRICK follows hpvg_set_conv_col_mode's rule. */
+#define HPVG_KERNEL_DIRECT 0
+#define HPVG_KERNEL_EXPAND 1
+#define HPVG_KERNEL_TC_BRICK 2
+#define HPVG_KERNEL_TC_COLUMN 3
+int hpvg_conv_kernel_choice(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int y_fmt);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Convolution, 3x3x3 (KD == 3) or 3x3 (KD == 1), stride 1, zero padding `pad` in {0,1,2} on every filtered axis.

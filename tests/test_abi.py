@@ -173,3 +173,30 @@ def test_library_optimizer_call_tables(monkeypatch):
     owned[3].grad = None
     with pytest.raises(lib.HpvgError):
         opt.step()
+
+
+def test_kernel_selection_rule():
+    """hpvg_conv_forward's choice of kernel per layer (host logic): the brick tcgen05 kernel when its 4-slice units
+    fill the SMs' unit slots and the depth is a multiple of 4, the column-streaming kernel otherwise; the 3-channel ends and
+    odd channel counts never reach tcgen05 kernels they do not support"""
+    from hpvg import lib
+    prev = lib.set_conv_col_mode(-1)
+    try:
+        pick = lib.conv_kernel_choice
+        assert pick(1, 64, 64, 16, 64, 64) == lib.KERNEL_TC_BRICK        # BASELINE configs[1], finest level: 128 full units
+        assert pick(1, 64, 64, 32, 128, 128) == lib.KERNEL_TC_BRICK      # configs[4]: 1 024 units, 7 rounds at 0.99 fill
+        assert pick(1, 64, 64, 13, 64, 64) == lib.KERNEL_TC_COLUMN       # default sampling rates: depth not a multiple of 4
+        assert pick(1, 64, 64, 6, 54, 54) == lib.KERNEL_TC_COLUMN        # ragged bricks, half-empty second unit
+        assert pick(1, 64, 64, 4, 32, 32) == lib.KERNEL_TC_COLUMN        # 16 units on 148 SMs
+        assert pick(1, 128, 64, 4, 32, 32) == lib.KERNEL_TC_BRICK        # decoder head: the column kernel is 64-input-channel only
+        assert pick(1, 64, 64, 1, 64, 64, kd=1) == lib.KERNEL_TC_BRICK   # 2-D layers (networks_2d): column kernel is 3-D only
+        assert pick(1, 64, 3, 16, 64, 64, y_wide=False) == lib.KERNEL_TC_BRICK     # thin-output tails run the brick kernel's NOUT = 16 form
+        assert pick(1, 3, 64, 16, 64, 64, x_wide=False) == lib.KERNEL_EXPAND       # head convs: TF32 mma.sync kernel
+        assert pick(1, 8, 8, 4, 8, 8) == lib.KERNEL_DIRECT                         # the 8-channel test networks
+        assert pick(1, 64, 64, 16, 64, 64, pad=3) < 0                              # invalid geometry is refused
+        lib.set_conv_col_mode(0)
+        assert pick(1, 64, 64, 6, 54, 54) == lib.KERNEL_TC_BRICK
+        lib.set_conv_col_mode(1)
+        assert pick(1, 64, 64, 16, 64, 64) == lib.KERNEL_TC_COLUMN
+    finally:
+        lib.set_conv_col_mode(prev)
