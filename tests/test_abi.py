@@ -200,3 +200,25 @@ def test_kernel_selection_rule():
         assert pick(1, 64, 64, 16, 64, 64) == lib.KERNEL_TC_COLUMN
     finally:
         lib.set_conv_col_mode(prev)
+
+
+def test_wgrad_workspace_plan():
+    """hpvg_conv_wgrad_workspace (host logic): fp32 partials [splits][taps][Cin][Cout] with splits x KD x channel blocks <= 148
+    CTAs, one split per group of bricks; large enough for either weight-gradient kernel form"""
+    from hpvg import lib
+    ws = lib.load().hpvg_conv_wgrad_workspace
+
+    def splits(n, cin, cout, d, h, w, kd, pad):
+        nbytes = ws(n, cin, cout, d, h, w, kd, pad, lib.FMT_NDHWC_BF16, lib.FMT_NDHWC_BF16)
+        per_split = kd * 9 * cin * cout * 4
+        assert nbytes % per_split == 0
+        return nbytes // per_split
+
+    assert splits(1, 64, 64, 16, 64, 64, 3, 1) == 47       # 512 bricks, 148 // 3 = 49 wanted -> 11 bricks per split
+    assert splits(1, 64, 64, 4, 32, 32, 3, 1) == 32        # 64 bricks, 2 per split
+    assert splits(1, 128, 64, 4, 32, 32, 3, 1) == 16       # two input-channel blocks share the SMs
+    assert splits(1, 64, 64, 1, 64, 64, 1, 1) == 32        # 2-D layer: 32 bricks, one each
+    for shape in [(1, 64, 64, 16, 64, 64, 3, 1), (2, 64, 128, 7, 20, 33, 3, 1), (1, 64, 64, 22, 50, 50, 3, 0)]:
+        s = splits(*shape)
+        blocks = (shape[1] // 64) * (shape[2] // 64)
+        assert 1 <= s and s * shape[6] * blocks <= 148
