@@ -97,6 +97,29 @@ def main():
             t0, t1, t2 = (timed(m_, x, g, pad, (cout, cin, 3, 3, 3)) for m_ in (0, 1, 2))
             print("%s: mode0 %.1f us  stacked %.1f us  mode0 + staged drain %.1f us (kernel + reduction, cold L2)" % ((n, d, h, w), t0, t1, t2),
                   flush=True)
+    if ok:
+        # per-CTA phase clocks (cycles): MMA issue loop, of which waiting for TMA stages, drain warps waiting for the accumulators, drain
+        n, d, h, w = CASES[0][2]
+        x = torch.randn((n, d, h, w, 64), device="cuda").bfloat16()
+        g = torch.randn((n, d, h, w, 64), device="cuda").bfloat16()
+        dbg = torch.zeros(160 * 8, dtype=torch.int64, device="cuda")
+        lib.call("hpvg_debug_set_clock_buffer", dbg.data_ptr())
+        try:
+            for mode in (0, 1, 2):
+                prev = lib.set_wgrad_mode(mode)
+                try:
+                    for _ in range(2):
+                        dbg.zero_()
+                        ops.wgrad_raw(x, g, 1, (64, 64, 3, 3, 3))
+                        torch.cuda.synchronize()
+                finally:
+                    lib.set_wgrad_mode(prev)
+                rows = dbg.view(160, 8)[:, :4].float().cpu()
+                rows = rows[rows[:, 0] > 0]
+                print("mode %d: %d CTAs, mean cycles [mma loop, wait tma, wait acc, drain] = %s" % (
+                    mode, rows.shape[0], [int(v) for v in rows.mean(0).tolist()]), flush=True)
+        finally:
+            lib.call("hpvg_debug_set_clock_buffer", None)
     print("ALL OK" if ok else "FAILED")
     return 0 if ok else 1
 

@@ -354,7 +354,9 @@ wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   } else {
     // drain: TMEM [lane = half*64 + ci][pr*192 + kd*64 + co] -> partial[split][kd*9 + kh*3 + kw][ci][co], kw = 2*pr + half
     const bool any = b_begin < b_end;
+    const long long t_d0 = clock64();
     mbar_wait(bar_acc, 0);
+    const long long t_d1 = clock64();
     tc_fence_after();
     const int q = warp & 3;
     const int m = q * 32 + lane;
@@ -393,6 +395,11 @@ wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           __syncwarp();     // the next tile reuses the staging area
         }
       }
+    }
+    if (p.dbg && threadIdx.x == 64) {      // per-CTA phase clocks of the drain warps (development aid)
+      const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      p.dbg[cta * 8 + 2] = t_d1 - t_d0;          // waiting for the accumulators
+      p.dbg[cta * 8 + 3] = clock64() - t_d1;     // drain (TMEM -> staging -> global partial)
     }
   }
   tc_fence_before();
