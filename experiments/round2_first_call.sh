@@ -12,6 +12,12 @@ timeout 90 python experiments/check_wgrad_stack.py > ${O}_wgrad_stack.txt 2>&1; 
 # 3. bench lines: default, maximum shared-memory carve-out, stacked weight gradient (only meaningful if step 2 said ALL OK)
 timeout 200 python bench.py > ${O}_bench_default.json 2> ${O}_bench_default.err
 HPVG_CARVEOUT=1 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_carveout.json 2> ${O}_bench_carveout.err
+# critic / encoder weight gradients on the side stream (hpvg.ops.deferred_weight): parity tests first, then the bench line
+HPVG_CRITIC_WSIDE=1 timeout 150 python -m pytest tests/test_gpu_modules.py tests/test_gpu_training.py -m gpu -q > ${O}_tests_critic_wside.txt 2>&1
+tail -2 ${O}_tests_critic_wside.txt
+if tail -1 ${O}_tests_critic_wside.txt | grep -q "passed" && ! tail -1 ${O}_tests_critic_wside.txt | grep -q "failed"; then
+  HPVG_CRITIC_WSIDE=1 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_critic_wside.json 2> ${O}_bench_critic_wside.err
+fi
 if grep -q "ALL OK" ${O}_wgrad_stack.txt; then
   HPVG_WGRAD_STACK=2 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_wgrad_staged.json 2> ${O}_bench_wgrad_staged.err
   HPVG_WGRAD_STACK=1 timeout 200 python bench.py --no-cpu-baseline > ${O}_bench_wgrad_stack.json 2> ${O}_bench_wgrad_stack.err

@@ -109,8 +109,9 @@ class ConvBlockSN(nn.Sequential):
         """`weight`: W / sigma computed by the caller for all layers of the network at once (ops.spectral_weights);
         in_link / out_link: ops.ChainLink handshakes with the neighbouring blocks of a chain (_run_sn_chain)"""
         w = self.weight() if weight is None else weight
+        w, token = ops.deferred_weight(w)        # (w, None) unless HPVG_CRITIC_WSIDE=1: weight gradient on the side stream
         return ops.conv(x, w, self.conv.bias, self.pad, out_wide, LRELU_SLOPE if self.has_act else None, in_link=in_link,
-                        out_link=out_link if self.has_act else None)
+                        out_link=out_link if self.has_act else None, token=token)
 
     def forward(self, x):
         _check_device(x)

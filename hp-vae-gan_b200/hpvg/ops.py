@@ -351,10 +351,10 @@ class ConvFwd(Function):
     in_link: x is the LeakyReLU output of the block owning that ChainLink; out_link: this block's own link."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, pad, out_wide, act_slope, stats, in_link=None, out_link=None):
+    def forward(ctx, x, w, bias, pad, out_wide, act_slope, stats, in_link=None, out_link=None, token=None):
         y = conv_raw(x, w, bias, pad, False, out_wide, act_slope=act_slope, stats=stats)
         ctx.pad, ctx.act_slope, ctx.has_bias = pad, act_slope, bias is not None
-        ctx.in_link, ctx.out_link = in_link, out_link
+        ctx.in_link, ctx.out_link, ctx.token = in_link, out_link, token
         ctx.save_for_backward(x, w, y if act_slope is not None else None)
         return y
 
@@ -394,10 +394,14 @@ class ConvFwd(Function):
                 gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
         if not _input_only():
             if ctx.needs_input_grad[1]:
-                gw = ConvWgrad.apply(x, gz, ctx.pad, tuple(w.shape))
+                if ctx.token is not None and plain:
+                    ctx.token.slot = (x, gz, ctx.pad)            # WeightProxy.backward computes it on the side stream
+                    gw = torch.empty(tuple(w.shape), dtype=torch.float32, device=w.device)
+                else:
+                    gw = ConvWgrad.apply(x, gz, ctx.pad, tuple(w.shape))
             if want_gb and gb is None:
                 gb = ChannelSum.apply(gz)
-        return gx, gw, gb, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
 class ConvDgrad(Function):
@@ -500,8 +504,8 @@ class ChannelSum(Function):
         return g.view(1, -1, 1, 1, 1).expand(ctx.shape).contiguous()
 
 
-def conv(x, w, bias, pad, out_wide, act_slope=None, stats=None, in_link=None, out_link=None):
-    return ConvFwd.apply(x, w, bias, pad, out_wide, act_slope, stats, in_link, out_link)
+def conv(x, w, bias, pad, out_wide, act_slope=None, stats=None, in_link=None, out_link=None, token=None):
+    return ConvFwd.apply(x, w, bias, pad, out_wide, act_slope, stats, in_link, out_link, token)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -602,13 +606,42 @@ class WeightProxy(Function):
     def backward(ctx, placeholder):
         job, ctx.token.slot = ctx.token.slot, None
         if job is None:
-            return None, None
+            return placeholder, None      # nothing deposited (the consumer computed the gradient itself): plain identity
         x, gy, pad = job
         side = torch.cuda.current_stream()
         x.record_stream(side)
         gy.record_stream(side)
         gw, _ = wgrad_raw(x, gy, pad, ctx.wshape)
         return gw, None
+
+
+# EXPERIMENTAL, off by default (HPVG_CRITIC_WSIDE=1; written after round 1's GPU budget was spent, not yet run): the same
+# deferral for the spectral-norm blocks (critic, encoder features).  Their weight gradients sit between the data-gradient
+# launches of the backward sweep without feeding them: ~10 wgrad_tc launches of the critic's real / fake passes per iteration.
+# Not used inside calc_gradient_penalty's critic pass (no_wgrad_proxy): there a weight is referenced by its ConvFwd node AND
+# by the ConvDgrad node of the create_graph sweep, and the proxy's placeholder gradient must not meet a real one.
+_CRITIC_WSIDE = [os.environ.get('HPVG_CRITIC_WSIDE', '0') == '1']
+_NO_PROXY = [False]
+
+
+class no_wgrad_proxy:
+    def __enter__(self):
+        self.prev = _NO_PROXY[0]
+        _NO_PROXY[0] = True
+
+    def __exit__(self, *a):
+        _NO_PROXY[0] = self.prev
+
+
+def deferred_weight(w):
+    """-> (w', token): w' = w behind a WeightProxy created under the side stream, or (w, None) when the deferral does not apply"""
+    side = _WGRAD_STREAM[0]
+    if not _CRITIC_WSIDE[0] or _NO_PROXY[0] or side is None or not torch.is_grad_enabled() or not w.requires_grad:
+        return w, None
+    token = _Deferred()
+    with torch.cuda.stream(side):
+        w = WeightProxy.apply(w, token)
+    return w, token
 
 
 class ConvBnLrelu(Function):
