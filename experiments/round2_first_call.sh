@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: everything that was written after round 1's GPU budget ran out, measured in one go.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash experiments/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash experiments/round2_first_call.sh'
 # Results land in gpurun_out/r02a_*.  Every step runs under its own timeout; a failing step does not stop the others.
 set -u
 mkdir -p gpurun_out
