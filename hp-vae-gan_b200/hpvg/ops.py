@@ -378,7 +378,7 @@ class ConvFwd(Function):
                 link = _MaskLink(y, ctx.act_slope) if (_FUSE_MASK[0] and not plain and _input_only() and is_wide(x)) else None
                 gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, False, link)
                 if ctx.needs_input_grad[0]:
-                    gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x), link)
+                    gx = ConvFwd._dgrad_node(ctx, gz, w, is_wide(x), link, plain)
         else:
             gz = gy.contiguous()
         if ctx.needs_input_grad[0] and gx is None:
@@ -391,7 +391,7 @@ class ConvFwd(Function):
                 in_link.premasked = True
                 in_link.gb = stats[:x.shape[-1]] if stats is not None else None
             else:
-                gx = ConvDgrad.apply(gz, w, ctx.pad, is_wide(x))
+                gx = ConvFwd._dgrad_node(ctx, gz, w, is_wide(x), None, plain)
         if not _input_only():
             if ctx.needs_input_grad[1]:
                 if ctx.token is not None and plain:
@@ -404,13 +404,24 @@ class ConvFwd(Function):
         return gx, gw, gb, None, None, None, None, None, None, None
 
 
+    @staticmethod
+    def _dgrad_node(ctx, gz, w, out_wide, link, plain):
+        """the differentiable data-gradient node.  With a deferred weight (ctx.token) and a differentiated sweep (not plain:
+        the gradient penalty's create_graph pass) the node gets its OWN proxy of the weight in front of this block's proxy: a
+        proxy must have exactly one consumer, because what reaches it is a placeholder, not a gradient."""
+        token = None
+        if ctx.token is not None and not plain:
+            w, token = deferred_weight(ctx.token.base)
+        return ConvDgrad.apply(gz, w, ctx.pad, out_wide, link, token)
+
+
 class ConvDgrad(Function):
     """gx = data gradient of conv(x, w) w.r.t. x given gz (a forward-type conv with flipped/transposed weights)."""
 
     @staticmethod
-    def forward(ctx, gz, w, pad, out_wide, link=None):
+    def forward(ctx, gz, w, pad, out_wide, link=None, token=None):
         gx = conv_raw(gz, w, None, 2 - pad, True, out_wide)
-        ctx.pad, ctx.link = pad, link
+        ctx.pad, ctx.link, ctx.token = pad, link, token
         ctx.save_for_backward(gz, w)
         return gx
 
@@ -428,8 +439,12 @@ class ConvDgrad(Function):
             else:
                 g_gz = ConvFwd.apply(ggx, w, None, ctx.pad, is_wide(gz), None, None)
         if ctx.needs_input_grad[1] and not _input_only():
-            g_w = ConvWgrad.apply(ggx, gz, ctx.pad, tuple(w.shape))
-        return g_gz, g_w, None, None, None
+            if ctx.token is not None and not torch.is_grad_enabled():
+                ctx.token.slot = (ggx, gz, ctx.pad)              # WeightProxy.backward computes it on the side stream
+                g_w = torch.empty(tuple(w.shape), dtype=torch.float32, device=w.device)
+            else:
+                g_w = ConvWgrad.apply(ggx, gz, ctx.pad, tuple(w.shape))
+        return g_gz, g_w, None, None, None, None
 
 
 class ConvWgrad(Function):
@@ -588,10 +603,11 @@ class wgrad_stream:
 
 
 class _Deferred:
-    __slots__ = ("slot",)
+    __slots__ = ("slot", "base")
 
-    def __init__(self):
+    def __init__(self, base=None):
         self.slot = None
+        self.base = base       # the weight in front of the proxy (for nodes that must not share this proxy: see ConvFwd.backward)
 
 
 class WeightProxy(Function):
@@ -618,8 +634,9 @@ class WeightProxy(Function):
 # EXPERIMENTAL, off by default (HPVG_CRITIC_WSIDE=1; written after round 1's GPU budget was spent, not yet run): the same
 # deferral for the spectral-norm blocks (critic, encoder features).  Their weight gradients sit between the data-gradient
 # launches of the backward sweep without feeding them: ~10 wgrad_tc launches of the critic's real / fake passes per iteration.
-# Not used inside calc_gradient_penalty's critic pass (no_wgrad_proxy): there a weight is referenced by its ConvFwd node AND
-# by the ConvDgrad node of the create_graph sweep, and the proxy's placeholder gradient must not meet a real one.
+# In calc_gradient_penalty's critic pass a weight is referenced by its ConvFwd node AND by the ConvDgrad node that the
+# create_graph sweep creates; a proxy's placeholder gradient must not meet a real one, so that ConvDgrad node gets a proxy of
+# its own (ConvFwd._dgrad_node).  no_wgrad_proxy() switches the deferral off for a region.
 _CRITIC_WSIDE = [os.environ.get('HPVG_CRITIC_WSIDE', '0') == '1']
 _NO_PROXY = [False]
 
@@ -638,7 +655,7 @@ def deferred_weight(w):
     side = _WGRAD_STREAM[0]
     if not _CRITIC_WSIDE[0] or _NO_PROXY[0] or side is None or not torch.is_grad_enabled() or not w.requires_grad:
         return w, None
-    token = _Deferred()
+    token = _Deferred(w)
     with torch.cuda.stream(side):
         w = WeightProxy.apply(w, token)
     return w, token

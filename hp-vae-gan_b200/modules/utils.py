@@ -12,8 +12,7 @@ def calc_gradient_penalty(netD, real_data, fake_data, LAMBDA, device):
     fprop/dgrad/wgrad kernels by hpvg.ops."""
     alpha = _ops.gp_alpha(real_data.device)         # same CPU-generator draw as the reference (:5), as a device float
     interpolates = _ops.lerp(real_data, fake_data, alpha).requires_grad_(True)
-    with _ops.no_wgrad_proxy():                     # (only matters with HPVG_CRITIC_WSIDE=1, see hpvg.ops.deferred_weight)
-        disc_interpolates = netD(interpolates)
+    disc_interpolates = netD(interpolates)
     ones = torch.ones(disc_interpolates.size(), device=disc_interpolates.device)
     with _ops.input_grad_only():
         gradients = torch.autograd.grad(outputs=disc_interpolates, inputs=interpolates, grad_outputs=ones,

@@ -21,7 +21,10 @@ def cpu_kernels(monkeypatch):
         return F.conv3d(x, w, bias, padding=pad)
 
     def wgrad_raw(x, gy, pad, wshape, want_bias=False):
+        import inspect
         calls["wgrad"] += 1
+        caller = inspect.stack()[1]
+        calls["deferred"] = calls.get("deferred", 0) + (caller.function == "backward")     # WeightProxy.backward vs ConvWgrad.forward
         return torch.nn.grad.conv3d_weight(x, wshape, gy, padding=pad), None
 
     monkeypatch.setattr(ops, "conv_raw", conv_raw)
@@ -91,3 +94,44 @@ def test_proxy_without_a_deposit_is_an_identity(cpu_kernels, monkeypatch):
     # create_graph=True: ConvFwd.backward is not `plain`, takes the differentiable ConvWgrad path and deposits nothing
     got = torch.autograd.grad(y, (w,), gy, create_graph=True)[0]
     torch.testing.assert_close(got, _reference(x, w, b, gy)[1], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+def test_gradient_penalty_like_double_backward(cpu_kernels, monkeypatch, deferred):
+    """calc_gradient_penalty's pattern (modules/utils.py:14-18): a create_graph sweep for d/d(input) only, then a backward of a
+    function of that gradient.  The weight is referenced by the ConvFwd node and by the sweep's ConvDgrad node: with deferred
+    weight gradients each gets its own proxy, and the weight gradient is the sum of both contributions, as in torch."""
+    from hpvg import ops
+    x, w, b, gy = _case(4)
+    ones = torch.ones_like(gy)
+
+    def run(conv):
+        for t in (x, w, b):
+            t.grad = None
+        y = conv()
+        ctx = ops.input_grad_only() if conv is not torch_conv else contextlib.nullcontext()
+        with ctx:
+            gx = torch.autograd.grad(y, x, ones, create_graph=True)[0]
+        ((gx ** 2).sum() + (y * gy).sum()).backward()
+        return x.grad.clone(), w.grad.clone(), b.grad.clone()
+
+    def torch_conv():
+        return F.conv3d(x, w, b, padding=1)
+
+    ref = run(torch_conv)
+    monkeypatch.setattr(ops, "_CRITIC_WSIDE", [deferred])
+    monkeypatch.setattr(ops, "_WGRAD_STREAM", [object() if deferred else None])
+    tokens = []
+
+    def hpvg_conv():
+        w_use, token = ops.deferred_weight(w)
+        tokens.append(token)
+        return ops.conv(x, w_use, b, 1, False, token=token)
+
+    cpu_kernels["wgrad"] = cpu_kernels["deferred"] = 0
+    got = run(hpvg_conv)
+    for a, r in zip(got, ref):
+        torch.testing.assert_close(a, r, rtol=1e-10, atol=1e-12)
+    assert cpu_kernels["wgrad"] == 2                  # the ConvFwd node's and the ConvDgrad node's contribution
+    assert cpu_kernels["deferred"] == (2 if deferred else 0)      # both computed by a WeightProxy, or both by ConvWgrad nodes
+    assert (tokens[0] is not None) == deferred
