@@ -80,9 +80,11 @@ static std::atomic<int> g_wgrad_mode{-1};
 int wgrad_mode() {
   int v = g_wgrad_mode.load(std::memory_order_relaxed);
   if (v < 0) {
-    const char* e = getenv("HPVG_WGRAD_STACK");      // 1 = kd-stacked kernel, 2 = measured kernel with the staged drain
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
+    // 1 = kd-stacked kernel (default: measured on B200 29.7 vs 37.9 us per 64 -> 64 call at 16 x 64 x 64, kernel + reduction),
+    // 0 = one kd per CTA, 2 = one kd per CTA with the staged drain
+    const char* e = getenv("HPVG_WGRAD_STACK");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
     g_wgrad_mode.store(v, std::memory_order_relaxed);
   }
   return v;

@@ -22,6 +22,12 @@ bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+bool conv_bn_fused_supported(const ConvGeom& g);
+int conv_bn_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, const ConvGeom& g, float slope,
+                  const float* gamma, const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,
+                  float eps, float* stats, unsigned* grid_counter, float* scale_shift, float* mean_invstd, uint32_t* mask_bits,
+                  cudaStream_t st);
+
 static int make_geom(ConvGeom& g, int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, const char* who) {
   if (!(N > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0)) {
     set_error("%s: extents must be positive (N=%d Cin=%d Cout=%d D=%d H=%d W=%d)", who, N, Cin, Cout, D, H, W);
@@ -98,6 +104,31 @@ int hpvg_conv_forward_ex(const void* x, int x_fmt, const float* w_f32, const voi
                  Cout);
   void* ph = prof_begin(HPVG_PROF_CONV_DIRECT, flops, st);
   int rc = conv_direct(x, x_fmt, w_f32, bias, y, y_fmt, g, transposed, act, lrelu_slope, stats, mask_src, st);
+  prof_end(ph, st);
+  return rc;
+}
+
+int hpvg_conv_bn_lrelu_fused_supported(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad) {
+  ConvGeom g;
+  if (make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_bn_lrelu_fused_supported")) return 0;
+  return (conv_backend() != HPVG_BACKEND_DIRECT && conv_bn_fused_supported(g)) ? 1 : 0;
+}
+
+int hpvg_conv_bn_lrelu_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, int N, int Cin, int Cout,
+                             int D, int H, int W, int KD, int pad, float slope, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                             float* stats, float* scale_shift, float* mean_invstd, void* mask_bits, void* stream) {
+  ConvGeom g;
+  if (int rc = make_geom(g, N, Cin, Cout, D, H, W, KD, pad, "conv_bn_lrelu_fused")) return rc;
+  HPVG_CHECK_ARG(x && w_packed && out && gamma && beta && stats && scale_shift && mean_invstd, "conv_bn_lrelu_fused: null tensor");
+  HPVG_CHECK_ARG(conv_bn_fused_supported(g), "conv_bn_lrelu_fused: layer not eligible (Cin=%d Cout=%d KD=%d, %d x %d x %d)", Cin, Cout,
+                 KD, g.Do, g.Ho, g.Wo);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const double flops = 2.0 * g.N * g.Do * g.Ho * g.Wo * (double)g.Cin * g.Cout * g.taps;
+  void* ph = prof_begin(HPVG_PROF_CONV_BN_FUSED, flops, st);
+  int rc = conv_bn_fused(x, w_packed, bias, y, out, g, slope, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+                         stats, reinterpret_cast<unsigned*>(stats + 2 * Cout), scale_shift, mean_invstd,
+                         reinterpret_cast<uint32_t*>(mask_bits), st);
   prof_end(ph, st);
   return rc;
 }

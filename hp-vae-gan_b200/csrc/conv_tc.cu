@@ -84,14 +84,29 @@ struct TcParams {
   const uint8_t* w_img;      // packed weight image (for the L2 prefetch; nullptr = off)
   unsigned w_img_bytes;
   long long* dbg;   // optional per-CTA phase clocks (development aid, hpvg_debug_set_clock_buffer)
+  // FUSE (conv + BatchNorm(train) + LeakyReLU in one launch, see the fused epilogue)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* nbt;
+  float momentum, eps;
+  long long count;            // voxels per channel: N * Do * Ho * Wo
+  float* scale_shift;         // [2*Cout] saved for the backward pass
+  float* mean_invstd;         // [2*Cout]
+  unsigned* grid_counter;     // zero-initialised arrival counter of the grid barrier
+  uint32_t* mask_bits;        // [voxel][Cout/32] LeakyReLU sign bits taken from the fp32 value (nullptr: not wanted)
+  int store_y;                // also store the conv output y (bf16) for the BatchNorm backward
 };
 
-template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK>
+template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK, bool FUSE>
 __global__ void __launch_bounds__((TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::THREADS), (TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>::MIN_CTAS))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_y, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
   using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
   static_assert(!STACK || KDT == 3, "kd stacking needs a 3-deep kernel");
+  static_assert(!FUSE || (STACK && NOUT == 64 && NGRP == 1 && KCHUNKS == 1), "the fused BatchNorm epilogue is built on the stacked 64 -> 64 form");
+  static_assert(!FUSE || NACC * 2 * STG_BYTES <= Cfg::NSLAB * SLAB_STRIDE, "fused epilogue stages its tiles in the dead slab area");
   // accumulator a lives at TMEM columns (NACC - 1 - a) * NOUT: descending slice order (see STACK)
   auto acc_col = [](int a) { return (uint32_t)((NACC - 1 - a) * NOUT); };
   constexpr int GACC = NACC / NGRP;            // accumulators per group
@@ -132,6 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     if (!Cfg::THIN) tma_prefetch_desc(&tmap_y);
+    if (FUSE) tma_prefetch_desc(&tmap_o);
   }
   if (threadIdx.x == 64 && p.w_img) {
     // Pull the whole packed weight image into L2, one slice per CTA.  The image of a frozen pyramid stage was last read an
@@ -435,6 +451,156 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
     __syncwarp();
+  } else if constexpr (FUSE) {
+    // ===================== fused epilogue: conv + BatchNorm(batch statistics) + LeakyReLU in ONE launch =====================
+    // reference: modules/networks_3d.py:48-56 (nn.Conv3d -> nn.BatchNorm3d in training mode -> nn.LeakyReLU(0.2)).
+    // The grid has exactly one unit per CTA and at most one CTA per SM (host-checked, cooperative launch), so the whole
+    // layer output sits in the TMEM of the resident CTAs when the MMAs are done.  Pass 1 reads the accumulators and reduces
+    // sum(y), sum(y^2) per channel FROM THE FP32 VALUES (warp-shuffle transpose reduction, one shared + one global atomic per
+    // channel and CTA); a grid-wide arrive / spin barrier makes the totals visible; pass 2 reads the accumulators again,
+    // normalises, applies the affine map and LeakyReLU in fp32 and stores the activated output, (optionally) the bf16 conv
+    // output the BatchNorm backward needs, and one sign bit per element: the LeakyReLU derivative the backward pass uses is
+    // then the fp32 one, not the sign of a bf16-rounded recomputation.
+    constexpr int CPT = 32;
+    const int q = warp & 3;
+    const int ch = (warp - Cfg::EPI_WARP0) >> 2;              // column half: channels ch*32 .. ch*32+31
+    const int m = q * 32 + lane;
+    const int et = threadIdx.x - 32 * Cfg::EPI_WARP0;
+    int nb, n, d0, h0, w0;
+    decode((long long)blockIdx.x, nb, n, d0, h0, w0);
+    const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
+    const bool row_ok = (oh < g.Ho) && (ow < g.Wo);
+    const int amax = min(NACC, g.Do - d0);
+    float* csum = reinterpret_cast<float*>(sgen + Cfg::OFF_B);      // [128] channel sums of this CTA, then [128] scale | shift
+    float* ss = csum + 128;
+    mbar_wait(bar_acc_full, 0);       // every MMA of the unit has completed: slabs and weight ring are dead from here on
+    tc_fence_after();
+    if (et < 128) csum[et] = 0.f;
+    float s1[CPT], s2[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) s1[j] = s2[j] = 0.f;
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + ch * CPT);
+#pragma unroll 1
+    for (int a = 0; a < amax; ++a) {
+      uint32_t r[CPT];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col(a) + ch * CPT, r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) {
+          const float4 bq = b4[j];
+          const float v0 = __uint_as_float(r[4 * j]) + bq.x, v1 = __uint_as_float(r[4 * j + 1]) + bq.y;
+          const float v2 = __uint_as_float(r[4 * j + 2]) + bq.z, v3 = __uint_as_float(r[4 * j + 3]) + bq.w;
+          s1[4 * j] += v0; s1[4 * j + 1] += v1; s1[4 * j + 2] += v2; s1[4 * j + 3] += v3;
+          s2[4 * j] = fmaf(v0, v0, s2[4 * j]); s2[4 * j + 1] = fmaf(v1, v1, s2[4 * j + 1]);
+          s2[4 * j + 2] = fmaf(v2, v2, s2[4 * j + 2]); s2[4 * j + 3] = fmaf(v3, v3, s2[4 * j + 3]);
+        }
+      }
+    }
+    // transpose reduction: 32 lanes x 32 columns -> lane l holds the sum of column l over the warp's 32 rows (31 shuffles per array)
+#pragma unroll
+    for (int wd = 16; wd >= 1; wd >>= 1) {
+      const bool upper = (lane & wd) != 0;
+#pragma unroll
+      for (int j = 0; j < wd; ++j) {
+        const float send1 = upper ? s1[j] : s1[j + wd], keep1 = upper ? s1[j + wd] : s1[j];
+        const float send2 = upper ? s2[j] : s2[j + wd], keep2 = upper ? s2[j + wd] : s2[j];
+        s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, wd);
+        s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, wd);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");      // csum zeroed
+    atomicAdd(csum + ch * CPT + lane, s1[0]);
+    atomicAdd(csum + 64 + ch * CPT + lane, s2[0]);
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+    if (et < 128) {
+      atomicAdd(p.stats + et, csum[et]);           // stats = [sum y : 64][sum y^2 : 64]
+      __threadfence();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+    if (et == 0) {
+      // grid barrier (all CTAs are co-resident): arrive, then spin until everyone has.  Bounded like mbar_wait.
+      __threadfence();
+      atomicAdd(p.grid_counter, 1u);
+      unsigned seen;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.grid_counter) : "memory");
+        if (seen < gridDim.x && clock64() - t0 > 2000000000LL) {
+          printf("hpvg: fused BatchNorm grid barrier timed out (block %d saw %u of %u)\n", blockIdx.x, seen, gridDim.x);
+          __trap();
+        }
+      } while (seen < gridDim.x);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+    if (et < 64) {
+      const int c = et;
+      const double inv = 1.0 / (double)p.count;
+      const double mean = (double)__ldcg(p.stats + c) * inv;
+      double var = (double)__ldcg(p.stats + 64 + c) * inv - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      const float sc = p.gamma[c] * invstd;
+      const float sh = p.beta[c] - (float)mean * sc;
+      ss[c] = sc;
+      ss[64 + c] = sh;
+      if (blockIdx.x == 0) {
+        p.scale_shift[c] = sc;
+        p.scale_shift[64 + c] = sh;
+        p.mean_invstd[c] = (float)mean;
+        p.mean_invstd[64 + c] = invstd;
+        if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+        if (p.running_var) {
+          const double unbiased = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
+          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+        }
+        if (c == 0 && p.nbt) p.nbt[0] += 1;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+    // pass 2: normalise + LeakyReLU from the fp32 accumulators; every accumulator has its own staging tiles in the dead slab area
+#pragma unroll 1
+    for (int a = 0; a < amax; ++a) {
+      const int od = d0 + a;
+      uint32_t r[CPT];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col(a) + ch * CPT, r);
+      tmem_ld_wait();
+      const uint32_t sy = s_slab + (uint32_t)(2 * a) * STG_BYTES + m * 128;
+      const uint32_t so = sy + STG_BYTES;
+      const uint32_t sphase = (sy >> 7) & 7u;      // tiles are 16 KB apart: same swizzle phase for both
+      uint32_t mbits = 0;
+#pragma unroll
+      for (int c = 0; c < CPT / 8; ++c) {
+        float v[8], o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = ch * CPT + 8 * c + e;
+          v[e] = __uint_as_float(r[8 * c + e]) + bias_s[col];
+          const float z = fmaf(v[e], ss[col], ss[64 + col]);
+          const bool pos = z > 0.f;
+          mbits |= (pos ? 1u : 0u) << (8 * c + e);
+          o[e] = pos ? z : z * p.slope;
+        }
+        const uint32_t chunk = ((uint32_t)((ch * (CPT / 8) + c) ^ sphase) << 4);
+        if (p.store_y)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sy + chunk), "r"(pack_bf16x2(v[0], v[1])),
+                       "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                       : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + chunk), "r"(pack_bf16x2(o[0], o[1])),
+                     "r"(pack_bf16x2(o[2], o[3])), "r"(pack_bf16x2(o[4], o[5])), "r"(pack_bf16x2(o[6], o[7]))
+                     : "memory");
+      }
+      if (p.mask_bits && row_ok)
+        p.mask_bits[((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 2 + ch] = mbits;
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
+      if (et == 0) {
+        if (p.store_y) tma_store_5d(&tmap_y, s_slab + (uint32_t)(2 * a) * STG_BYTES, 0, w0, h0, od, n);
+        tma_store_5d(&tmap_o, s_slab + (uint32_t)(2 * a + 1) * STG_BYTES, 0, w0, h0, od, n);
+        tma_store_commit();
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
   } else if (!Cfg::THIN) {
     // ===================== epilogue, wide output: NEPI warps, TMEM lane quadrant = warp & 3, CPT columns per thread ==========
     // Measured (bench_kernels.py clk): of the ~6.5 k cycles after the last MMA about half is this chain and half the
@@ -625,7 +791,7 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -640,9 +806,118 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   p.nblocks = NOUT == 64 ? g.Cout / 64 : 1;
   p.num_units = (long long)p.nblocks * g.N * p.units_d * p.units_h * p.units_w;
   const int grid = (int)min((long long)num_sms(), p.num_units);
-  launch_k(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, mx, mw, my, p);
+  launch_k(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK, false>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, mx, mw, my, my, p);
   HPVG_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv + BatchNorm(train) + LeakyReLU in one launch (FUSE epilogue).  One unit per CTA, one CTA per SM, the whole grid
+// co-resident (cooperative launch): eligible when the layer's units fit the SMs.
+// ---------------------------------------------------------------------------------------------------------------
+static int fused_nacc(const ConvGeom& g) {
+  if (g.KD != 3 || g.Cin != 64 || g.Cout != 64 || g.pad_d != g.pad) return 0;
+  const long long per_slice = (long long)g.N * cdiv(g.Ho, BH) * cdiv(g.Wo, BW);
+  const long long sms = num_sms();
+  // 2-slice units put twice as many SMs to work on the small pyramid levels; 4-slice units have the better MMA shapes
+  if (g.Do % 2 == 0 && per_slice * (g.Do / 2) <= sms) return 2;
+  if (per_slice * cdiv(g.Do, 4) <= sms) return 4;
+  return 0;
+}
+
+bool conv_bn_fused_supported(const ConvGeom& g) { return fused_nacc(g) != 0; }
+
+template <int NACC>
+static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mo, TcParams& p,
+                        cudaStream_t st) {
+  using Cfg = TcCfg<1, NACC, 1, 64, true>;
+  auto kernel = conv_tc_kernel<1, NACC, 3, 1, 64, true, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_bn_fused: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_done = true;
+  }
+  const ConvGeom& g = p.g;
+  p.units_d = (int)cdiv(g.Do, NACC);
+  p.units_h = (int)cdiv(g.Ho, BH);
+  p.units_w = (int)cdiv(g.Wo, BW);
+  p.nblocks = 1;
+  p.num_units = (long long)g.N * p.units_d * p.units_h * p.units_w;
+  if (p.num_units > num_sms()) {
+    set_error("conv_bn_fused: %lld units do not fit %d SMs", p.num_units, num_sms());
+    return -1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.num_units);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of the whole grid is guaranteed by the driver (or the launch fails)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  static const bool coop = !(getenv("HPVG_FUSED_COOP") && atoi(getenv("HPVG_FUSED_COOP")) == 0);
+  cfg.numAttrs = coop ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, mx, mw, my, mo, p);
+  HPVG_CHECK_LAUNCH("conv_tc_kernel<fused BatchNorm>");
+  return 0;
+}
+
+int conv_bn_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, const ConvGeom& g, float slope,
+                  const float* gamma, const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,
+                  float eps, float* stats, unsigned* grid_counter, float* scale_shift, float* mean_invstd, uint32_t* mask_bits,
+                  cudaStream_t st) {
+  const int nacc = fused_nacc(g);
+  if (nacc == 0) {
+    set_error("conv_bn_fused: layer not eligible (Cin=%d Cout=%d KD=%d %dx%dx%d)", g.Cin, g.Cout, g.KD, g.Do, g.Ho, g.Wo);
+    return -1;
+  }
+  CUtensorMap mx, mw, my, mo;
+  {
+    uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.Di, (uint64_t)g.N};
+    uint32_t box[5] = {64, SLAB_W, SLAB_H, 1, 1};
+    if (int rc = make_tmap_bf16(&mx, x, 5, dims, box)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)g.Cin, (uint64_t)g.taps * g.Cout};
+    uint32_t box[2] = {64, 64};
+    if (int rc = make_tmap_bf16(&mw, w_packed, 2, dims, box)) return rc;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)g.Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)g.N};
+    uint32_t box[5] = {64, BW, BH, 1, 1};
+    if (int rc = make_tmap_bf16(&mo, out, 5, dims, box)) return rc;
+    if (y) {
+      if (int rc = make_tmap_bf16(&my, y, 5, dims, box)) return rc;
+    } else {
+      my = mo;
+    }
+  }
+  TcParams p = {};
+  p.g = g;
+  p.act = HPVG_ACT_NONE;
+  p.slope = slope;
+  p.bias = bias;
+  p.stats = stats;
+  p.mask_src = nullptr;
+  p.y_thin = nullptr;
+  p.dbg = nullptr;
+  p.w_img = reinterpret_cast<const uint8_t*>(w_packed);
+  p.w_img_bytes = (unsigned)((size_t)g.taps * g.Cout * g.Cin * 2);
+  p.gamma = gamma; p.beta = beta;
+  p.running_mean = running_mean; p.running_var = running_var; p.nbt = nbt;
+  p.momentum = momentum; p.eps = eps;
+  p.count = (long long)g.N * g.Do * g.Ho * g.Wo;
+  p.scale_shift = scale_shift; p.mean_invstd = mean_invstd;
+  p.grid_counter = grid_counter;
+  p.mask_bits = mask_bits;
+  p.store_y = y != nullptr;
+  if (nacc == 2) return launch_fused<2>(mx, mw, my, mo, p, st);
+  return launch_fused<4>(mx, mw, my, mo, p, st);
 }
 
 // wide -> wide (Cout multiple of 64) or wide -> thin (Cout <= 16, packed weights zero-padded to 16 rows per tap)
@@ -704,7 +979,7 @@ int conv_tc(const void* x, const void* w_packed, const float* bias, void* y, int
   } else {
     my = mx;
   }
-  TcParams p;
+  TcParams p = {};
   p.g = g;
   p.act = act;
   p.slope = slope;

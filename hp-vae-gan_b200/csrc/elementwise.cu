@@ -138,7 +138,8 @@ __device__ __forceinline__ void block_channel_sum(const float (&acc)[8], int c0,
 __global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gout,
                                                                   const float* __restrict__ scale_shift,
                                                                   const float* __restrict__ mean_invstd, float* __restrict__ sums,
-                                                                  long long nvox, int C, float slope) {
+                                                                  long long nvox, int C, float slope,
+                                                                  const uint8_t* __restrict__ mask) {
   pdl_enter();
   extern __shared__ float sm[];  // [4*C] params, then [rows][2*C] partials
   float* prm = sm;
@@ -158,6 +159,8 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* _
     for (long long r = (long long)blockIdx.x * rows + rl; r < nvox; r += (long long)gridDim.x * rows) {
       const uint4 yv = __ldg(y + r * cvec + cg);
       const uint4 gv = __ldg(gout + r * cvec + cg);
+      // mask (fused forward): bit b of byte [voxel][channel / 8] = the fp32 pre-activation of channel 8*(c/8) + b was positive
+      const uint32_t mb = mask ? (uint32_t)__ldg(mask + r * cvec + cg) : 0u;
       const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_reduce_kernel(const uint4* _
         for (int e = 0; e < 2; ++e) {
           const int c = c0 + 2 * k + e;
           const float z = fmaf(ye[e], prm[c], prm[C + c]);
-          const float dz = z > 0.f ? ge[e] : ge[e] * slope;
+          const bool pos = mask ? ((mb >> (2 * k + e)) & 1u) != 0u : z > 0.f;
+          const float dz = pos ? ge[e] : ge[e] * slope;
           const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
           s0[2 * k + e] += dz;
           s1[2 * k + e] = fmaf(dz, xh, s1[2 * k + e]);
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
                                                                  const float* __restrict__ mean_invstd, const float* __restrict__ sums,
                                                                  uint4* __restrict__ gy, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, long long nvox, int C, float slope,
-                                                                 float* __restrict__ chsum) {
+                                                                 float* __restrict__ chsum, const uint8_t* __restrict__ mask) {
   pdl_enter();
   extern __shared__ float prm[];  // scale, shift, mean, invstd, m0 = sum dz / M, m1 = sum dz*xhat / M, [C] reduction scratch
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cvec) << 3;
     const uint4 yv = __ldg(y + i), gv = __ldg(gout + i);
+    const uint32_t mb = mask ? (uint32_t)__ldg(mask + i) : 0u;
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
     uint32_t ow[4];
 #pragma unroll
@@ -230,7 +235,8 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
       for (int e = 0; e < 2; ++e) {
         const int c = c0 + 2 * k + e;
         const float z = fmaf(ye[e], prm[c], prm[C + c]);
-        const float dz = z > 0.f ? ge[e] : ge[e] * slope;
+        const bool pos = mask ? ((mb >> (2 * k + e)) & 1u) != 0u : z > 0.f;
+        const float dz = pos ? ge[e] : ge[e] * slope;
         const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
         res[e] = prm[c] * (dz - prm[4 * C + c] - xh * prm[5 * C + c]);
       }
@@ -914,27 +920,30 @@ int hpvg_bn_apply_lrelu_per_sample(const void* y, const float* stats, const floa
 }
 
 int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
-                             long long nvox, int C, float slope, void* stream) {
+                             long long nvox, int C, float slope, const void* mask_bits, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 256, "bn_lrelu_bwd_reduce: C=%d must be a multiple of 8 (<= 256)", C);
   MEMSET0(sums, 3 * C * sizeof(float), ST(stream), "bn_lrelu_bwd_reduce");   // [2C] sums + [C] bias-gradient accumulator
   const int rows = 256 / (C / 8);
   const size_t smem = (size_t)(4 * C + rows * 2 * C) * sizeof(float);
   const int blocks = (int)max(1LL, min(cdiv(nvox, rows), (long long)num_sms() * 4));
   launch_k(bn_lrelu_bwd_reduce_kernel, blocks, 256, smem, ST(stream), reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout),
-                                                                scale_shift, mean_invstd, sums, nvox, C, slope);
+                                                                scale_shift, mean_invstd, sums, nvox, C, slope,
+                                                                reinterpret_cast<const uint8_t*>(mask_bits));
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_reduce");
   return 0;
 }
 
 int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
-                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum, void* stream) {
+                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum,
+                            const void* mask_bits, void* stream) {
   HPVG_CHECK_ARG(C % 8 == 0 && C <= 256 && (256 % (C / 8)) == 0, "bn_lrelu_bwd_apply: C=%d must be a multiple of 8 dividing 2048", C);
   const long long nvec = nvox * (C / 8);
   // with the fused channel sum every block ends with C global atomics on the same C addresses: keep the grid at 2 CTAs per SM
   const int blocks = want_chsum ? min(ew_blocks(nvec, 256), 2 * num_sms()) : ew_blocks(nvec, 256);
   launch_k(bn_lrelu_bwd_apply_kernel, blocks, 256, 7 * C * sizeof(float), ST(stream), 
       reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift, mean_invstd, sums,
-      reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr);
+      reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr,
+      reinterpret_cast<const uint8_t*>(mask_bits));
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
   return 0;
 }

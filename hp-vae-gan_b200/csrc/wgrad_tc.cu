@@ -41,7 +41,7 @@ struct WgParams {
   long long* dbg;             // optional per-CTA phase clocks (development aid)
 };
 
-// STAGED (hpvg_set_wgrad_mode(2), unmeasured): the drain writes its partials through a swizzled shared-memory tile so that every
+// STAGED (hpvg_set_wgrad_mode(2); measured: drain 9.8 k -> 5.6 k cycles per CTA): the drain writes its partials through a swizzled shared-memory tile so that every
 // store instruction covers 512 contiguous bytes (see wgrad_tc_kdstack_kernel); <false> is the measured kernel, unchanged.
 template <bool STAGED>
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -222,8 +222,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// kd-stacked form (KD == 3 only; OFF by default: hpvg_set_wgrad_mode(1) / HPVG_WGRAD_STACK=1).  NOT YET RUN ON A GPU —
-// written at the end of round 1 after the GPU budget was spent; experiments/check_wgrad_stack.py is its parity check.
+// kd-stacked form (KD == 3 only; the default: hpvg_set_wgrad_mode(1)).  Measured on B200 (experiments/check_wgrad_stack.py,
+// profiles/r02a_wgrad_stack.txt): bit-for-bit the same partial sums as the one-kd-per-CTA kernel up to fp32 summation order
+// (1.4e-6 relative), 18.8 k instead of 29.8 k cycles of MMA issue per CTA, 29.7 instead of 37.9 us per call at 16 x 64 x 64.
 //
 // Measured cost model: an M = 128, K = 16 MMA with both operands in shared memory costs max(64, N/2)
 // cycles, so the N = 64 instructions above run the tensor pipe at half rate by construction (5 x 64 = 320 clk per
@@ -234,7 +235,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // One instruction serves the three kd taps of a (kh,kw) position.  A CTA owns one kh (blockIdx.z): taps kw = 0,1 share an
 // M = 128 instruction, kw = 2 takes a second one (upper half duplicated and ignored): 2 x 96 = 192 clk per k-step and
 // slab for the same 9 taps.  TMEM: 2 accumulators x 192 columns.  gy slices outside the volume are fetched as fully
-// out-of-bounds TMA boxes (zero fill, full byte count) — the first thing to confirm on the GPU.
+// out-of-bounds TMA boxes (zero fill, full byte count; confirmed on the GPU).
 // Partials keep the layout [split][tap][ci][co]; the reduction kernel is shared.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int WK_STAGE_BYTES = WG_SLAB_STRIDE + 3 * WG_GY_BYTES;   // 72704 (multiple of 1024)

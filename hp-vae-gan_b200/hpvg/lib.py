@@ -42,9 +42,14 @@ PROTOTYPES = {
     "hpvg_bn_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_longlong,
                                  c_void_p, c_void_p, c_int, c_void_p]),
     "hpvg_bn_apply_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
-    "hpvg_bn_lrelu_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "hpvg_bn_lrelu_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p,
+                                         c_void_p]),
     "hpvg_bn_lrelu_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_longlong, c_int, c_float, c_int, c_void_p]),
+                                        c_longlong, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "hpvg_conv_bn_lrelu_fused_supported": (c_int, [c_int] * 8),
+    "hpvg_conv_bn_lrelu_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hpvg_bn_finalize_apply_lrelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                              c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "hpvg_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_int, c_void_p, c_void_p]),

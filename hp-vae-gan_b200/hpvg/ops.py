@@ -20,23 +20,26 @@ from torch.autograd.function import once_differentiable
 from . import lib
 from .lib import ACT_LRELU, ACT_NONE, FMT_NCDHW_F32, FMT_NDHWC_BF16
 
-_tls = threading.local()
+_INPUT_ONLY = [False]
 
 
 class input_grad_only:
     """Context: conv backward passes inside it skip weight/bias gradients (used around the first-order
-    autograd.grad of the gradient penalty, which only asks for d/d(interpolates))."""
+    autograd.grad of the gradient penalty, which only asks for d/d(interpolates)).
+    A process-wide flag, not a thread-local: for CUDA tensors the backward of a Function runs on the autograd engine's
+    device thread, not on the thread that called torch.autograd.grad (which blocks until the sweep is done), so a
+    thread-local set by the caller is invisible exactly where it is read."""
 
     def __enter__(self):
-        self.prev = getattr(_tls, "input_only", False)
-        _tls.input_only = True
+        self.prev = _INPUT_ONLY[0]
+        _INPUT_ONLY[0] = True
 
     def __exit__(self, *a):
-        _tls.input_only = self.prev
+        _INPUT_ONLY[0] = self.prev
 
 
 def _input_only():
-    return getattr(_tls, "input_only", False)
+    return _INPUT_ONLY[0]
 
 
 def _stream():
@@ -377,7 +380,7 @@ class ConvFwd(Function):
             else:
                 link = _MaskLink(y, ctx.act_slope) if (_FUSE_MASK[0] and not plain and _input_only() and is_wide(x)) else None
                 gz = LReluBwd.apply(gy.contiguous(), y, ctx.act_slope, False, link)
-                if ctx.needs_input_grad[0]:
+                if link is not None and ctx.needs_input_grad[0]:
                     gx = ConvFwd._dgrad_node(ctx, gz, w, is_wide(x), link, plain)
         else:
             gz = gy.contiguous()
@@ -551,12 +554,12 @@ class BnLrelu(Function):
         c, nvox = ctx.c, ctx.nvox
         sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
-                 float(ctx.slope), _stream())
+                 float(ctx.slope), None, _stream())
         gy = torch.empty_like(y)
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
-                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), 0, _stream())
+                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), 0, None, _stream())
         return gy, None, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -631,13 +634,13 @@ class WeightProxy(Function):
         return gw, None
 
 
-# EXPERIMENTAL, off by default (HPVG_CRITIC_WSIDE=1; written after round 1's GPU budget was spent, not yet run): the same
+# On by default (HPVG_CRITIC_WSIDE=0 turns it off; measured on B200, config 2: 5.38 -> 5.22 ms per iteration): the same
 # deferral for the spectral-norm blocks (critic, encoder features).  Their weight gradients sit between the data-gradient
 # launches of the backward sweep without feeding them: ~10 wgrad_tc launches of the critic's real / fake passes per iteration.
 # In calc_gradient_penalty's critic pass a weight is referenced by its ConvFwd node AND by the ConvDgrad node that the
 # create_graph sweep creates; a proxy's placeholder gradient must not meet a real one, so that ConvDgrad node gets a proxy of
 # its own (ConvFwd._dgrad_node).  no_wgrad_proxy() switches the deferral off for a region.
-_CRITIC_WSIDE = [os.environ.get('HPVG_CRITIC_WSIDE', '0') == '1']
+_CRITIC_WSIDE = [os.environ.get('HPVG_CRITIC_WSIDE', '1') == '1']
 _NO_PROXY = [False]
 
 
@@ -661,6 +664,33 @@ def deferred_weight(w):
     return w, token
 
 
+# conv + BatchNorm + LeakyReLU in one launch (hpvg_conv_bn_lrelu_fused).  The kernel spins on a grid-wide barrier, so two of
+# them must never be partially resident at the same time: the training iteration serialises the generator's passes (they
+# share BatchNorm buffers), the multi-stream sampler switches the fusion off (fused_bn(False)).
+_FUSED_BN = [os.environ.get('HPVG_FUSED_BN', '1') != '0']
+
+
+class fused_bn:
+    """Context: allow / forbid the one-launch conv + BatchNorm + LeakyReLU kernel inside the block"""
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = _FUSED_BN[0]
+        _FUSED_BN[0] = self.on
+
+    def __exit__(self, *a):
+        _FUSED_BN[0] = self.prev
+
+
+def _fused_bn_ok(x, w, pad):
+    if not _FUSED_BN[0] or not is_wide(x) or w.dim() != 5 or w.shape[0] != 64 or w.shape[1] != 64:
+        return False
+    n, c, d, h, wd = dims_of(x)
+    return bool(lib.load().hpvg_conv_bn_lrelu_fused_supported(n, 64, 64, d, h, wd, 3, int(pad)))
+
+
 class ConvBnLrelu(Function):
     """ConvBlock3D/2D as ONE autograd node (reference modules/networks_3d.py:48-56).
     forward : conv (+bias) with BatchNorm sums fused into its epilogue -> finalize + normalise + affine + LeakyReLU (1 launch)
@@ -672,37 +702,59 @@ class ConvBnLrelu(Function):
         _require_cuda(x, w, gamma, beta)
         ctx.token = token
         cout = w.shape[0]
-        stats = zeros_small(2 * cout, x.device)
-        y = conv_raw(x, w, bias, pad, False, True, stats=stats)
-        n, c, d, h, wd = dims_of(y)
-        nvox = n * d * h * wd
-        scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
-        mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
-        out = torch.empty_like(y)
         track = _BN_TRACK[0]
-        lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean if track else None),
-                 _ptr(running_var if track else None), _ptr(nbt if track else None), float(momentum), float(eps), _ptr(scale_shift),
-                 _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
+        need_bwd = any(ctx.needs_input_grad[:5])       # all False when the caller runs under no_grad
+        mask = None
+        if _fused_bn_ok(x, w, pad):
+            # ONE launch: the convolution's accumulators stay in TMEM across a grid barrier on the channel sums; statistics,
+            # normalisation and the LeakyReLU sign all come from the fp32 values (hpvg_conv_bn_lrelu_fused)
+            x = x.contiguous()
+            n, cin, d, h, wd = dims_of(x)
+            kd = _kd_of(w)
+            packed = packed_for(w.contiguous(), cout, cin, kd * 9, False, cout)
+            do, ho, wo = d + 2 * pad - 2, h + 2 * pad - 2, wd + 2 * pad - 2
+            c, nvox = cout, n * do * ho * wo
+            stats = zeros_small(2 * cout + 32, x.device)        # sums + the grid barrier's arrival counter
+            out = _empty(n, cout, do, ho, wo, True, x.device)
+            y = torch.empty_like(out) if need_bwd else None
+            mask = torch.empty((nvox * (cout // 8),), dtype=torch.uint8, device=x.device) if need_bwd else None
+            scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=x.device)
+            mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=x.device)
+            lib.call("hpvg_conv_bn_lrelu_fused", _ptr(x), _ptr(packed), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
+                     _ptr(out), n, cin, cout, d, h, wd, kd, pad, float(slope), _ptr(gamma), _ptr(beta),
+                     _ptr(running_mean if track else None), _ptr(running_var if track else None), _ptr(nbt if track else None),
+                     float(momentum), float(eps), _ptr(stats), _ptr(scale_shift), _ptr(mean_invstd), _ptr(mask), _stream())
+        else:
+            stats = zeros_small(2 * cout, x.device)
+            y = conv_raw(x, w, bias, pad, False, True, stats=stats)
+            n, c, d, h, wd = dims_of(y)
+            nvox = n * d * h * wd
+            scale_shift = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+            mean_invstd = torch.empty((2 * c,), dtype=torch.float32, device=y.device)
+            out = torch.empty_like(y)
+            lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean if track else None),
+                     _ptr(running_var if track else None), _ptr(nbt if track else None), float(momentum), float(eps), _ptr(scale_shift),
+                     _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
         ctx.pad, ctx.slope, ctx.c, ctx.nvox, ctx.has_bias = pad, slope, c, nvox, bias is not None
-        ctx.save_for_backward(x, w, y, scale_shift, mean_invstd)
+        ctx.save_for_backward(x, w, y, scale_shift, mean_invstd, mask)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
-        x, w, y, scale_shift, mean_invstd = ctx.saved_tensors
+        x, w, y, scale_shift, mean_invstd, mask = ctx.saved_tensors
         gout = gout.contiguous()
         c, nvox = ctx.c, ctx.nvox
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
         fuse_gb = want_gb and _chsum_fusable(c)
         sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
-                 float(ctx.slope), _stream())
+                 float(ctx.slope), _ptr(mask), _stream())
         gy = torch.empty_like(y)
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
         lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
-                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _stream())
+                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _ptr(mask), _stream())
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = conv_raw(gy, w, None, 2 - ctx.pad, True, is_wide(x))

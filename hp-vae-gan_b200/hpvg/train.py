@@ -442,8 +442,10 @@ class Sampler:
             torch.cuda.synchronize()
 
     def _draw(self):
-        # BatchNorm sums of the forward: ~35 layers x batch x 128 floats (x 32-float granules), zeroed by one fill
-        with ops.bn_running_stats(self.track_bn), ops.bn_per_sample(self.per_sample_bn), ops.zero_arena(self.device, 48 * 160 * max(1, self.batch)):
+        # BatchNorm sums of the forward: ~35 layers x batch x 128 floats (x 32-float granules), zeroed by one fill.  The one-launch
+        # conv + BatchNorm kernel spins on a grid barrier: never with several draws in flight on different streams.
+        with ops.bn_running_stats(self.track_bn), ops.bn_per_sample(self.per_sample_bn), ops.fused_bn(self.nstreams == 1), \
+                ops.zero_arena(self.device, 48 * 160 * max(1, self.batch)):
             z = images.generate_noise(size=self.size, device=self.device)
             fake, _ = self.netG(z, self.opt.Noise_Amps, noise_init=z, mode="rand")
         return fake

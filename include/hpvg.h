@@ -52,6 +52,7 @@ long long hpvg_launch_count(void);
 #define HPVG_PROF_WGRAD_DIRECT 3
 #define HPVG_PROF_CONV_EXPAND 4
 #define HPVG_PROF_WGRAD_NARROW 5
+#define HPVG_PROF_CONV_BN_FUSED 6
 /* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
 int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
@@ -65,10 +66,10 @@ int hpvg_set_pdl(int on);
  * column-streaming kernel conv_col.cu (single-tile work units, no quantisation loss); 0 = brick kernel always; 1 = column
  * kernel whenever it supports the layer.  Initial value from HPVG_TC_COL.  Returns the previous mode. */
 int hpvg_set_conv_col_mode(int mode);
-/* Weight-gradient kernel of the 3-D wide layers: 0 = one kd tap plane per CTA, N = 64 MMAs (default, measured);
- * 1 = kd-stacked form, one N = 192 MMA per (kh,kw) position serves the three kd taps; 2 = the measured kernel with its fp32
- * partials written through a swizzled shared-memory tile (coalesced stores).  Modes 1 and 2 are EXPERIMENTAL: written after
- * round 1's GPU budget was spent, not yet run — experiments/check_wgrad_stack.py.  Initial value from HPVG_WGRAD_STACK.
+/* Weight-gradient kernel of the 3-D wide layers: 1 = kd-stacked form, one N = 192 MMA per (kh,kw) position serves the three
+ * kd taps (default; measured on B200: 29.7 vs 37.9 us per 64 -> 64 call at 16 x 64 x 64); 0 = one kd tap plane per CTA, N = 64
+ * MMAs; 2 = mode 0 with its fp32 partials written through a swizzled shared-memory tile (coalesced stores).  All three produce
+ * the same sums up to fp32 summation order (experiments/check_wgrad_stack.py).  Initial value from HPVG_WGRAD_STACK.
  * Returns the previous mode. */
 int hpvg_set_wgrad_mode(int mode);
 int hpvg_profile_dump(double* rows, int max_rows);
@@ -152,6 +153,17 @@ int hpvg_channel_sum(const void* t, int fmt, float* out, int N, int C, long long
  *   dz = gout * lrelu'(y*scale+shift).
  * bn_lrelu_bwd_apply: gy = scale * (dz - sums0/M - xhat*sums1/M) ; dgamma = sums1, dbeta = sums0 (written once); with
  *   want_chsum, sums[2C..3C) += per-channel sum of the stored gy = the bias gradient of the preceding convolution.
+ *   mask_bits (both backward kernels; may be NULL): uint8 [nvox][C/8] written by hpvg_conv_bn_lrelu_fused — bit b of byte
+ *   [v][c/8] says that the fp32 pre-activation of channel 8*(c/8)+b at voxel v was positive; when given, lrelu' is read from
+ *   it instead of from the sign of the recomputed y*scale+shift (y is stored in bf16, the forward saw fp32).
+ * hpvg_conv_bn_lrelu_fused: ConvBlock3D (modules/networks_3d.py:48-56) in ONE launch for 64 -> 64 3x3x3 layers whose work
+ *   units fit the SMs (hpvg_conv_bn_lrelu_fused_supported): the tcgen05 convolution keeps its accumulators in TMEM across a
+ *   grid-wide barrier on sum(y), sum(y^2) — taken from the fp32 accumulators — then normalises, applies the affine map and
+ *   LeakyReLU in fp32 and stores `out` (NDHWC_BF16), optionally `y` (the bf16 conv output the backward needs; NULL: not
+ *   stored) and `mask_bits` (NULL: not stored).  `stats` is float32 [2*Cout + 32], ZEROED by the caller: [0, 2*Cout) the sums,
+ *   element 2*Cout the grid barrier's arrival counter.  scale_shift / mean_invstd / running statistics as bn_finalize.
+ *   Launched cooperatively: never run two of these concurrently on one device from different streams unless both grids fit
+ *   the SMs together.
  * ------------------------------------------------------------------------------------------------------------- */
 int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, long long* num_batches_tracked, float momentum, float eps,
@@ -159,10 +171,15 @@ int hpvg_bn_finalize(const float* stats, const float* gamma, const float* beta, 
 int hpvg_bn_apply_lrelu(const void* y, const float* scale_shift, void* out, long long nvox, int C, float slope,
                         void* stream);
 int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
-                             float* sums, long long nvox, int C, float slope, void* stream);
+                             float* sums, long long nvox, int C, float slope, const void* mask_bits, void* stream);
 int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
                             float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
-                            float slope, int want_chsum, void* stream);
+                            float slope, int want_chsum, const void* mask_bits, void* stream);
+int hpvg_conv_bn_lrelu_fused_supported(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad);
+int hpvg_conv_bn_lrelu_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, int N, int Cin, int Cout,
+                             int D, int H, int W, int KD, int pad, float slope, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                             float* stats, float* scale_shift, float* mean_invstd, void* mask_bits, void* stream);
 /* inference-only BatchNorm(batch statistics of each sample) + LeakyReLU: y, out NDHWC_BF16 [N][nvox_per_sample][C],
  * stats [N][2C] from hpvg_conv_forward_ex(stats_per_sample = 1); no running statistics, nothing saved for a backward */
 int hpvg_bn_apply_lrelu_per_sample(const void* y, const float* stats, const float* gamma, const float* beta, float eps,

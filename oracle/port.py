@@ -119,12 +119,33 @@ def batch_norm_train(sd, prefix, y):
     return out
 
 
+FUSED_BN_SMS = [148]     # storage emulation: SM count of the device whose fused-layer rule is modelled (0: no fused layers)
+
+
+def fused_bn_layer(x, w, pad):
+    """storage emulation only: would the CUDA path run this ConvBlock as ONE launch (hpvg_conv_bn_lrelu_fused)?  Same rule as
+    conv_tc.cu::fused_nacc: 64 -> 64 3x3x3 layers whose 16 x 8-voxel bricks x (2 or 4)-slice units fit the SMs.  Such a layer
+    takes BatchNorm statistics, normalisation and the LeakyReLU sign from the fp32 accumulators; the bf16 copy of the conv
+    output exists only for the backward pass."""
+    if w.dim() != 5 or tuple(w.shape[:2]) != (64, 64) or x.dim() != 5 or FUSED_BN_SMS[0] <= 0:
+        return False
+    n, _, d, h, wd = x.shape
+    do, ho, wo = d + 2 * pad - 2, h + 2 * pad - 2, wd + 2 * pad - 2
+    per_slice = n * -(-ho // 16) * -(-wo // 8)
+    if do % 2 == 0 and per_slice * (do // 2) <= FUSED_BN_SMS[0]:
+        return True
+    return per_slice * -(-do // 4) <= FUSED_BN_SMS[0]
+
+
 def conv_block(sd, prefix, x, pad):
     """ConvBlock3D/2D: conv [+ BatchNorm] [+ LeakyReLU]; the mu/logvar heads have neither (networks_3d.py:48-56, :99-100)"""
     w = sd[prefix + 'conv.weight']
-    y = store(conv(head_operand(x, w), head_operand(mma_weight(w), w), sd[prefix + 'conv.bias'], pad))
+    y = conv(head_operand(x, w), head_operand(mma_weight(w), w), sd[prefix + 'conv.bias'], pad)
     if prefix + 'norm.weight' in sd:
+        y = store_grad(y) if (_STORAGE[-1] == 'bf16' and fused_bn_layer(x, w, pad)) else store(y)
         y = store(F.leaky_relu(batch_norm_train(sd, prefix + 'norm.', y), SLOPE))
+    else:
+        y = store(y)
     return y
 
 
