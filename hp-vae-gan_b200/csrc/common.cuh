@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/hpvg.h"
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL) && !defined(__CUDA_ARCH_FEAT_SM103_ALL)
@@ -50,6 +51,19 @@ static inline int num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+// cudaFuncSetAttribute applies to the CURRENT device: a process that drives several GPUs (nn.DataParallel's per-device
+// threads, train_video.py:91-94) must opt in to large dynamic shared memory once per device, not once per process
+static inline bool attr_pending(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (mask.load(std::memory_order_acquire) & (1ull << (dev & 63))) == 0;
+}
+static inline void attr_set(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
 }
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }

@@ -411,14 +411,14 @@ long long conv_col_brick_units(const ConvGeom& g) {
 int conv_col(const void* x, const void* w_packed, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
              const void* mask_src, cudaStream_t st) {
   using namespace col;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(conv_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_col: cannot opt in to %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
       return -2;
     }
-    attr_done = true;
+    attr_set(attr_mask);
   }
   CUtensorMap mx, mw, my;
   {

@@ -789,15 +789,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 template <int KCHUNKS, int NACC, int KDT, int NGRP, int NOUT, bool STACK = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<KCHUNKS, NACC, NGRP, NOUT, STACK>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return -2;
     }
-    attr_done = true;
+    attr_set(attr_mask);
   }
   const ConvGeom& g = p.g;
   p.units_d = (int)cdiv(g.Do, NACC);
@@ -832,14 +832,14 @@ static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
                         cudaStream_t st) {
   using Cfg = TcCfg<1, NACC, 1, 64, true>;
   auto kernel = conv_tc_kernel<1, NACC, 3, 1, 64, true, true>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_bn_fused: cannot opt in to %d bytes of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return -2;
     }
-    attr_done = true;
+    attr_set(attr_mask);
   }
   const ConvGeom& g = p.g;
   p.units_d = (int)cdiv(g.Do, NACC);

@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) frames_to_uint8_kernel(const float* __res
   pdl_enter();
   const long long total = (long long)T * H * W * 3;
   const size_t plane = (size_t)T * H * W;
+  video += (size_t)blockIdx.y * 3 * plane;      // blockIdx.y = video of a batch
+  out += (size_t)blockIdx.y * 3 * plane;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % 3);
     const long long vox = i / 3;
@@ -58,10 +60,14 @@ int hpvg_clip_from_frames(const uint8_t* frames, float* clip, int num_frames, in
 }
 
 int hpvg_frames_to_uint8(const float* video, uint8_t* out, int T, int H, int W, void* stream) {
-  HPVG_CHECK_ARG(video && out && T > 0 && H > 0 && W > 0, "frames_to_uint8: bad arguments");
+  return hpvg_frames_to_uint8_batched(video, out, 1, T, H, W, stream);
+}
+
+int hpvg_frames_to_uint8_batched(const float* video, uint8_t* out, int N, int T, int H, int W, void* stream) {
+  HPVG_CHECK_ARG(video && out && N > 0 && N <= 65535 && T > 0 && H > 0 && W > 0, "frames_to_uint8: bad arguments");
   const long long total = (long long)3 * T * H * W;
-  const int blocks = (int)max(1LL, min(cdiv(total, 256), (long long)num_sms() * 8));
-  launch_k(frames_to_uint8_kernel, blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), video, out, T, H, W);
+  const int blocks = (int)max(1LL, min(cdiv(total, 256), cdiv((long long)num_sms() * 8, N)));
+  launch_k(frames_to_uint8_kernel, dim3(blocks, N), 256, 0, reinterpret_cast<cudaStream_t>(stream), video, out, T, H, W);
   HPVG_CHECK_LAUNCH("frames_to_uint8");
   return 0;
 }

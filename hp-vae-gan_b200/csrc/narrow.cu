@@ -384,11 +384,11 @@ int expand_conv(const void* x, const float* w, const float* w_tco, const float* 
   static const bool no_mma = getenv("HPVG_EXPAND_FMA") != nullptr;     // development aid: force the CUDA-core kernel
   if (w_tco != nullptr && g.Cin <= 3 && !no_mma) {
     const size_t smem_mma = expand_mma_smem(g.KD);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_mask{0};
+    if (attr_pending(attr_mask)) {
       cudaFuncSetAttribute(expand_conv_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
       cudaFuncSetAttribute(expand_conv_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr_done = true;
+      attr_set(attr_mask);
     }
     if (g.KD == 3)
       launch_k(expand_conv_mma_kernel<3>, (unsigned)blocks, 256, smem_mma, st, reinterpret_cast<const float*>(x), w_tco, bias,
@@ -775,10 +775,10 @@ size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g) {
 
 template <int KDT, int NC>
 static void oc_launch(const OuterCorrParams& p, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
     cudaFuncSetAttribute(outer_corr_kernel<KDT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_done = true;
+    attr_set(attr_mask);
   }
   launch_k(outer_corr_kernel<KDT, NC>, grid, OC_THREADS, smem, st, p);
 }
@@ -825,11 +825,11 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
     }
     p.partial = reinterpret_cast<float*>(workspace);
     const size_t smem_mma = (size_t)OC_TH * OC_TW * 128 + ((size_t)p.J * g.KD * OC_HH * OC_HW + OC_ONES) * sizeof(float);
-    static bool attr_mma = false;
-    if (!attr_mma) {
+    static std::atomic<unsigned long long> attr_mma{0};
+    if (attr_pending(attr_mma)) {
       cudaFuncSetAttribute(outer_corr_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
       cudaFuncSetAttribute(outer_corr_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr_mma = true;
+      attr_set(attr_mma);
     }
     if (g.KD == 3)
       launch_k(outer_corr_mma_kernel<3>, grid, OM_THREADS, smem_mma, st, p);

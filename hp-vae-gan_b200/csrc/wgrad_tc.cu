@@ -510,8 +510,8 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
     uint32_t box[5] = {64, WG_BW, WG_BH, 1, 1};
     if (int rc = make_tmap_bf16(&mg, gy, 5, dims, box)) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e == cudaSuccess)
@@ -520,7 +520,7 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
       set_error("wgrad_tc: cannot opt in to %d bytes of shared memory: %s", max(WG_SMEM_BYTES, WK_SMEM_BYTES), cudaGetErrorString(e));
       return -2;
     }
-    attr_done = true;
+    attr_set(attr_mask);
   }
   if (stacked) {
     dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), 3u);

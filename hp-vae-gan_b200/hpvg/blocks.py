@@ -234,16 +234,22 @@ def make_family(dims):
             super().__init__()
             self.opt = opt
             self.N = int(opt.nfc)
-            self.encode = EncodeVAE(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks)
+            self.encode = self._make_encoder(opt)      # first, as in the reference: construction order fixes the initial values
             self.decoder = _stage(opt, self.N, opt.latent_dim, opt.padd_size)
             self.decoder.add_module('tail', Conv(self.N, opt.nc_im, opt.ker_size, 1, opt.ker_size // 2))
             self.body = torch.nn.ModuleList([])
+
+        def _make_encoder(self, opt):
+            return EncodeVAE(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks)
 
         def init_next_stage(self):
             if len(self.body) == 0:
                 first = _stage(self.opt, self.N, self.opt.nc_im, self.opt.padd_size)
                 first.add_module('tail', Conv(self.N, self.opt.nc_im, self.opt.ker_size, 1, self.opt.ker_size // 2))
-                self.body.append(first)
+                # built on the CPU like the reference's (same initial values for a given seed), then moved to the generator's
+                # device: the train scripts call init_next_stage() AFTER netG.to(device) (train_video.py:397,416) and wrap
+                # the result in nn.DataParallel, which requires every parameter on that device
+                self.body.append(first.to(next(self.decoder.parameters()).device))
             else:
                 self.body.append(copy.deepcopy(self.body[-1]))
 
@@ -294,6 +300,129 @@ def make_family(dims):
                     x_in = x_up
                 x_prev_out = ops.TanhAdd.apply(like_input(_run_stage(block, x_in, half), dims), like_input(x_up, dims))
             return x_prev_out
+
+
+    Pool = nn.AdaptiveAvgPool3d if dims == 3 else nn.AdaptiveAvgPool2d
+
+    class EncodeVAE_nb(nn.Module):
+        """Bernoulli-gated encoder (reference modules/networks_3d.py:110-138, networks_2d.py:115-143): a 1-channel sigmoid gate
+        multiplies the features, mu / logvar are global averages of their conv maps.  The convolutions (spectral-norm feature
+        chain, the nfc -> 1 gate, the two nfc -> out_dim heads) run on the library's kernels; the gate product, the sigmoid and
+        the global average are small torch element-wise ops on the way."""
+
+        def __init__(self, opt, out_dim=None, num_blocks=2):
+            super().__init__()
+            if out_dim is None:
+                out_dim = opt.nfc
+            elif type(out_dim) is not int:
+                raise AssertionError("out_dim must be an int")
+            half = opt.ker_size // 2
+            self.features = FeatureExtractor(opt.nc_im, opt.nfc, opt.ker_size, half, 1, num_blocks=num_blocks)
+            self.mu = nn.Sequential(_ConvBlock(opt.nfc, out_dim, opt.ker_size, half, 1, bn=False, act=None), Pool(1))
+            self.logvar = nn.Sequential(_ConvBlock(opt.nfc, out_dim, opt.ker_size, half, 1, bn=False, act=None), Pool(1))
+            self.bern = _ConvBlock(opt.nfc, 1, opt.ker_size, half, 1, bn=False, act=None)
+
+        def forward(self, x):
+            _check_device(x)
+            feat = self.features.run(as5d(x).contiguous())                            # wide [N,D,H,W,nfc]
+            gate = torch.sigmoid(self.bern.run(feat, out_wide=False))                 # thin [N,1,D,H,W]
+            gated = (feat * gate.permute(0, 2, 3, 4, 1).to(feat.dtype)).contiguous()
+
+            def pooled(head):
+                m = head[0].run(gated)                                                # wide [N,D,H,W,out_dim]
+                v = m.float().mean(dim=(1, 2, 3))                                     # AdaptiveAvgPool(1)
+                return v.view(v.shape[0], v.shape[1], *([1] * dims))
+            return pooled(self.mu), pooled(self.logvar), like_input(gate, dims)
+
+    def reparameterize_bern(x, training):
+        """reference modules/networks_3d.py:38-43 (Gumbel-style relaxation of the gate)"""
+        if training:
+            eps = torch.zeros_like(x).uniform_()
+            return torch.log(x + 1e-20) - torch.log(-torch.log(eps + 1e-20) + 1e-20)
+        return torch.zeros_like(x).bernoulli_()
+
+    class GeneratorVAE_nb(GeneratorHPVAEGAN):
+        """HP-VAE-GAN generator with the Bernoulli-gated encoder (reference modules/networks_3d.py:409-485, networks_2d.py:272-348):
+        the latent is z_norm (a [N,latent,1,..] vector) times z_bern (a [N,1,T,H,W] map); every refinement level adds noise in
+        'rand' mode and the first GAN level detaches unconditionally.  Decoder and refinement stages are the same kernels."""
+
+        def _make_encoder(self, opt):
+            return EncodeVAE_nb(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks)
+
+        def forward(self, video, noise_amp, noise_init_norm=None, noise_init_bern=None, sample_init=None, mode='rand'):
+            if sample_init is not None:
+                assert len(self.body) > sample_init[0], "Strating index must be lower than # of body blocks"
+            half = self.opt.ker_size // 2
+            if noise_init_norm is None:
+                mu, logvar, bern = self.encode(video)
+                if self.training:
+                    eps = torch.zeros_like(logvar).normal_()
+                    z_norm = eps.mul(logvar.mul(0.5).exp()).add(mu)
+                else:
+                    z_norm = torch.zeros_like(mu).normal_()
+                z_bern = reparameterize_bern(bern, self.training)
+            else:
+                _check_device(noise_init_norm)
+                z_norm, z_bern = noise_init_norm, noise_init_bern
+            z = ops.ToWide.apply(as5d(z_norm * z_bern).contiguous())
+            vae_out = ops.TanhAdd.apply(like_input(_run_stage(self.decoder, z, half), dims), None)
+            if sample_init is not None:
+                x_prev_out = self.refinement_layers(sample_init[0], sample_init[1], noise_amp, mode)
+            else:
+                x_prev_out = self.refinement_layers(0, vae_out, noise_amp, mode)
+            if noise_init_norm is None:
+                return x_prev_out, vae_out, (mu, logvar, bern)
+            return x_prev_out, vae_out
+
+        def refinement_layers(self, start_idx, x_prev_out, noise_amp, mode):
+            opt = self.opt
+            half = opt.ker_size // 2
+            for idx, block in enumerate(self.body[start_idx:], start_idx):
+                if opt.vae_levels == idx + 1:
+                    x_prev_out.detach_()
+                x5 = as5d(x_prev_out)
+                size = images.video_target_size(idx + 1, opt) if dims == 3 else [1] + images.image_target_size(idx + 1, opt)
+                x_up = images.resize(x5, size)
+                if mode == 'rand':
+                    noise = as5d(images.generate_noise(ref=like_input(x_up, dims)))
+                    x_in = images.resize(x5, size, noise=noise, amp=float(noise_amp[idx + 1]))
+                else:
+                    x_in = x_up
+                x_prev_out = ops.TanhAdd.apply(like_input(_run_stage(block, x_in, half), dims), like_input(x_up, dims))
+            return x_prev_out
+
+    class _TorchSNBlock(nn.Sequential):
+        """spectral-norm conv + LeakyReLU in plain torch: pass-through for kernel sizes the library does not cover (1x1x1)"""
+
+        def __init__(self, cin, cout, ker_size, padding, stride):
+            super().__init__()
+            self.add_module('conv', nn.utils.spectral_norm(Conv(cin, cout, kernel_size=ker_size, stride=stride, padding=padding)))
+            self.add_module('lrelu', nn.LeakyReLU(LRELU_SLOPE, inplace=True))
+
+    class _TorchConv(nn.Sequential):
+        def __init__(self, cin, cout, ker_size, padding, stride):
+            super().__init__()
+            self.add_module('conv', Conv(cin, cout, kernel_size=ker_size, stride=stride, padding=padding))
+
+    class EncodeVAE1x1(nn.Module):
+        """1x1x1 encoder (reference modules/networks_3d.py:141-160; no network of the reference instantiates it): plain torch
+        pass-through — a 1x1x1 convolution is a per-voxel matrix product, outside the 3x3x3 kernels of this library."""
+
+        def __init__(self, opt, out_dim=None):
+            super().__init__()
+            if out_dim is None:
+                out_dim = opt.nfc
+            elif type(out_dim) is not int:
+                raise AssertionError("out_dim must be an int")
+            self.features = nn.Sequential()
+            for i in range(3):
+                self.features.add_module('conv_block_{}'.format(i), _TorchSNBlock(opt.nc_im if i == 0 else opt.nfc, opt.nfc, 1, 0, 1))
+            self.mu = _TorchConv(opt.nfc, out_dim, 1, 0, 1)
+            self.logvar = _TorchConv(opt.nfc, out_dim, 1, 0, 1)
+
+        def forward(self, x):
+            feat = self.features(x)
+            return self.mu(feat), self.logvar(feat)
 
     class GeneratorSG(nn.Module):
         """SinGAN-style baseline: valid (pad 0) convolutions on inputs zero-padded by num_layer + 2 voxels (3-D only)."""
@@ -384,9 +513,10 @@ def make_family(dims):
     class WDiscriminatorBaselines(nn.Module):
         """BatchNorm critic of the SinGAN-style baselines (reference modules/networks_3d.py:184-210): the input is zero-padded
         by num_layer + 2 voxels, head = conv + LeakyReLU, num_layer ConvBlocks, plain tail conv.  Forward and first-order
-        backward run on the library's kernels; the WGAN-GP double backward through BatchNorm is not implemented (the
-        BatchNorm node is once-differentiable: calc_gradient_penalty(...).backward() raises) — the reference's default critic
-        for every script, WDiscriminator3D, has no BatchNorm and is fully covered.  3-D only."""
+        backward run on the library's kernels (fused conv + BatchNorm node); under calc_gradient_penalty the blocks switch to
+        the double-differentiable form (hpvg.ops.twice_differentiable: library convolutions, BatchNorm + LeakyReLU composed of
+        element-wise torch operations), so the WGAN-GP double backward of train_video_baselines.py --discriminator
+        WDiscriminatorBaselines works.  3-D only."""
 
         def __init__(self, opt):
             super().__init__()
@@ -412,6 +542,8 @@ def make_family(dims):
         'ConvBlock': _ConvBlock, 'ConvBlockSN': _ConvBlockSN, 'FeatureExtractor': FeatureExtractor, 'EncodeVAE': EncodeVAE,
         'WDiscriminator': WDiscriminator, 'GeneratorHPVAEGAN': GeneratorHPVAEGAN, 'GeneratorSG': GeneratorSG,
         'GeneratorCSG': GeneratorCSG, 'WDiscriminatorBaselines': WDiscriminatorBaselines,
+        'EncodeVAE_nb': EncodeVAE_nb, 'GeneratorVAE_nb': GeneratorVAE_nb, 'EncodeVAE1x1': EncodeVAE1x1,
+        'reparameterize_bern': reparameterize_bern,
     }
 
 

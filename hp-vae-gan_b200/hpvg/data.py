@@ -46,13 +46,20 @@ class ResidentVideo:
         return real, real_zero
 
 
-def to_uint8_frames(video):
-    """[3, T, H, W] float32 in [-1, 1] -> uint8 [T, H, W, 3] as utils/saver.py::write_video converts frames before encoding"""
+def to_uint8_frames(video, out=None):
+    """[3, T, H, W] float32 in [-1, 1] -> uint8 [T, H, W, 3] as utils/saver.py::write_video converts frames before encoding;
+    a batch [N, 3, T, H, W] -> [N, T, H, W, 3] in one launch.  `out`: optional preallocated result."""
     ops._require_cuda(video)
     video = video.contiguous()
-    if video.dim() != 4 or video.shape[0] != 3 or video.dtype != torch.float32:
-        raise ValueError("expected a float32 [3, T, H, W] video")
-    _, t, h, w = video.shape
-    out = torch.empty((t, h, w, 3), dtype=torch.uint8, device=video.device)
-    lib.call("hpvg_frames_to_uint8", video.data_ptr(), out.data_ptr(), t, h, w, _stream())
+    batched = video.dim() == 5
+    if video.dim() not in (4, 5) or video.shape[-4] != 3 or video.dtype != torch.float32:
+        raise ValueError("expected a float32 [3, T, H, W] video or a [N, 3, T, H, W] batch")
+    n = video.shape[0] if batched else 1
+    t, h, w = video.shape[-3:]
+    shape = (n, t, h, w, 3) if batched else (t, h, w, 3)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=video.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 tensor of shape %s" % (shape,))
+    lib.call("hpvg_frames_to_uint8_batched", video.data_ptr(), out.data_ptr(), n, t, h, w, _stream())
     return out

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "hpvg_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "hpvg_clip_from_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "hpvg_frames_to_uint8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hpvg_frames_to_uint8_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hpvg_sn_power_iter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p]),
     "hpvg_sn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -149,7 +150,7 @@ def get_conv_backend():
     return int(load().hpvg_get_conv_backend())
 
 
-PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow"}
+PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow", 6: "conv_bn_fused"}
 
 
 def set_conv_col_mode(mode):

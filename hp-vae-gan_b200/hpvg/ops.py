@@ -813,8 +813,44 @@ def _conv_bn_lrelu_per_sample(x, w, bias, gamma, beta, pad, eps, slope):
     return out
 
 
+_TWICE = [False]
+
+
+class twice_differentiable:
+    """Context: ConvBlocks with BatchNorm built inside it can be differentiated twice.  calc_gradient_penalty wraps the critic's
+    pass over the interpolates in it: the fused ConvBnLrelu node is first-order only (BatchNorm blocks live in the generators,
+    which never see a double backward), but WDiscriminatorBaselines (reference modules/networks_3d.py:184-210) is a critic WITH
+    BatchNorm.  In this mode the convolution stays on the library's double-differentiable family (ConvFwd / ConvDgrad /
+    ConvWgrad) and the BatchNorm + LeakyReLU of the block is composed of element-wise torch operations, whose double
+    backward autograd derives."""
+
+    def __enter__(self):
+        self.prev = _TWICE[0]
+        _TWICE[0] = True
+
+    def __exit__(self, *a):
+        _TWICE[0] = self.prev
+
+
+def _conv_bn_lrelu_twice(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope):
+    y = ConvFwd.apply(x, w, bias, pad, True, None, None).float()             # wide [N,D,H,W,C] -> fp32 for the statistics
+    dims = (0, 1, 2, 3)
+    mean = y.mean(dims)
+    var = y.var(dims, unbiased=False)
+    out = torch.nn.functional.leaky_relu((y - mean) * torch.rsqrt(var + eps) * gamma + beta, slope)
+    if _BN_TRACK[0] and running_mean is not None:
+        with torch.no_grad():
+            count = y.numel() // y.shape[-1]
+            running_mean.mul_(1 - momentum).add_(momentum * mean.detach())
+            running_var.mul_(1 - momentum).add_(momentum * var.detach() * (count / max(count - 1, 1)))
+            nbt.add_(1)
+    return out.to(torch.bfloat16)
+
+
 def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum=0.1, eps=1e-5, slope=0.2):
     """ConvBlock3D/2D (reference modules/networks_3d.py:48-56) through the fused node"""
+    if _TWICE[0] and torch.is_grad_enabled():
+        return _conv_bn_lrelu_twice(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope)
     if _BN_PER_SAMPLE[0]:
         if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
             raise lib.HpvgError("per-sample BatchNorm statistics are an inference mode: run it under torch.no_grad()")
@@ -1063,6 +1099,7 @@ class _GpAlpha:
     lerp kernel reads a fresh value."""
     external = False
     tensors = {}
+    generator = None      # CPU generator for the draw (None: torch's default one, as the reference); see ScaleTrainer(distributed=True)
 
     @classmethod
     def tensor(cls, device):
@@ -1075,7 +1112,8 @@ class _GpAlpha:
     @classmethod
     def draw(cls, device):
         t = cls.tensor(device)
-        t.fill_(float(torch.rand(1, 1)))     # scalar travels as a kernel argument: no host buffer to race with
+        a = torch.rand(1, 1) if cls.generator is None else torch.rand(1, 1, generator=cls.generator)
+        t.fill_(float(a))     # scalar travels as a kernel argument: no host buffer to race with
         return t
 
 

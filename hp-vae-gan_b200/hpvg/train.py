@@ -58,7 +58,11 @@ def generator_param_groups(opt, netG):
 
 
 class GradBucket:
-    """flat fp32 bucket for the per-backward gradient all-reduce (average over ranks)"""
+    """per-backward gradient all-reduce (average over ranks).
+    CUDA / NCCL: ONE coalesced NCCL call over the gradient tensors in place (ncclGroupStart .. ncclGroupEnd, ReduceOp.AVG) —
+    no packing into a flat buffer and back, no separate division: three launches fewer per backward than the flat bucket, and
+    the collective records into the iteration's CUDA graph like any kernel.  Other backends (the gloo CPU tests): a flat fp32
+    bucket, SUM then divide."""
 
     def __init__(self, group=None):
         self.group = group
@@ -70,6 +74,11 @@ class GradBucket:
         if not grads:
             return 0
         n = sum(g.numel() for g in grads)
+        if grads[0].is_cuda and dist.get_backend(self.group) == "nccl" and os.environ.get("HPVG_FLAT_BUCKET", "0") != "1":
+            with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            return n * 4
         if self.flat is None or self.flat.numel() != n or self.flat.device != grads[0].device:
             self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
         views, off = [], 0
@@ -115,8 +124,13 @@ class ScaleTrainer:
         self.optimizerG = adam(generator_param_groups(opt, netG), lr=opt.lr_g, betas=(opt.beta1, 0.999))
         self.optimizerD = adam(netD.parameters(), lr=opt.lr_d, betas=(opt.beta1, 0.999)) if self.gan else None
         self.distributed = distributed
+        if distributed and ops._GpAlpha.generator is None:
+            # the reference draws ONE alpha for the whole (DataParallel) batch (modules/utils.py:5): every rank draws it from a
+            # CPU generator seeded identically, independent of the per-rank noise seeds
+            ops._GpAlpha.generator = torch.Generator().manual_seed(0x5EED)
         self.bucketG, self.bucketD = GradBucket(), GradBucket()
-        self.allreduce_bytes = 0
+        self.allreduce_bytes = 0              # all eager iterations so far
+        self.allreduce_bytes_per_iter = 0     # one iteration (what a replay of the recorded iteration moves as well)
         self.iterations = 0
         self.graph = None
         self.overlap = torch.cuda.is_available() if overlap is None else bool(overlap)
@@ -146,11 +160,15 @@ class ScaleTrainer:
                 opt.Noise_Amps.append(0)
                 z_rec, _, _ = self.netG(real_zero, opt.Noise_Amps, mode="rec")
                 mse = F.mse_loss(real, z_rec)
+                global_batch = opt.batch_size
                 if self.distributed:
+                    # the reference's multi-GPU mode is nn.DataParallel over ONE batch: RMSE over all clips, divided by the
+                    # global batch size (train_video.py:143-144); here the clips are spread one per rank
                     import torch.distributed as dist
                     dist.all_reduce(mse, op=dist.ReduceOp.SUM)
                     mse /= dist.get_world_size()
-                opt.noise_amp = opt.noise_amp_init * torch.sqrt(mse).item() / opt.batch_size
+                    global_batch = opt.batch_size * dist.get_world_size()
+                opt.noise_amp = opt.noise_amp_init * torch.sqrt(mse).item() / global_batch
                 opt.Noise_Amps[-1] = opt.noise_amp
 
     def iteration(self, real, real_zero):
@@ -178,6 +196,7 @@ class ScaleTrainer:
 
     def _iteration_body(self, real, real_zero, noise_init, out):
         opt, G, D = self.opt, self.netG, self.netD
+        bytes_before = self.allreduce_bytes
         from modules.losses import kl_criterion
         from modules.utils import calc_gradient_penalty
         side = None
@@ -234,6 +253,7 @@ class ScaleTrainer:
             self.optimizerG.step()
         out['total_loss'] = total_loss.detach()
         self.iterations += 1
+        self.allreduce_bytes_per_iter = self.allreduce_bytes - bytes_before
         return out
 
 
@@ -325,6 +345,63 @@ class ScaleTrainer:
         ops.invalidate_packed_weights()                    # the replay stepped the optimizers behind torch's version counters
         self.iterations += 1
         return self.static_out
+
+
+class NoiseFeed:
+    """Injected random draws: while active, every N(0,1) draw of the networks (the single hook images.draw_normal) is a copy
+    of a persistent device buffer, in call order, and the WGAN-GP alpha (torch.rand(1, 1), reference modules/utils.py:5)
+    is the supplied value.  Used by the parity tests and by bench.py's parity leg to step the CUDA path and the CPU oracle
+    on identical draws.  Works under CUDA-graph capture too: the recording holds the copies out of the buffers, so
+    `load()` before a replay feeds that replay.
+
+        feed = NoiseFeed(device)
+        with feed:
+            feed.load([noise_init, eps, noise_3, noise_4], alpha); out = trainer.iteration(real, real_zero)
+    """
+
+    def __init__(self, device):
+        self.device, self.bufs, self.i, self.n = device, [], 0, 0
+        self.alpha = None
+
+    def load(self, tensors, alpha=None):
+        for k, t in enumerate(tensors):
+            if k < len(self.bufs) and tuple(self.bufs[k].shape) == tuple(t.shape):
+                self.bufs[k].copy_(t, non_blocking=True)
+            else:
+                buf = t.to(device=self.device, dtype=torch.float32).clone()
+                if k < len(self.bufs):
+                    self.bufs[k] = buf
+                else:
+                    self.bufs.append(buf)
+        self.i, self.n, self.alpha = 0, len(tensors), alpha
+
+    def rewind(self):
+        self.i = 0
+
+    def _draw(self, shape, dtype, device):
+        if self.i >= self.n:
+            raise RuntimeError("NoiseFeed: the path asked for draw %d but only %d were loaded" % (self.i + 1, self.n))
+        b = self.bufs[self.i]
+        if tuple(b.shape) != tuple(shape):
+            raise RuntimeError("NoiseFeed: draw %d has shape %s, the path asked for %s" % (self.i, tuple(b.shape), tuple(shape)))
+        self.i += 1
+        return b.to(dtype=dtype).clone()
+
+    def _rand(self, *a, **k):
+        if self.alpha is None:
+            raise RuntimeError("NoiseFeed: no alpha loaded")
+        return torch.full((1, 1), float(self.alpha))
+
+    def exhausted(self):
+        return self.i == self.n
+
+    def __enter__(self):
+        self._saved = (images.draw_normal, torch.rand)
+        images.draw_normal, torch.rand = self._draw, self._rand
+        return self
+
+    def __exit__(self, *a):
+        images.draw_normal, torch.rand = self._saved
 
 
 def draws_for_rank(total, world, rank):

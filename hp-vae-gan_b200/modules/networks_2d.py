@@ -36,15 +36,10 @@ def reparameterize(mu, logvar, training):
     return _ops.ToThin.apply(z).view_as(mu)
 
 
-def _out_of_scope(name, where):
-    class _Stub(torch.nn.Module):
-        def __init__(self, *a, **k):
-            super().__init__()
-            raise NotImplementedError(
-                "%s (%s) is outside the accelerated hot path of hpvg-b200 (SURVEY.md section 2)" % (name, where))
-    _Stub.__name__ = _Stub.__qualname__ = name
-    return _Stub
+def reparameterize_bern(x, training):
+    """reference :45-50"""
+    return _family['reparameterize_bern'](x, training)
 
 
-Encode2DVAE_nb = _out_of_scope('Encode2DVAE_nb', 'modules/networks_2d.py:115-143')
-GeneratorVAE_nb = _out_of_scope('GeneratorVAE_nb', 'modules/networks_2d.py:272-348')
+Encode2DVAE_nb = _export('EncodeVAE_nb', 'Encode2DVAE_nb')             # reference :115-143
+GeneratorVAE_nb = _export('GeneratorVAE_nb', 'GeneratorVAE_nb')        # reference :272-348

@@ -52,17 +52,11 @@ def reparameterize(mu, logvar, training):
     return _ops.ToThin.apply(z).view_as(mu)
 
 
-def _out_of_scope(name, where):
-    class _Stub(torch.nn.Module):
-        def __init__(self, *a, **k):
-            super().__init__()
-            raise NotImplementedError(
-                "%s (%s) is outside the accelerated hot path of hpvg-b200 (SURVEY.md section 2: no BASELINE config uses it)"
-                % (name, where))
-    _Stub.__name__ = _Stub.__qualname__ = name
-    return _Stub
+def reparameterize_bern(x, training):
+    """reference :38-43"""
+    return _family['reparameterize_bern'](x, training)
 
 
-Encode3DVAE_nb = _out_of_scope('Encode3DVAE_nb', 'modules/networks_3d.py:110-138')
-Encode3DVAE1x1 = _out_of_scope('Encode3DVAE1x1', 'modules/networks_3d.py:141-160')
-GeneratorVAE_nb = _out_of_scope('GeneratorVAE_nb', 'modules/networks_3d.py:409-485')
+Encode3DVAE_nb = _export('EncodeVAE_nb', 'Encode3DVAE_nb')             # reference :110-138
+Encode3DVAE1x1 = _export('EncodeVAE1x1', 'Encode3DVAE1x1')             # reference :141-160 (plain torch: 1x1x1 convolutions)
+GeneratorVAE_nb = _export('GeneratorVAE_nb', 'GeneratorVAE_nb')        # reference :409-485

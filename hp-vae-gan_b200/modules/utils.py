@@ -12,7 +12,8 @@ def calc_gradient_penalty(netD, real_data, fake_data, LAMBDA, device):
     fprop/dgrad/wgrad kernels by hpvg.ops."""
     alpha = _ops.gp_alpha(real_data.device)         # same CPU-generator draw as the reference (:5), as a device float
     interpolates = _ops.lerp(real_data, fake_data, alpha).requires_grad_(True)
-    disc_interpolates = netD(interpolates)
+    with _ops.twice_differentiable():      # critics with BatchNorm (WDiscriminatorBaselines): see hpvg.ops.twice_differentiable
+        disc_interpolates = netD(interpolates)
     ones = torch.ones(disc_interpolates.size(), device=disc_interpolates.device)
     with _ops.input_grad_only():
         gradients = torch.autograd.grad(outputs=disc_interpolates, inputs=interpolates, grad_outputs=ones,

@@ -261,6 +261,8 @@ int hpvg_lerp(const float* a, const float* b, float* out, const float* alpha, lo
 int hpvg_clip_from_frames(const uint8_t* frames, float* clip, int num_frames, int first, int every, int T, int H, int W,
                           int hflip, void* stream);
 int hpvg_frames_to_uint8(const float* video, uint8_t* out, int T, int H, int W, void* stream);
+/* the same for a batch of videos: float32 [N][3][T][H][W] -> uint8 [N][T][H][W][3] in one launch */
+int hpvg_frames_to_uint8_batched(const float* video, uint8_t* out, int N, int T, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Spectral normalisation, one power iteration (nn.utils.spectral_norm as used by ConvBlock3DSN/2DSN,

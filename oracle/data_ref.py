@@ -3,8 +3,10 @@
 clip_from_frames follows SingleVideoDataset.__getitem__ / _get_transformed_frames (datasets/video.py:44-82); kornia
 (pinned kornia==0.2.0 in env.sh:5, absent here) is restated from its documented semantics: image_to_tensor = HWC -> CHW
 (batched: BHWC -> BCHW) without scaling, hflip = flip of the last axis, normalize(x, mean, std) = (x - mean) / std.
-frames_to_uint8 follows utils/saver.py::write_video (:16-18).  Parity unpinned by reference vectors (the reference has no
-tests and the dataset class needs kornia + a decodable video); the functions are short enough to check by reading.
+frames_to_uint8 follows utils/saver.py::write_video (:16-18).  Pinned by tests/golden/data_video.pt, recorded from the unmodified
+reference's SingleVideoDataset.__getitem__ and write_video by tests/golden/make_data_golden.py (kornia through the shim of
+tests/integration/shims): tests/test_oracle.py::test_data_formats_match_the_reference_dataset_and_writer holds both functions to
+those vectors bit for bit.
 """
 import numpy as np
 import torch

@@ -80,7 +80,7 @@ class ScaleTrainer(object):
         generator in the reference's order."""
         opt, sd_g, sd_d = self.opt, self.sd_g, self.sd_d
         if noise_init is None:
-            noise_init = torch.zeros(*opt.Z_init_size).normal_(0, 1)                       # :126
+            noise_init = torch.zeros(*opt.Z_init_size, device=real.device).normal_(0, 1)   # :126
         if self.iterations == 0 and len(opt.Noise_Amps) < opt.scale_idx + 1:               # :131-145
             if opt.const_amp:
                 opt.Noise_Amps.append(1)

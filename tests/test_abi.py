@@ -4,6 +4,7 @@ import os
 import re
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -86,6 +87,24 @@ def test_state_dict_keys_of_the_baseline_networks(golden):
     g = networks_3d.GeneratorCSG(opt_from(golden("csg3d_wide")))
     w = g.body[0].block0.conv.weight
     assert abs(w.std().item() - 0.02) < 2e-3 and abs(g.head.norm.weight.mean().item() - 1.0) < 2e-2
+
+
+def test_state_dict_keys_of_the_bernoulli_variants(golden):
+    """GeneratorVAE_nb (3-D and 2-D) and Encode3DVAE1x1 construct on the CPU with the reference's state_dict keys and shapes"""
+    from helpers import opt_from
+    from modules import networks_2d, networks_3d
+    for dims, nets in ((3, networks_3d), (2, networks_2d)):
+        fx = golden("nb%dd_tiny" % dims)
+        g = nets.GeneratorVAE_nb(opt_from(fx))
+        g.init_next_stage()
+        g.init_next_stage()
+        assert [(k, tuple(v.shape)) for k, v in g.state_dict().items()] == [(k, tuple(s)) for k, s in fx['state']]
+    enc = networks_3d.Encode3DVAE1x1(opt_from(golden("nb3d_tiny")))
+    keys = list(enc.state_dict().keys())
+    assert 'features.conv_block_0.conv.weight_orig' in keys and 'mu.conv.weight' in keys and 'logvar.conv.bias' in keys
+    x = torch.zeros(1, 3, 2, 5, 5)
+    mu, logvar = enc(x)                      # plain torch pass-through: runs on the CPU
+    assert mu.shape == (1, 8, 2, 5, 5) and logvar.shape == mu.shape
 
 
 def test_zero_arena_and_per_sample_switch_host_logic():

@@ -45,6 +45,28 @@ def test_frames_to_uint8_is_bit_exact():
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
+def test_device_data_path_against_the_reference_dataset_and_writer(golden):
+    """hpvg.data.ResidentVideo / to_uint8_frames against the vectors recorded from the UNMODIFIED reference dataset and writer
+    (tests/golden/data_video.pt): bit for bit, every pyramid level, both flip states; the batched conversion too"""
+    from hpvg import data
+    fx = golden("data_video")
+    opt = port.Opt(img_size=28, min_size=18, sampling_rates=fx['sampling_rates'])
+    assert opt.fps_lcm == fx['fps_lcm']
+    for c in fx['cases']:
+        opt.fps_index = c['fps_index']
+        rv = data.ResidentVideo(fx['levels'][c['scale']], fx['zero'], opt, 'cuda')
+        real, real_zero = rv.clip(c['idx'], hflip=c['hflip'])
+        assert torch.equal(real.cpu(), c['real']), (c['scale'], c['idx'], c['hflip'])
+        if c['scale'] > 0:
+            assert torch.equal(real_zero.cpu(), c['real_zero'])
+    out = data.to_uint8_frames(fx['video'].cuda())
+    assert torch.equal(out.cpu(), fx['written'])
+    batch = torch.stack([fx['video'], -fx['video'], fx['video'] * 0.5]).cuda()
+    outs = data.to_uint8_frames(batch)
+    for k in range(3):
+        assert torch.equal(outs[k], data.to_uint8_frames(batch[k]))
+
+
 def test_resident_video_rejects_out_of_range_slices():
     from hpvg import data, lib
     opt = port.Opt(img_size=64, sampling_rates=[4, 3, 2, 1])

@@ -290,8 +290,25 @@ def test_discriminator_baselines_parity(golden, name):
     (-out_real.mean() + out_fake.mean()).backward()
     _check_grads(d, _oracle_grads(sd), 2 * EMU_GRAD_TOL[fam], 2e-3, name + '/grads_vs_emu')
     _check_grads(d, fx['grads'], REF_GRAD_TOL[fam], 2e-3, name + '/grads_vs_ref')
-    with pytest.raises(RuntimeError):
-        mutils.calc_gradient_penalty(d, fx['real'].cuda(), fx['fake'].cuda(), 0.1, 'cuda').backward()
+
+
+def test_discriminator_baselines_gradient_penalty(golden, monkeypatch):
+    """the WGAN-GP double backward THROUGH BatchNorm (WDiscriminatorBaselines, reference modules/networks_3d.py:184-210 under
+    modules/utils.py:4-19): penalty value and every parameter gradient of the critic loss of train_video_baselines.py:131-149
+    against the unmodified reference (tests/golden/make_nb_golden.py::dbase_gp_case)"""
+    from modules import networks_3d
+    from modules import utils as mutils
+    fx = golden("dbase3d_gp_tiny")
+    opt = opt_from(fx)
+    d = _cuda_module(networks_3d.WDiscriminatorBaselines, opt, fx)
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: torch.full((1, 1), fx['alpha']))
+    real, fake = fx['real'].cuda(), fx['fake'].cuda()
+    d.zero_grad()
+    loss = -d(real).mean() + d(fake).mean()
+    gp = mutils.calc_gradient_penalty(d, real, fake, fx['lambda'], 'cuda')
+    (loss + gp).backward()
+    assert abs(gp.item() - fx['gp']) <= LOSS_TOL * abs(fx['gp']), (gp.item(), fx['gp'])
+    _check_grads(d, fx['grads'], REF_GRAD_TOL['tiny'], 2e-3, 'dbase3d_gp_tiny/grads_vs_ref')
 
 
 @pytest.mark.parametrize("nfc,col_mode", [(64, 0), (64, 1), (8, -1)])
@@ -452,3 +469,31 @@ def test_modules_refuse_cpu_tensors():
     d = networks_3d.WDiscriminator3D(opt)
     with pytest.raises(HpvgError):
         d(torch.zeros(1, 3, 3, 8, 8))
+
+
+@pytest.mark.parametrize("dims", [3, 2])
+def test_bernoulli_gated_variants_match_the_reference(golden, dims):
+    """row f4: GeneratorVAE_nb / Encode{3D,2D}VAE_nb (reference modules/networks_3d.py:110-138, :409-485; networks_2d.py:115-143,
+    :272-348) on the library's convolution kernels, against vectors recorded from the unmodified reference
+    (tests/golden/make_nb_golden.py): encoder outputs (mu, logvar, gate), generator output in 'rec' mode driven by
+    noise_init_norm / noise_init_bern, and every parameter gradient of a fixed linear loss"""
+    from modules import networks_2d, networks_3d
+    nets = networks_3d if dims == 3 else networks_2d
+    fx = golden("nb%dd_tiny" % dims)
+    opt = opt_from(fx)
+    g = _cuda_module(nets.GeneratorVAE_nb, opt, fx, stages=2)
+    assert [k for k, _ in fx['state']] == list(g.state_dict().keys())
+    mu, logvar, bern = g.encode(fx['video'].cuda())
+    assert mu.shape == fx['mu'].shape and bern.shape == fx['bern'].shape
+    assert rel_err(mu, fx['mu']) < REF_OUT_TOL and rel_err(logvar, fx['logvar']) < REF_OUT_TOL and rel_err(bern, fx['bern']) < REF_OUT_TOL
+    out, vae_out = g(None, fx['amps'], noise_init_norm=fx['z_norm'].cuda(), noise_init_bern=fx['z_bern'].cuda(), mode='rec')
+    assert rel_err(out, fx['out']) < REF_OUT_TOL and rel_err(vae_out, fx['vae_out']) < REF_OUT_TOL
+    s = fx['seeds']
+    loss = (out * fx['gout'].cuda()).sum() + (mu * port.det_tensor(tuple(mu.shape), s['mu']).cuda()).sum() \
+        + (logvar * port.det_tensor(tuple(logvar.shape), s['logvar']).cuda()).sum() + (bern * port.det_tensor(tuple(bern.shape), s['bern']).cuda()).sum()
+    g.zero_grad()
+    loss.backward()
+    _check_grads(g, fx['grads'], REF_GRAD_TOL['tiny'], 2e-3, 'nb%dd_tiny vs reference' % dims)
+    # the sampling entry point draws its own noise: shapes and finiteness only
+    x, v, (m2, l2, b2) = g(fx['video'].cuda(), fx['amps'], mode='rand')
+    assert x.shape == out.shape and torch.isfinite(x).all() and m2.shape == mu.shape and b2.shape == bern.shape

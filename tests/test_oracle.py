@@ -282,3 +282,23 @@ def test_numpy_clip_and_adam_match_torch():
             assert np.allclose(params[i].detach().numpy(), p_np[i], rtol=1e-10, atol=1e-14)
             assert np.allclose(opt.state[params[i]]['exp_avg'].numpy(), m_np[i], rtol=1e-10, atol=1e-300)
             assert np.allclose(opt.state[params[i]]['exp_avg_sq'].numpy(), v_np[i], rtol=1e-10, atol=1e-300)
+
+
+def test_data_formats_match_the_reference_dataset_and_writer(golden):
+    """rows f2 / f3: oracle/data_ref.py against what the UNMODIFIED reference produced (tests/golden/make_data_golden.py):
+    SingleVideoDataset.__getitem__ (datasets/video.py:44-66) at every pyramid level, two indices, with and without the
+    horizontal flip, and the uint8 frames utils/saver.py::write_video hands to the encoder — bit for bit"""
+    import numpy as np
+    from oracle import data_ref
+    fx = golden("data_video")
+    rates, lcm = fx['sampling_rates'], fx['fps_lcm']
+    assert any(c['hflip'] for c in fx['cases']) and not all(c['hflip'] for c in fx['cases'])
+    for c in fx['cases']:
+        frames = fx['levels'][c['scale']].numpy()
+        real = data_ref.clip_from_frames(frames, c['idx'], lcm, rates[c['fps_index']], c['hflip'])
+        assert torch.equal(real, c['real']), (c['scale'], c['idx'], c['hflip'])
+        if c['scale'] > 0:
+            zero = data_ref.clip_from_frames(fx['zero'].numpy(), c['idx'], lcm, rates[0], c['hflip'])
+            assert torch.equal(zero, c['real_zero'])
+    out = data_ref.frames_to_uint8(fx['video'].numpy())
+    assert np.array_equal(out, fx['written'].numpy())
