@@ -191,6 +191,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Grid-wide barrier for kernels whose whole grid is resident (at most one CTA per SM, cooperative launch): ONE thread per CTA
+// arrives on a zero-initialised global counter and spins until all `expected` CTAs have; the caller brackets it with its own
+// CTA-level barriers and makes its global writes visible with __threadfence() first.  Bounded like mbar_wait: a protocol or
+// residency bug fails the launch instead of hanging the GPU.  (CTAs of a grid are dispatched before any CTA of a later grid, so
+// a grid that fits the machine always becomes fully resident: measured with two such grids racing on two streams,
+// experiments/coop_concurrency.py.)
+__device__ __forceinline__ void grid_barrier_arrive_and_wait(unsigned* counter, unsigned expected) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  unsigned seen;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    if (seen < expected && clock64() - t0 > 2000000000LL) {
+      printf("hpvg: grid barrier timed out (block %d saw %u of %u)\n", blockIdx.x, seen, expected);
+      __trap();
+    }
+  } while (seen < expected);
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

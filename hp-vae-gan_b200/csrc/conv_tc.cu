@@ -518,20 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __threadfence();
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
-    if (et == 0) {
-      // grid barrier (all CTAs are co-resident): arrive, then spin until everyone has.  Bounded like mbar_wait.
-      __threadfence();
-      atomicAdd(p.grid_counter, 1u);
-      unsigned seen;
-      const long long t0 = clock64();
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.grid_counter) : "memory");
-        if (seen < gridDim.x && clock64() - t0 > 2000000000LL) {
-          printf("hpvg: fused BatchNorm grid barrier timed out (block %d saw %u of %u)\n", blockIdx.x, seen, gridDim.x);
-          __trap();
-        }
-      } while (seen < gridDim.x);
-    }
+    if (et == 0) grid_barrier_arrive_and_wait(p.grid_counter, gridDim.x);      // all CTAs are co-resident (cooperative launch)
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI_THREADS) : "memory");
     if (et < 64) {
       const int c = et;

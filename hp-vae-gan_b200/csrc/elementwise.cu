@@ -257,6 +257,180 @@ __global__ void __launch_bounds__(256) bn_lrelu_bwd_apply_kernel(const uint4* __
   }
 }
 
+
+// BatchNorm running statistics applied AFTER the fact, in order: entry e updates running_mean / running_var / num_batches_tracked
+// of its layer from the batch mean / invstd that the layer's forward saved (mean_invstd), exactly as bn_finalize would have:
+//   running <- (1 - momentum) * running + momentum * {mean, unbiased variance}.
+// The generator's reconstruction and sampling passes run concurrently on two streams and go through the SAME BatchNorm layers;
+// their updates are logged and applied by one launch in the reference's order (all of 'rec', then all of 'rand') instead of
+// racing on the buffers.  One thread per channel walks the entries sequentially: entries of the same layer stay ordered.
+struct BnRunBatch {
+  int n;
+  float* rm[HPVG_BN_LOG_MAX];
+  float* rv[HPVG_BN_LOG_MAX];
+  long long* nbt[HPVG_BN_LOG_MAX];
+  const float* mean_invstd[HPVG_BN_LOG_MAX];
+  long long count[HPVG_BN_LOG_MAX];
+  int C[HPVG_BN_LOG_MAX];
+  float momentum[HPVG_BN_LOG_MAX];
+  float eps[HPVG_BN_LOG_MAX];
+};
+
+__global__ void __launch_bounds__(256) bn_running_update_kernel(const BnRunBatch b) {
+  pdl_enter();
+  // block = one LAYER: the first entry that names a buffer owns it and applies every later entry of the same buffer, in order;
+  // blocks whose entry is not the first of its layer leave at once.  Layers are independent, so they update in parallel.
+  const int first = blockIdx.x;
+  for (int e = 0; e < first; ++e)
+    if (b.mean_invstd[e] != nullptr && b.rm[e] == b.rm[first] && b.rv[e] == b.rv[first] && b.nbt[e] == b.nbt[first]) return;
+  const int c = threadIdx.x;
+  for (int e = first; e < b.n; ++e) {
+    if (e != first && !(b.rm[e] == b.rm[first] && b.rv[e] == b.rv[first] && b.nbt[e] == b.nbt[first])) continue;
+    if (c < b.C[e]) {
+      const float mean = b.mean_invstd[e][c];
+      const float invstd = b.mean_invstd[e][b.C[e] + c];
+      double var = 1.0 / ((double)invstd * (double)invstd) - (double)b.eps[e];
+      if (var < 0.0) var = 0.0;
+      const long long n = b.count[e];
+      const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+      const float m = b.momentum[e];
+      if (b.rm[e]) b.rm[e][c] = (1.f - m) * b.rm[e][c] + m * mean;
+      if (b.rv[e]) b.rv[e][c] = (1.f - m) * b.rv[e][c] + m * (float)unbiased;
+    }
+    if (c == 0 && b.nbt[e]) b.nbt[e][0] += 1;
+  }
+}
+
+// BatchNorm + LeakyReLU backward in ONE launch (reduce + apply): every CTA loads its share of y and gout ONCE into shared
+// memory, adds its partial sums of dz and dz * xhat to the global totals, crosses a grid-wide barrier, and applies
+// gy = scale * (dz - mean(dz) - xhat * mean(dz * xhat)) from shared memory.  HBM traffic: y + gout read once and gy written once
+// (25 MB per 64-channel layer at 16 x 64 x 64) instead of y + gout twice (42 MB) in two launches.  Persistent grid of at most one CTA
+// per SM, cooperative launch; eligible when the tensor fits the SMs' shared memory (host check), else the two-launch path runs.
+// `sums`: float32 [3C + 1], zeroed by the caller: [0,C) sum dz, [C,2C) sum dz*xhat, [2C,3C) bias-gradient sums, [3C] barrier counter.
+constexpr int BNB_THREADS = 512;
+__global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gout,
+                                                                            const float* __restrict__ scale_shift,
+                                                                            const float* __restrict__ mean_invstd, float* __restrict__ sums,
+                                                                            uint4* __restrict__ gy, float* __restrict__ dgamma,
+                                                                            float* __restrict__ dbeta, long long nvox, int C, float slope,
+                                                                            int want_chsum, const uint8_t* __restrict__ mask,
+                                                                            int rows_per_cta) {
+  extern __shared__ __align__(16) uint8_t bnb_smem[];
+  const int cvec = C >> 3;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const int rows = (int)max(0LL, min((long long)rows_per_cta, nvox - row0));
+  const int nvec = rows * cvec;
+  float* prm = reinterpret_cast<float*>(bnb_smem);                 // scale, shift, mean, invstd [4C]; m0, m1 [2C]; red [3C]
+  float* red = prm + 6 * C;
+  uint4* sy = reinterpret_cast<uint4*>(bnb_smem + 9 * C * sizeof(float));
+  uint4* sg = sy + (size_t)rows_per_cta * cvec;
+  uint8_t* sm = reinterpret_cast<uint8_t*>(sg + (size_t)rows_per_cta * cvec);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    prm[i] = scale_shift[i];
+    prm[2 * C + i] = mean_invstd[i];
+  }
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x % cvec;      // blockDim.x is a multiple of cvec: a thread's 8-channel group is fixed
+  const int c0 = cg << 3;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
+  const uint4* yb = y + row0 * cvec;
+  const uint4* gb = gout + row0 * cvec;
+  const uint8_t* mb_base = mask ? mask + row0 * cvec : nullptr;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 yv = __ldg(yb + v), gv = __ldg(gb + v);
+    const uint32_t mb = mb_base ? (uint32_t)__ldg(mb_base + v) : 0u;
+    sy[v] = yv;
+    sg[v] = gv;
+    if (mb_base) sm[v] = (uint8_t)mb;
+    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 yf = unpack_bf16x2(yw[k]), gf = unpack_bf16x2(gw[k]);
+      const float ye[2] = {yf.x, yf.y}, ge[2] = {gf.x, gf.y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * k + e;
+        const bool pos = mb_base ? ((mb >> (2 * k + e)) & 1u) != 0u : fmaf(ye[e], prm[c], prm[C + c]) > 0.f;
+        const float dz = pos ? ge[e] : ge[e] * slope;
+        const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
+        s0[2 * k + e] += dz;
+        s1[2 * k + e] = fmaf(dz, xh, s1[2 * k + e]);
+      }
+    }
+  }
+  // lanes that share a channel group (32 / cvec rows per warp) combine first, then one shared-memory atomic per channel and warp
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float a = s0[k], b = s1[k];
+    for (int o = 16; o >= cvec; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) < cvec) {
+      atomicAdd(red + c0 + k, a);
+      atomicAdd(red + C + c0 + k, b);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, red[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) grid_barrier_arrive_and_wait(reinterpret_cast<unsigned*>(sums + 3 * C), gridDim.x);
+  __syncthreads();
+  const float invM = 1.f / (float)nvox;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const float tot = __ldcg(sums + i);
+    prm[4 * C + i] = tot * invM;
+    if (blockIdx.x == 0) {
+      if (i < C) { if (dbeta) dbeta[i] = tot; }
+      else if (dgamma) dgamma[i - C] = tot;
+    }
+  }
+  __syncthreads();
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4* gyb = gy + row0 * cvec;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 yv = sy[v], gv = sg[v];
+    const uint32_t mb = mb_base ? (uint32_t)sm[v] : 0u;
+    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 yf = unpack_bf16x2(yw[k]), gf = unpack_bf16x2(gw[k]);
+      const float ye[2] = {yf.x, yf.y}, ge[2] = {gf.x, gf.y};
+      float res[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * k + e;
+        const bool pos = mb_base ? ((mb >> (2 * k + e)) & 1u) != 0u : fmaf(ye[e], prm[c], prm[C + c]) > 0.f;
+        const float dz = pos ? ge[e] : ge[e] * slope;
+        const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
+        res[e] = prm[c] * (dz - prm[4 * C + c] - xh * prm[5 * C + c]);
+      }
+      ow[k] = pack_bf16x2(res[0], res[1]);
+      if (want_chsum) {     // sum of the STORED (bf16) gradient: the bias gradient of the convolution in front of this BatchNorm
+        const float2 st = unpack_bf16x2(ow[k]);
+        csum[2 * k] += st.x;
+        csum[2 * k + 1] += st.y;
+      }
+    }
+    gyb[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  if (want_chsum) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = csum[k];
+      for (int o = 16; o >= cvec; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((threadIdx.x & 31) < cvec) atomicAdd(red + 2 * C + c0 + k, a);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(sums + 2 * C + i, red[2 * C + i]);
+  }
+}
+
 __global__ void __launch_bounds__(256) lrelu_bwd_kernel(const uint4* __restrict__ gout, const uint4* __restrict__ outv,
                                                         uint4* __restrict__ gz, long long nvec, float slope, int C,
                                                         float* __restrict__ chsum) {
@@ -381,6 +555,14 @@ __device__ __forceinline__ float adj_weight(int o, int i, float scale, int in) {
   return w;
 }
 
+// exact range of the outputs with a non-zero weight on input index i (adj_range is conservative: up to 4 extra candidates per
+// axis, i.e. 360 instead of ~45 candidate outputs per input voxel for the 6 x 54 x 54 -> 16 x 64 x 64 resize)
+__device__ __forceinline__ void adj_trim(int i, float scale, int in, int out, int& lo, int& hi) {
+  adj_range(i, scale, out, lo, hi);
+  while (lo <= hi && adj_weight(lo, i, scale, in) == 0.f) ++lo;
+  while (hi >= lo && adj_weight(hi, i, scale, in) == 0.f) --hi;
+}
+
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int NC, int Di, int Hi,
                                                            int Wi, int Do, int Ho, int Wo, float sd, float sh, float sw) {
   pdl_enter();
@@ -392,9 +574,9 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
     const int id = (int)(t % Di);
     const long long nc = t / Di;
     int dlo, dhi, hlo, hhi, wlo, whi;
-    adj_range(id, sd, Do, dlo, dhi);
-    adj_range(ih, sh, Ho, hlo, hhi);
-    adj_range(iw, sw, Wo, wlo, whi);
+    adj_trim(id, sd, Di, Do, dlo, dhi);
+    adj_trim(ih, sh, Hi, Ho, hlo, hhi);
+    adj_trim(iw, sw, Wi, Wo, wlo, whi);
     const float* g = gout + nc * (long long)Do * Ho * Wo;
     float acc = 0.f;
     for (int od = dlo; od <= dhi; ++od) {
@@ -945,6 +1127,73 @@ int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_
       reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum ? sums + 2 * C : nullptr,
       reinterpret_cast<const uint8_t*>(mask_bits));
   HPVG_CHECK_LAUNCH("bn_lrelu_bwd_apply");
+  return 0;
+}
+
+
+int hpvg_bn_running_update_batched(int n, float* const* running_mean, float* const* running_var, long long* const* num_batches_tracked,
+                                   const float* const* mean_invstd, const long long* count, const int* C, const float* momentum,
+                                   const float* eps, void* stream) {
+  HPVG_CHECK_ARG(n >= 1 && n <= HPVG_BN_LOG_MAX, "bn_running_update_batched: 1..%d entries per call, got %d", HPVG_BN_LOG_MAX, n);
+  BnRunBatch b;
+  b.n = n;
+  for (int i = 0; i < n; ++i) {
+    HPVG_CHECK_ARG(mean_invstd[i] && C[i] > 0 && C[i] <= 256, "bn_running_update_batched: entry %d: C=%d must be in 1..256", i, C[i]);
+    b.rm[i] = running_mean[i]; b.rv[i] = running_var[i]; b.nbt[i] = num_batches_tracked[i];
+    b.mean_invstd[i] = mean_invstd[i]; b.count[i] = count[i]; b.C[i] = C[i]; b.momentum[i] = momentum[i]; b.eps[i] = eps[i];
+  }
+  launch_k(bn_running_update_kernel, n, 256, 0, ST(stream), b);
+  HPVG_CHECK_LAUNCH("bn_running_update");
+  return 0;
+}
+
+// rows of y / gout (+ mask bytes) a CTA can keep in shared memory: 9C floats of parameters + rows * (2 * 2C + C/8) bytes
+static int bnb_rows_per_cta(long long nvox, int C, int& grid) {
+  const int sms = num_sms();
+  grid = (int)max(1LL, min((long long)sms, cdiv(nvox, 64)));
+  const long long rows = cdiv(nvox, grid);
+  const size_t need = (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8);
+  return need <= (size_t)220 * 1024 ? (int)rows : 0;
+}
+
+int hpvg_bn_lrelu_bwd_fused_supported(long long nvox, int C) {
+  int grid;
+  const int cvec = C / 8;      // lanes that share a channel group combine by shuffles: C / 8 must be a power of two <= 32
+  return (C % 8 == 0 && C >= 8 && C <= 256 && (cvec & (cvec - 1)) == 0 && nvox > 0 && bnb_rows_per_cta(nvox, C, grid) > 0) ? 1 : 0;
+}
+
+int hpvg_bn_lrelu_bwd_fused(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums, void* gy,
+                            float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum, const void* mask_bits,
+                            void* stream) {
+  HPVG_CHECK_ARG(y && gout && scale_shift && mean_invstd && sums && gy, "bn_lrelu_bwd_fused: null tensor");
+  HPVG_CHECK_ARG(hpvg_bn_lrelu_bwd_fused_supported(nvox, C), "bn_lrelu_bwd_fused: %lld voxels x %d channels do not fit the SMs' shared memory", nvox, C);
+  int grid;
+  const int rows = bnb_rows_per_cta(nvox, C, grid);
+  grid = (int)cdiv(nvox, rows);
+  const size_t smem = (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8) + 16;
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (attr_pending(attr_mask)) {
+    cudaError_t e = cudaFuncSetAttribute(bn_lrelu_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) {
+      set_error("bn_lrelu_bwd_fused: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set(attr_mask);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(BNB_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ST(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, bn_lrelu_bwd_fused_kernel, reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift,
+                     mean_invstd, sums, reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum,
+                     reinterpret_cast<const uint8_t*>(mask_bits), rows);
+  HPVG_CHECK_LAUNCH("bn_lrelu_bwd_fused");
   return 0;
 }
 

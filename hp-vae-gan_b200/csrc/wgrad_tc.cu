@@ -16,6 +16,7 @@
 //  * grid = (voxel splits, 64x64 channel blocks, KD); each CTA reduces its bricks into TMEM, then writes one fp32
 //    partial; a second kernel sums the splits in fixed order (deterministic) into PyTorch [Cout][Cin][taps] layout.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hpvg {
 
@@ -39,6 +40,10 @@ struct WgParams {
   int splits;
   float* partial;             // [splits][taps][Cin][Cout] fp32
   long long* dbg;             // optional per-CTA phase clocks (development aid)
+  // in-kernel split-K reduction (kd-stacked kernel): after a grid-wide barrier every CTA sums a slice of the partials over the
+  // splits and writes dw in PyTorch layout — the separate reduction launch and its ~9 us on the stream disappear
+  float* dw;                  // nullptr: the partials are reduced by wgrad_reduce_kernel
+  unsigned* counter;          // zero-initialised arrival counter of the grid barrier
 };
 
 // STAGED (hpvg_set_wgrad_mode(2); measured: drain 9.8 k -> 5.6 k cycles per CTA): the drain writes its partials through a swizzled shared-memory tile so that every
@@ -406,6 +411,37 @@ wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<WG_TMEM_COLS>(tmem_base);
+  if (p.dw != nullptr) {
+    // ===================== split-K reduction inside the launch =====================
+    // every CTA of the grid is resident (at most one per SM, cooperative launch): publish the partials, cross the grid barrier,
+    // then sum a contiguous slice of the [taps][Cin][Cout] result over the splits in split order (deterministic) and write it in
+    // PyTorch's [Cout][Cin][taps] layout.  110 592 outputs over ~141 CTAs: ~1 float4 per thread, 47 L2-resident loads each.
+    __threadfence();
+    __syncthreads();
+    const unsigned nctas = gridDim.x * gridDim.y * gridDim.z;
+    if (threadIdx.x == 0) grid_barrier_arrive_and_wait(p.counter, nctas);
+    __syncthreads();
+    const long long total4 = (long long)g.taps * g.Cin * g.Cout / 4;
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const long long per = (total4 + nctas - 1) / nctas;
+    const long long i_end = min(total4, (long long)(cta + 1) * per);
+    const float4* part4 = reinterpret_cast<const float4*>(p.partial);
+    for (long long i = (long long)cta * per + threadIdx.x; i < i_end; i += WG_THREADS) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int k = 0; k < p.splits; ++k) {
+        const float4 v = __ldcg(part4 + (size_t)k * total4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const long long e = i * 4;
+      const int co = (int)(e % g.Cout);
+      const int ci = (int)((e / g.Cout) % g.Cin);
+      const int tap = (int)(e / ((long long)g.Cout * g.Cin));
+      float* o = p.dw + ((size_t)co * g.Cin + ci) * g.taps + tap;
+      const size_t stride = (size_t)g.Cin * g.taps;
+      o[0] = acc.x; o[stride] = acc.y; o[2 * stride] = acc.z; o[3 * stride] = acc.w;
+    }
+  }
 }
 
 // dw[co][ci][tap] = sum_s partial[s][tap][ci][co]: 4 consecutive co per thread (128-bit loads), splits walked by 4
@@ -481,7 +517,7 @@ size_t wgrad_tc_workspace(const ConvGeom& g) {
     wgrad_plan_kdstack(g, bh, bw, nb, s2, per);
     splits = max(splits, s2);
   }
-  return (size_t)splits * g.taps * g.Cin * g.Cout * sizeof(float);
+  return (size_t)splits * g.taps * g.Cin * g.Cout * sizeof(float) + 256;      // + the grid barrier's counter (fused reduction)
 }
 
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
@@ -499,6 +535,8 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
   }
   p.partial = reinterpret_cast<float*>(workspace);
   p.dbg = debug_clock_buffer();
+  p.dw = nullptr;
+  p.counter = nullptr;
   CUtensorMap mx, mg;
   {
     uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.Wi, (uint64_t)g.Hi, (uint64_t)g.Di, (uint64_t)g.N};
@@ -524,6 +562,30 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
   }
   if (stacked) {
     dim3 grid((unsigned)p.splits, (unsigned)((g.Cin / 64) * (g.Cout / 64)), 3u);
+    static const bool fused_reduce = !(getenv("HPVG_WGRAD_FUSED_REDUCE") && atoi(getenv("HPVG_WGRAD_FUSED_REDUCE")) == 0);
+    const size_t counter_off = (need + 127) & ~(size_t)127;
+    if (fused_reduce && (long long)grid.x * grid.y * grid.z <= num_sms() && ws_bytes >= counter_off + 8) {
+      // one launch: the kernel reduces its own partials after a grid barrier (cooperative: the whole grid is resident)
+      p.dw = dw;
+      p.counter = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(workspace) + counter_off);
+      if (cudaMemsetAsync(p.counter, 0, 8, st) != cudaSuccess) {
+        set_error("wgrad_tc: cannot clear the barrier counter: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(WG_THREADS);
+      cfg.dynamicSmemBytes = WK_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, wgrad_tc_kdstack_kernel, mx, mg, p);
+      HPVG_CHECK_LAUNCH("wgrad_tc_kdstack_kernel (fused reduction)");
+      return 0;
+    }
     launch_k(wgrad_tc_kdstack_kernel, grid, WG_THREADS, WK_SMEM_BYTES, st, mx, mg, p);
     HPVG_CHECK_LAUNCH("wgrad_tc_kdstack_kernel");
   } else {

@@ -46,6 +46,11 @@ PROTOTYPES = {
                                          c_void_p]),
     "hpvg_bn_lrelu_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_longlong, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "hpvg_bn_running_update_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p]),
+    "hpvg_bn_lrelu_bwd_fused_supported": (c_int, [c_longlong, c_int]),
+    "hpvg_bn_lrelu_bwd_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+                                        c_float, c_int, c_void_p, c_void_p]),
     "hpvg_conv_bn_lrelu_fused_supported": (c_int, [c_int] * 8),
     "hpvg_conv_bn_lrelu_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
@@ -122,6 +127,7 @@ OPT_MAX_TENSORS = 32      # HPVG_OPT_MAX_TENSORS: tensors per hpvg_adam_step / h
 OPT_BLOCKS = 16           # HPVG_OPT_BLOCKS: partial sums per tensor
 OPT_STATE_FLOATS = 8
 SN_MAX_LAYERS = 8
+BN_LOG_MAX = 48           # HPVG_BN_LOG_MAX: entries per hpvg_bn_running_update_batched call
 SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the spectral-norm backward
 
 
@@ -136,6 +142,15 @@ def longlong_array(values):
 
 def int_array(values):
     return (c_int * len(values))(*[int(v) for v in values])
+
+
+def float_array(values):
+    return (c_float * len(values))(*[float(v) for v in values])
+
+
+def ptr_array_opt(tensors):
+    """host array of device pointers where entries may be None (NULL)"""
+    return (c_void_p * len(tensors))(*[(None if t is None else t.data_ptr()) for t in tensors])
 
 
 def launch_count():

@@ -215,6 +215,34 @@ def prepack_pairs(weights):
             cache[(True, cin)] = (stamp, r)          # packed_for(w, cin, cout, taps, True, rows=cin): the data-gradient form
 
 
+def prepack_module(module, backward=True):
+    """Bring the cached operand images of every convolution weight of `module` up to date on the CURRENT stream: the bf16
+    [tap][Cout][Cin] image of the tcgen05 layers (and its transposed data-gradient form when `backward`), the 16-row image of the
+    thin-output tails, the float32 filter image of the 3-channel heads.  conv_raw() packs lazily on whatever stream first needs an
+    image and later users take the cached tensor without a stream dependency — fine on one stream, a race when two passes that
+    share weights run on two streams.  hpvg.train.ScaleTrainer calls this before it forks the generator's passes."""
+    if lib.get_conv_backend() == lib.BACKEND_DIRECT:
+        return
+    for w in module.parameters():
+        if w.dim() not in (4, 5) or not w.is_cuda or w.dtype != torch.float32:
+            continue
+        cout, cin = w.shape[0], w.shape[1]
+        taps = _kd_of(w) * 9
+        wc = w            # the Parameter object itself: the cache lives on it (packed_for), the kernels only see its pointer
+        if cin in (64, 128) and cout % 64 == 0:
+            packed_for(wc, cout, cin, taps, False, cout)
+            if backward and w.requires_grad:
+                packed_for(wc, cin, cout, taps, True, cin)
+        elif cin == 64 and cout <= THIN_ROWS:
+            packed_for(wc, cout, cin, taps, False, THIN_ROWS)
+            if backward and w.requires_grad:
+                expand_image_for(wc, cout, taps, True)
+        elif cin <= 4 and cout == 64:
+            expand_image_for(wc, cin, taps, False)
+            if backward and w.requires_grad:
+                packed_for(wc, cin, cout, taps, True, THIN_ROWS)
+
+
 def expand_image_for(w, cin, taps, transposed):
     """float32 [taps][cin][64] filter image for the thin -> wide kernel, cached on the weight like packed_for()"""
     key = ('expand', bool(transposed))
@@ -668,6 +696,7 @@ def deferred_weight(w):
 # them must never be partially resident at the same time: the training iteration serialises the generator's passes (they
 # share BatchNorm buffers), the multi-stream sampler switches the fusion off (fused_bn(False)).
 _FUSED_BN = [os.environ.get('HPVG_FUSED_BN', '1') != '0']
+_FUSED_BN_BWD = [os.environ.get('HPVG_FUSED_BN_BWD', '1') != '0']      # BatchNorm backward: reduce + apply in one launch (grid barrier)
 
 
 class fused_bn:
@@ -691,6 +720,36 @@ def _fused_bn_ok(x, w, pad):
     return bool(lib.load().hpvg_conv_bn_lrelu_fused_supported(n, 64, 64, d, h, wd, 3, int(pad)))
 
 
+_BN_LOG = [None]
+
+
+class bn_stat_log:
+    """`with bn_stat_log() as log:` — BatchNorm blocks inside the block do NOT touch running_mean / running_var /
+    num_batches_tracked; each appends what its update needs to `log.entries`.  `flush_bn_stats(entries)` applies them later, in
+    list order, with one launch.  hpvg.train.ScaleTrainer runs the generator's 'rec' and 'rand' passes on two streams inside two
+    logs and flushes rec + rand in the reference's order."""
+
+    def __init__(self):
+        self.entries = []
+
+    def __enter__(self):
+        self.prev = _BN_LOG[0]
+        _BN_LOG[0] = self
+        return self
+
+    def __exit__(self, *a):
+        _BN_LOG[0] = self.prev
+
+
+def flush_bn_stats(entries):
+    """apply logged running-statistics updates in order (reference semantics of nn.BatchNorm in training mode)"""
+    for i in range(0, len(entries), lib.BN_LOG_MAX):
+        chunk = entries[i:i + lib.BN_LOG_MAX]
+        lib.call("hpvg_bn_running_update_batched", len(chunk), lib.ptr_array_opt([e[0] for e in chunk]), lib.ptr_array_opt([e[1] for e in chunk]),
+                 lib.ptr_array_opt([e[2] for e in chunk]), lib.ptr_array([e[3] for e in chunk]), lib.longlong_array([e[4] for e in chunk]),
+                 lib.int_array([e[5] for e in chunk]), lib.float_array([e[6] for e in chunk]), lib.float_array([e[7] for e in chunk]), _stream())
+
+
 class ConvBnLrelu(Function):
     """ConvBlock3D/2D as ONE autograd node (reference modules/networks_3d.py:48-56).
     forward : conv (+bias) with BatchNorm sums fused into its epilogue -> finalize + normalise + affine + LeakyReLU (1 launch)
@@ -703,6 +762,9 @@ class ConvBnLrelu(Function):
         ctx.token = token
         cout = w.shape[0]
         track = _BN_TRACK[0]
+        log = _BN_LOG[0] if track else None
+        if log is not None:
+            track = False          # the update is logged and applied later, in order (bn_stat_log)
         need_bwd = any(ctx.needs_input_grad[:5])       # all False when the caller runs under no_grad
         mask = None
         if _fused_bn_ok(x, w, pad):
@@ -735,6 +797,8 @@ class ConvBnLrelu(Function):
             lib.call("hpvg_bn_finalize_apply_lrelu", _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean if track else None),
                      _ptr(running_var if track else None), _ptr(nbt if track else None), float(momentum), float(eps), _ptr(scale_shift),
                      _ptr(mean_invstd), _ptr(out), nvox, c, float(slope), _stream())
+        if log is not None:
+            log.entries.append((running_mean, running_var, nbt, mean_invstd, nvox, c, float(momentum), float(eps)))
         ctx.pad, ctx.slope, ctx.c, ctx.nvox, ctx.has_bias = pad, slope, c, nvox, bias is not None
         ctx.save_for_backward(x, w, y, scale_shift, mean_invstd, mask)
         return out
@@ -747,14 +811,20 @@ class ConvBnLrelu(Function):
         c, nvox = ctx.c, ctx.nvox
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
         fuse_gb = want_gb and _chsum_fusable(c)
-        sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
-        lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
-                 float(ctx.slope), _ptr(mask), _stream())
         gy = torch.empty_like(y)
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=y.device)
-        lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
-                 _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _ptr(mask), _stream())
+        if _FUSED_BN_BWD[0] and lib.load().hpvg_bn_lrelu_bwd_fused_supported(nvox, c):
+            # reduce + apply in ONE launch: y and gout are read once into shared memory, the sums cross a grid barrier
+            sums = zeros_small(3 * c + 32, y.device)
+            lib.call("hpvg_bn_lrelu_bwd_fused", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                     _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _ptr(mask), _stream())
+        else:
+            sums = torch.empty((3 * c,), dtype=torch.float32, device=y.device)
+            lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c,
+                     float(ctx.slope), _ptr(mask), _stream())
+            lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                     _ptr(dgamma), _ptr(dbeta), nvox, c, float(ctx.slope), int(fuse_gb), _ptr(mask), _stream())
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = conv_raw(gy, w, None, 2 - ctx.pad, True, is_wide(x))
@@ -765,7 +835,7 @@ class ConvBnLrelu(Function):
             else:
                 gw, _ = wgrad_raw(x, gy, ctx.pad, tuple(w.shape))
         if want_gb:
-            gb = sums[2 * c:] if fuse_gb else channel_sum(gy)
+            gb = sums[2 * c:3 * c] if fuse_gb else channel_sum(gy)
         return gx, gw, gb, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 

@@ -137,6 +137,8 @@ class ScaleTrainer:
         if skip_critic_grads is None:
             skip_critic_grads = os.environ.get('HPVG_SKIP_CRITIC_GRADS', '1') != '0'
         self.skip_critic_grads = bool(skip_critic_grads)
+        # the generator's 'rec' and 'rand' passes on two streams at once (needs `overlap`); HPVG_CONCURRENT_PASSES=0 serialises them
+        self.concurrent_passes = os.environ.get('HPVG_CONCURRENT_PASSES', '1') != '0'
         self._side = self._wside = None
         if self.overlap:
             # parameters receive gradients from nodes on several streams by design; the engine synchronises them
@@ -200,12 +202,17 @@ class ScaleTrainer:
         from modules.losses import kl_criterion
         from modules.utils import calc_gradient_penalty
         side = None
+        rec_log = rand_log = None
         if self.gan and self.overlap and real.is_cuda:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=real.device)
             side, main = self._side, torch.cuda.current_stream()
+            # the two generator passes share every weight: bring the cached operand images up to date HERE, on the main stream,
+            # so that neither pass packs an image the other one reads without a stream dependency (ops.prepack_module)
+            ops.prepack_module(G)
             side.wait_stream(main)
-            with torch.cuda.stream(side):
+            rec_log = ops.bn_stat_log() if self.concurrent_passes else None
+            with torch.cuda.stream(side), (rec_log if rec_log is not None else contextlib.nullcontext()):
                 generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
         else:
             generated, generated_vae, (mu, logvar) = G(real_zero, opt.Noise_Amps, mode="rec")
@@ -217,11 +224,14 @@ class ScaleTrainer:
         else:
             D.zero_grad()
             errD_real = -D(real).mean()
-            if side is not None:
-                # (a third stream for this pass, so that its backward overlaps the fake / gradient-penalty backward, was
-                # measured: no further gain)
+            if side is not None and rec_log is None:
                 torch.cuda.current_stream().wait_stream(side)      # the 'rand' pass shares BatchNorm buffers with 'rec'
-            fake, _ = G(noise_init, opt.Noise_Amps, noise_init=noise_init, mode="rand")
+            # concurrent_passes: the 'rand' pass starts while 'rec' is still running on the side stream.  They share BatchNorm
+            # layers, whose running statistics would be updated by both: each pass logs its updates instead (ops.bn_stat_log) and
+            # one launch applies them in the reference's order — all of 'rec', then all of 'rand' — after the join below.
+            rand_log = ops.bn_stat_log() if rec_log is not None else None
+            with (rand_log if rand_log is not None else contextlib.nullcontext()):
+                fake, _ = G(noise_init, opt.Noise_Amps, noise_init=noise_init, mode="rand")
             errD_fake = D(fake.detach()).mean()
             gradient_penalty = calc_gradient_penalty(D, real, fake, opt.lambda_grad, real.device)
             errD_total = errD_real + errD_fake + gradient_penalty
@@ -230,6 +240,9 @@ class ScaleTrainer:
                 self.allreduce_bytes += self.bucketD.average(list(D.parameters()))
             self.optimizerD.step()
 
+            if rec_log is not None:
+                torch.cuda.current_stream().wait_stream(side)      # join: 'rec' has finished
+                ops.flush_bn_stats(rec_log.entries + rand_log.entries)
             rec_loss = F.mse_loss(generated, real)
             frozen = [p for p in D.parameters() if p.requires_grad] if self.skip_critic_grads else []
             for p in frozen:

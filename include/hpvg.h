@@ -175,6 +175,20 @@ int hpvg_bn_lrelu_bwd_reduce(const void* y, const void* gout, const float* scale
 int hpvg_bn_lrelu_bwd_apply(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd,
                             float* sums, void* gy, float* dgamma, float* dbeta, long long nvox, int C,
                             float slope, int want_chsum, const void* mask_bits, void* stream);
+/* Deferred running-statistics updates: entry i applies running <- (1 - momentum) running + momentum {mean, unbiased var} and
+ * num_batches_tracked += 1 to its layer from the mean_invstd vector the layer's forward saved, entries in call order (several
+ * entries may name the same layer).  Lets passes that share BatchNorm layers run concurrently without racing on the buffers. */
+#define HPVG_BN_LOG_MAX 48
+int hpvg_bn_running_update_batched(int n, float* const* running_mean, float* const* running_var,
+                                   long long* const* num_batches_tracked, const float* const* mean_invstd, const long long* count,
+                                   const int* C, const float* momentum, const float* eps, void* stream);
+/* bn_lrelu_bwd_reduce + bn_lrelu_bwd_apply in ONE launch: y and gout are read once into shared memory, the partial sums cross a
+ * grid-wide barrier, gy is written from shared memory.  `sums`: float32 [3C + 32] ZEROED by the caller ([3C] is the barrier's
+ * arrival counter).  Eligible (.._supported) when nvox * C fits the SMs' shared memory; the two-launch pair covers the rest. */
+int hpvg_bn_lrelu_bwd_fused_supported(long long nvox, int C);
+int hpvg_bn_lrelu_bwd_fused(const void* y, const void* gout, const float* scale_shift, const float* mean_invstd, float* sums,
+                            void* gy, float* dgamma, float* dbeta, long long nvox, int C, float slope, int want_chsum,
+                            const void* mask_bits, void* stream);
 int hpvg_conv_bn_lrelu_fused_supported(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad);
 int hpvg_conv_bn_lrelu_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, int N, int Cin, int Cout,
                              int D, int H, int W, int KD, int pad, float slope, const float* gamma, const float* beta,

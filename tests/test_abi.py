@@ -223,12 +223,13 @@ def test_kernel_selection_rule():
 
 def test_wgrad_workspace_plan():
     """hpvg_conv_wgrad_workspace (host logic): fp32 partials [splits][taps][Cin][Cout] with splits x KD x channel blocks <= 148
-    CTAs, one split per group of bricks; large enough for either weight-gradient kernel form"""
+    CTAs, one split per group of bricks, plus 256 bytes for the arrival counter of the in-kernel reduction's grid barrier; large
+    enough for either weight-gradient kernel form"""
     from hpvg import lib
     ws = lib.load().hpvg_conv_wgrad_workspace
 
     def splits(n, cin, cout, d, h, w, kd, pad):
-        nbytes = ws(n, cin, cout, d, h, w, kd, pad, lib.FMT_NDHWC_BF16, lib.FMT_NDHWC_BF16)
+        nbytes = ws(n, cin, cout, d, h, w, kd, pad, lib.FMT_NDHWC_BF16, lib.FMT_NDHWC_BF16) - 256    # + the grid barrier's counter slot
         per_split = kd * 9 * cin * cout * 4
         assert nbytes % per_split == 0
         return nbytes // per_split

@@ -199,3 +199,43 @@ def test_fused_convblock_against_cpu_reference(vol):
     print("fused vs fp32: out %.2e gx %.2e gw %.2e | two-launch: out %.2e gx %.2e gw %.2e" % (
         rel_err(_to_ncdhw(out), out_ref), rel_err(_to_ncdhw(gx), gx_ref), rel_err(gw.cpu(), gw_ref),
         rel_err(_to_ncdhw(out_u), out_ref), rel_err(_to_ncdhw(gx_u), gx_ref), rel_err(gw_u.cpu(), gw_ref)))
+
+
+@pytest.mark.parametrize("vol,c", [((16, 64, 64), 64), ((6, 54, 54), 64), ((3, 20, 9), 64), ((4, 17, 13), 8), ((2, 9, 11), 128)],
+                         ids=["16x64x64", "6x54x54", "3x20x9", "8ch", "128ch"])
+def test_one_launch_batchnorm_backward_equals_the_two_launch_pair(vol, c):
+    """hpvg_bn_lrelu_bwd_fused (y and gout read once into shared memory, grid barrier) against hpvg_bn_lrelu_bwd_reduce + _apply:
+    same formulas on the same values, so the results agree to fp32 summation order; with and without the sign-bit mask, with the
+    fused bias-gradient sum"""
+    from hpvg import lib
+    from hpvg.ops import _ptr, _stream
+    d, h, w = vol
+    nvox = d * h * w
+    assert lib.load().hpvg_bn_lrelu_bwd_fused_supported(nvox, c) == 1
+    gen = torch.Generator(device='cuda').manual_seed(31)
+    y = torch.randn((nvox, c), device='cuda', generator=gen).bfloat16()
+    gout = torch.randn((nvox, c), device='cuda', generator=gen).bfloat16()
+    scale_shift = torch.cat([1.0 + 0.1 * torch.randn(c, device='cuda', generator=gen), 0.1 * torch.randn(c, device='cuda', generator=gen)])
+    mean_invstd = torch.cat([0.05 * torch.randn(c, device='cuda', generator=gen), 1.0 + 0.1 * torch.rand(c, device='cuda', generator=gen)])
+    for use_mask in (False, True):
+        mask = torch.randint(0, 256, (nvox * c // 8,), device='cuda', dtype=torch.uint8, generator=gen) if use_mask else None
+        res = {}
+        for fused in (False, True):
+            gy = torch.empty_like(y)
+            dgamma, dbeta = torch.empty(c, device='cuda'), torch.empty(c, device='cuda')
+            if fused:
+                sums = torch.zeros(3 * c + 32, device='cuda')
+                lib.call("hpvg_bn_lrelu_bwd_fused", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                         _ptr(dgamma), _ptr(dbeta), nvox, c, 0.2, 1, _ptr(mask), _stream())
+            else:
+                sums = torch.empty(3 * c, device='cuda')
+                lib.call("hpvg_bn_lrelu_bwd_reduce", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), nvox, c, 0.2,
+                         _ptr(mask), _stream())
+                lib.call("hpvg_bn_lrelu_bwd_apply", _ptr(y), _ptr(gout), _ptr(scale_shift), _ptr(mean_invstd), _ptr(sums), _ptr(gy),
+                         _ptr(dgamma), _ptr(dbeta), nvox, c, 0.2, 1, _ptr(mask), _stream())
+            torch.cuda.synchronize()
+            res[fused] = (gy.float(), dgamma.clone(), dbeta.clone(), sums[2 * c:3 * c].clone())
+        a, b = res[True], res[False]
+        assert rel_err(a[1], b[1]) < 1e-4 and rel_err(a[2], b[2]) < 1e-4          # dgamma, dbeta: summation order
+        assert rel_err(a[0], b[0]) < 2e-3                                         # gy: bf16 roundings flipped by 1-ulp mean differences
+        assert (a[3] - b[3]).abs().max().item() <= 2e-3 * b[0].abs().sum(0).max().item() + 1e-3    # bias-gradient sums

@@ -193,9 +193,20 @@ def test_recorded_iteration_equals_the_eager_iteration_and_the_reference(golden)
             # the critic's outputs are means of near-cancelling values (errG ~ 1e-2 here): absolute floor on that scale
             assert abs(a - b) <= 5e-3 * abs(b) + (5e-4 if key.startswith('err') else 1e-5), (it, key, a, b)
         assert abs(hist_r[it]['rec_loss'] - ref[it]['rec_loss']) <= REC_TOL * abs(ref[it]['rec_loss']), (it, hist_r[it], ref[it])
-    for (k, a), (_, b) in zip(g_r.state_dict().items(), g_e.state_dict().items()):
-        if a.is_floating_point():
-            assert (a.float() - b.float()).norm().item() <= 2e-3 * b.float().norm().item() + 1e-6, k
+    sd_r = g_r.state_dict()
+    for (k, a), (_, b) in zip(sd_r.items(), g_e.state_dict().items()):
+        if not a.is_floating_point():
+            continue
+        if k.endswith('conv.bias') and k.replace('conv.bias', 'norm.weight') in sd_r:
+            # a conv bias in front of BatchNorm has a mathematically zero gradient: what reaches Adam is rounding noise, and Adam's
+            # normalised step turns noise of any size into steps of size lr — bounded by lr x iterations, not by the weights' scale
+            assert (a.float() - b.float()).abs().max().item() <= 2.0 * opt_r.lr_g * iters, k
+            continue
+        if k.endswith('norm.running_mean'):
+            # the running mean of conv(x) + bias carries that free-floating bias
+            assert (a.float() - b.float()).abs().max().item() <= 2.0 * opt_r.lr_g * iters + 2e-3 * b.float().abs().max().item(), k
+            continue
+        assert (a.float() - b.float()).norm().item() <= 2e-3 * b.float().norm().item() + 1e-6, k
     for (k, a), (_, b) in zip(d_r.state_dict().items(), d_e.state_dict().items()):
         assert (a.float() - b.float()).norm().item() <= 2e-3 * b.float().norm().item() + 1e-6, k
     tail = [p for p in g_r.body[-1].parameters()][0]
