@@ -3,6 +3,7 @@
 // layout conversion, weight packing and spectral normalisation.  All are one pass over their operands with
 // 128-bit accesses where the layout allows; reductions use warp shuffles and one atomic per warp or block.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hpvg {
 
@@ -320,31 +321,51 @@ __global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(cons
   const long long row0 = (long long)blockIdx.x * rows_per_cta;
   const int rows = (int)max(0LL, min((long long)rows_per_cta, nvox - row0));
   const int nvec = rows * cvec;
-  float* prm = reinterpret_cast<float*>(bnb_smem);                 // scale, shift, mean, invstd [4C]; m0, m1 [2C]; red [3C]
+  const uint32_t mbar = smem_u32(bnb_smem);                        // 16 bytes: the bulk copies' completion barrier
+  float* prm = reinterpret_cast<float*>(bnb_smem + 16);            // scale, shift, mean, invstd [4C]; m0, m1 [2C]; red [3C]
   float* red = prm + 6 * C;
-  uint4* sy = reinterpret_cast<uint4*>(bnb_smem + 9 * C * sizeof(float));
+  uint4* sy = reinterpret_cast<uint4*>(bnb_smem + 16 + 9 * C * sizeof(float));
   uint4* sg = sy + (size_t)rows_per_cta * cvec;
   uint8_t* sm = reinterpret_cast<uint8_t*>(sg + (size_t)rows_per_cta * cvec);
+  const uint4* yb = y + row0 * cvec;
+  const uint4* gb = gout + row0 * cvec;
+  const uint8_t* mb_base = mask ? mask + row0 * cvec : nullptr;
+  // The CTA's rows are contiguous in memory: y and gout arrive as a few 1-D bulk asynchronous copies (cp.async.bulk, at most
+  // 32 KB each) that complete on one mbarrier — every byte of the CTA's 2 x 113 KB is in flight at once.  (Per-thread 16-byte
+  // loads in a loop left one round trip per iteration exposed: 36 k active cycles per launch in ncu for 25 MB of traffic.)
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t bytes = (uint32_t)nvec * 16u;
+    mbar_expect_tx(mbar, 2u * bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = min(32768u, bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sy) + off),
+                   "l"(reinterpret_cast<const uint8_t*>(yb) + off), "r"(n), "r"(mbar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sg) + off),
+                   "l"(reinterpret_cast<const uint8_t*>(gb) + off), "r"(n), "r"(mbar)
+                   : "memory");
+    }
+  }
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     prm[i] = scale_shift[i];
     prm[2 * C + i] = mean_invstd[i];
   }
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  if (mb_base)
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) sm[v] = __ldg(mb_base + v);
+  __syncthreads();          // barrier initialised (thread 0) before anyone waits on it; parameters and mask bytes in place
+  mbar_wait(mbar, 0);
   const int cg = threadIdx.x % cvec;      // blockDim.x is a multiple of cvec: a thread's 8-channel group is fixed
   const int c0 = cg << 3;
   float s0[8], s1[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
-  const uint4* yb = y + row0 * cvec;
-  const uint4* gb = gout + row0 * cvec;
-  const uint8_t* mb_base = mask ? mask + row0 * cvec : nullptr;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    const uint4 yv = __ldg(yb + v), gv = __ldg(gb + v);
-    const uint32_t mb = mb_base ? (uint32_t)__ldg(mb_base + v) : 0u;
-    sy[v] = yv;
-    sg[v] = gv;
-    if (mb_base) sm[v] = (uint8_t)mb;
+    const uint4 yv = sy[v], gv = sg[v];
+    const uint32_t mb = mb_base ? (uint32_t)sm[v] : 0u;
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -953,19 +974,30 @@ struct SnBatch {
   float* scratch[HPVG_SN_MAX_LAYERS];     // K + Cout + 4 floats: v_raw, t_raw, norms
   const float* gw_sn[HPVG_SN_MAX_LAYERS];  // backward only
   float* gw[HPVG_SN_MAX_LAYERS];
+  float* u_saved[HPVG_SN_MAX_LAYERS];      // forward only, may be null: copies of the updated u / v for the backward pass
+  float* v_saved[HPVG_SN_MAX_LAYERS];
   int cout[HPVG_SN_MAX_LAYERS], k[HPVG_SN_MAX_LAYERS];
 };
 
+// v_raw = W^T u: a block owns 64 columns, its four 64-thread groups each walk a quarter of the rows; the quarters are combined in
+// a fixed order (bit-reproducible).  (One thread per column over all rows left 49 blocks on 148 SMs: 15 us per call.)
 __global__ void __launch_bounds__(256) snb_wtu_kernel(const SnBatch b) {
   pdl_enter();
+  __shared__ float part[4][64];
   const int l = blockIdx.y, K = b.k[l], Cout = b.cout[l];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+  const int kc = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int k = blockIdx.x * 64 + kc;
   const float* W = b.w[l];
   const float* u = b.u[l];
   float acc = 0.f;
-  for (int r = 0; r < Cout; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
-  b.scratch[l][k] = acc;
+  if (k < K) {
+    const int per = (Cout + 3) / 4;
+    const int r1 = min(Cout, (rg + 1) * per);
+    for (int r = rg * per; r < r1; ++r) acc = fmaf(W[(size_t)r * K + k], u[r], acc);
+  }
+  part[rg][kc] = acc;
+  __syncthreads();
+  if (rg == 0 && k < K) b.scratch[l][k] = ((part[0][kc] + part[1][kc]) + part[2][kc]) + part[3][kc];
 }
 __global__ void __launch_bounds__(256) snb_wv_kernel(const SnBatch b, int update_uv) {
   pdl_enter();
@@ -991,8 +1023,16 @@ __global__ void __launch_bounds__(256) snb_finalize_kernel(const SnBatch b, int 
     const float nv = fmaxf(sqrtf(sn_norm2_256(v_raw, K, red, &bcast)), eps);
     const float tn = sqrtf(sn_norm2_256(t_raw, Cout, red, &bcast)) / nv;  // || W v ||
     const float nu = fmaxf(tn, eps);
-    for (int k = threadIdx.x; k < K; k += blockDim.x) b.v[l][k] = v_raw[k] / nv;
-    for (int r = threadIdx.x; r < Cout; r += blockDim.x) b.u[l][r] = (t_raw[r] / nv) / nu;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float x = v_raw[k] / nv;
+      b.v[l][k] = x;
+      if (b.v_saved[l]) b.v_saved[l][k] = x;
+    }
+    for (int r = threadIdx.x; r < Cout; r += blockDim.x) {
+      const float x = (t_raw[r] / nv) / nu;
+      b.u[l][r] = x;
+      if (b.u_saved[l]) b.u_saved[l][r] = x;
+    }
     if (threadIdx.x == 0) b.sigma[l][0] = tn * tn / nu;  // u^T (W v)
   } else {
     float acc = 0.f;
@@ -1152,7 +1192,7 @@ static int bnb_rows_per_cta(long long nvox, int C, int& grid) {
   const int sms = num_sms();
   grid = (int)max(1LL, min((long long)sms, cdiv(nvox, 64)));
   const long long rows = cdiv(nvox, grid);
-  const size_t need = (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8);
+  const size_t need = 16 + (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8);
   return need <= (size_t)220 * 1024 ? (int)rows : 0;
 }
 
@@ -1170,7 +1210,7 @@ int hpvg_bn_lrelu_bwd_fused(const void* y, const void* gout, const float* scale_
   int grid;
   const int rows = bnb_rows_per_cta(nvox, C, grid);
   grid = (int)cdiv(nvox, rows);
-  const size_t smem = (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8) + 16;
+  const size_t smem = 16 + (size_t)9 * C * sizeof(float) + (size_t)rows * (4 * C + C / 8) + 16;
   static std::atomic<unsigned long long> attr_mask{0};
   if (attr_pending(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(bn_lrelu_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -1189,7 +1229,8 @@ int hpvg_bn_lrelu_bwd_fused(const void* y, const void* gout, const float* scale_
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool coop = !(getenv("HPVG_FUSED_COOP") && atoi(getenv("HPVG_FUSED_COOP")) == 0);
+  cfg.numAttrs = coop ? 1 : 0;
   cudaLaunchKernelEx(&cfg, bn_lrelu_bwd_fused_kernel, reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(gout), scale_shift,
                      mean_invstd, sums, reinterpret_cast<uint4*>(gy), dgamma, dbeta, nvox, C, slope, want_chsum,
                      reinterpret_cast<const uint8_t*>(mask_bits), rows);
@@ -1402,6 +1443,7 @@ static int sn_fill_batch(SnBatch& b, int n, const int* cout, const int* k, const
     HPVG_CHECK_ARG(cout[l] > 0 && k[l] > 0, "%s: bad shape of layer %d", who, l);
     b.cout[l] = cout[l];
     b.k[l] = k[l];
+    b.u_saved[l] = b.v_saved[l] = nullptr;
   }
   return 0;
 }
@@ -1409,8 +1451,18 @@ static int sn_fill_batch(SnBatch& b, int n, const int* cout, const int* k, const
 int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
                                float* const* w_sn, float* const* scratch, const int* cout, const int* k, int update_uv, float eps,
                                void* stream) {
+  return hpvg_sn_power_iter_batched_ex(n, w_orig, u, v, sigma, w_sn, scratch, cout, k, update_uv, eps, nullptr, nullptr, stream);
+}
+
+int hpvg_sn_power_iter_batched_ex(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
+                                  float* const* w_sn, float* const* scratch, const int* cout, const int* k, int update_uv, float eps,
+                                  float* const* u_saved, float* const* v_saved, void* stream) {
   SnBatch b;
   if (int rc = sn_fill_batch(b, n, cout, k, "sn_power_iter_batched")) return rc;
+  for (int l = 0; l < n; ++l) {
+    b.u_saved[l] = u_saved ? u_saved[l] : nullptr;
+    b.v_saved[l] = v_saved ? v_saved[l] : nullptr;
+  }
   int maxk = 0, maxc = 0;
   long long maxn = 0;
   for (int l = 0; l < n; ++l) {
@@ -1419,7 +1471,7 @@ int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* 
     maxn = max(maxn, (long long)cout[l] * k[l]);
   }
   if (update_uv) {
-    launch_k(snb_wtu_kernel, dim3((unsigned)cdiv(maxk, 256), n), 256, 0, ST(stream), b);
+    launch_k(snb_wtu_kernel, dim3((unsigned)cdiv(maxk, 64), n), 256, 0, ST(stream), b);
     HPVG_CHECK_LAUNCH("snb_wtu");
   }
   launch_k(snb_wv_kernel, dim3(maxc, n), 256, 0, ST(stream), b, update_uv);

@@ -84,6 +84,8 @@ PROTOTYPES = {
     "hpvg_sn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hpvg_sn_power_iter_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_float, c_void_p]),
+    "hpvg_sn_power_iter_batched_ex": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "hpvg_sn_backward_batched": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p]),
     "hpvg_grad_clip_coef": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
@@ -124,7 +126,7 @@ def call(name, *args):
 
 
 OPT_MAX_TENSORS = 32      # HPVG_OPT_MAX_TENSORS: tensors per hpvg_adam_step / hpvg_grad_clip_coef call
-OPT_BLOCKS = 16           # HPVG_OPT_BLOCKS: partial sums per tensor
+OPT_BLOCKS = 64           # HPVG_OPT_BLOCKS: partial sums per tensor
 OPT_STATE_FLOATS = 8
 SN_MAX_LAYERS = 8
 BN_LOG_MAX = 48           # HPVG_BN_LOG_MAX: entries per hpvg_bn_running_update_batched call

@@ -1263,12 +1263,23 @@ class SpectralWeights(Function):
             total += k + c + 4
         scratch_all = torch.empty((total,), dtype=torch.float32, device=dev)
         scratch = [scratch_all[o:] for o in offs]
-        lib.call("hpvg_sn_power_iter_batched", n, lib.ptr_array(ws), lib.ptr_array(us), lib.ptr_array(vs), lib.ptr_array(sig),
-                 lib.ptr_array(outs), lib.ptr_array(scratch), lib.int_array(couts), lib.int_array(ks), int(bool(update_uv)), float(eps),
-                 _stream())
-        # u, v are buffers mutated in place; the backward must see the values used for these sigmas
+        # u, v are buffers mutated in place; the backward must see the values used for these sigmas.  In training mode the
+        # kernel that normalises them writes the copies as well (no clone launches); otherwise they are cloned.
+        if update_uv:
+            saved = torch.empty((sum(couts) + sum(ks),), dtype=torch.float32, device=dev)
+            u_saved, v_saved, off = [], [], 0
+            for c, k in zip(couts, ks):
+                u_saved.append(saved[off:off + c]); off += c
+                v_saved.append(saved[off:off + k]); off += k
+            lib.call("hpvg_sn_power_iter_batched_ex", n, lib.ptr_array(ws), lib.ptr_array(us), lib.ptr_array(vs), lib.ptr_array(sig),
+                     lib.ptr_array(outs), lib.ptr_array(scratch), lib.int_array(couts), lib.int_array(ks), 1, float(eps),
+                     lib.ptr_array(u_saved), lib.ptr_array(v_saved), _stream())
+        else:
+            lib.call("hpvg_sn_power_iter_batched", n, lib.ptr_array(ws), lib.ptr_array(us), lib.ptr_array(vs), lib.ptr_array(sig),
+                     lib.ptr_array(outs), lib.ptr_array(scratch), lib.int_array(couts), lib.int_array(ks), 0, float(eps), _stream())
+            u_saved, v_saved = [u.clone() for u in us], [v.clone() for v in vs]
         ctx.n, ctx.couts, ctx.ks = n, couts, ks
-        ctx.save_for_backward(sigmas, *outs, *[u.clone() for u in us], *[v.clone() for v in vs])
+        ctx.save_for_backward(sigmas, *outs, *u_saved, *v_saved)
         return tuple(outs)
 
     @staticmethod

@@ -296,6 +296,11 @@ int hpvg_sn_backward(const float* gw_sn, const float* w_sn, const float* u, cons
 int hpvg_sn_power_iter_batched(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
                                float* const* w_sn, float* const* scratch, const int* Cout, const int* K, int update_uv,
                                float eps, void* stream);
+/* .._ex: with update_uv, also writes the updated u / v of layer l to u_saved[l] / v_saved[l] (device pointers, arrays or entries
+ * may be NULL): the copies the backward pass needs, without 2 copy launches per layer */
+int hpvg_sn_power_iter_batched_ex(int n, const float* const* w_orig, float* const* u, float* const* v, float* const* sigma,
+                                  float* const* w_sn, float* const* scratch, const int* cout, const int* k, int update_uv,
+                                  float eps, float* const* u_saved, float* const* v_saved, void* stream);
 int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* const* w_sn, const float* const* u,
                              const float* const* v, const float* const* sigma, float* const* gw_orig, float* const* scratch,
                              const int* Cout, const int* K, void* stream);
@@ -318,7 +323,7 @@ int hpvg_sn_backward_batched(int n, const float* const* gw_sn, const float* cons
  *   graph advances it at every replay.
  * ------------------------------------------------------------------------------------------------------------- */
 #define HPVG_OPT_MAX_TENSORS 32
-#define HPVG_OPT_BLOCKS 16
+#define HPVG_OPT_BLOCKS 64
 #define HPVG_OPT_STATE_FLOATS 8
 int hpvg_grad_clip_coef(int n, const float* const* grads, const long long* numel, float* partials, int slot_base,
                         int total_slots, int finalize, float max_norm, float* state, void* stream);

@@ -1,0 +1,106 @@
+"""Multi-GPU modes on real devices: needs >= 2 visible GPUs (skipped otherwise; run with `gpurun --gpus 2`).
+
+Batched-noise data-parallel training: one clip per rank, replicated weights, one NCCL all-reduce (average) of the gradients per
+backward.  The critic has no BatchNorm, so the gradient of the two-clip batch is exactly the mean of the per-clip gradients: the
+averaged gradients a rank holds after the distributed iteration must equal the mean of the gradients two single-GPU iterations
+produce on the two clips, and both ranks must take the same optimizer steps."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    for p in (os.path.join(ROOT, "hp-vae-gan_b200"), ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from helpers import state_d_from, state_from, train_opt_from
+        from hpvg import train
+        from modules import networks_3d
+        fx = torch.load(os.path.join(ROOT, "tests", "golden", "train_gan_tiny.pt"), map_location="cpu", weights_only=False)
+
+        def build(distributed):
+            opt = train_opt_from(fx)
+            g = networks_3d.GeneratorHPVAEGAN(opt)
+            for _ in range(fx['stages']):
+                g.init_next_stage()
+            g.load_state_dict(state_from(fx), strict=True)
+            d = networks_3d.WDiscriminator3D(opt)
+            d.load_state_dict(state_d_from(fx), strict=True)
+            g.to(dev); d.to(dev)
+            return opt, g, d, train.ScaleTrainer(opt, g, d, distributed=distributed)
+
+        dr = fx['draws'][0]
+        draws = [dr['noise_init'], dr['eps_amp'], dr['eps']] + [dr['noises'][l] for l in sorted(dr['noises'])]
+        clips = [(fx['real'] * (1.0 - 0.3 * r) + 0.05 * r, fx['real_zero'] * (1.0 - 0.3 * r) + 0.05 * r) for r in range(world)]
+        # single-GPU iterations on every clip (each rank computes all of them): per-clip critic gradients
+        singles = []
+        for r in range(world):
+            opt_s, g_s, d_s, tr_s = build(False)
+            opt_s.Noise_Amps = list(fx['amps_before']) + [0.1]        # fixed amplitude: the distributed run averages the MSE over ranks
+            feed = train.NoiseFeed(dev)
+            with feed:
+                feed.load(draws, dr['alpha'])
+                tr_s.iterations = 1                                    # skip the amplitude computation (and its eps_amp draw)
+                feed.load([draws[0]] + draws[2:], dr['alpha'])
+                tr_s.iteration(clips[r][0].to(dev), clips[r][1].to(dev))
+            singles.append({k: p.grad.detach().clone() for k, p in d_s.named_parameters()})
+        opt_d, g_d, d_d, tr_d = build(True)
+        opt_d.Noise_Amps = list(fx['amps_before']) + [0.1]
+        feed = train.NoiseFeed(dev)
+        with feed:
+            tr_d.iterations = 1
+            feed.load([draws[0]] + draws[2:], dr['alpha'])
+            tr_d.iteration(clips[rank][0].to(dev), clips[rank][1].to(dev))
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k, p in d_d.named_parameters():
+            mean = sum(s[k] for s in singles) / world
+            err = (p.grad - mean).norm().item() / (mean.norm().item() + 1e-12)
+            worst = max(worst, err)
+        # both ranks took the same steps: weights identical across ranks
+        flat = torch.cat([p.detach().flatten() for p in list(g_d.parameters()) + list(d_d.parameters())])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        spread = max((t - gathered[0]).abs().max().item() for t in gathered)
+        out[rank] = (worst, spread, tr_d.allreduce_bytes_per_iter)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_critic_gradients_equal_the_mean_of_single_gpu_gradients():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = dict(out)
+    print("worst relative error of the averaged critic gradients, weight spread across ranks, all-reduce bytes:", res)
+    assert set(res) == {0, 1}
+    for worst, spread, nbytes in res.values():
+        assert worst < 5e-3, res          # same kernels on the same inputs: atomics' summation order only
+        assert spread == 0.0, res         # identical averaged gradients -> bit-identical steps on every rank
+        assert nbytes > 0

