@@ -416,6 +416,51 @@ def roofline_from(rows, prof_steps, ms_per_step, workload):
                     "graph-replay ms per iteration (the replay overlaps streams, so shares can sum above 1)"}
 
 
+def dependent_chain_leg(dev):
+    """The dominant kernel as it runs inside the recorded iteration: TEN dependent launches of the 64 -> 64 tcgen05 convolution at
+    the finest level's shape (16 x 64 x 64, output of one launch = input of the next, two 8.4 MB tensors ping-pong), recorded into a
+    CUDA graph and timed with ONE CUDA-event pair around the replay.  No per-launch event records between the kernels: the figure
+    is kernel + the dependency gap to the next kernel, the cost a layer has in the benched iteration.  (Per-launch event pairs, the
+    `roofline` object's primary figure, add the front-end latency of an isolated launch: ncu's sm__cycles_active for the same
+    launch is 32.4 k cycles = 16.5 us against 24 us of gpu__time_duration, profiles/r02k_ncu_full_top_kernels.txt.)"""
+    from hpvg import lib, ops
+    d, h, w = 16, 64, 64
+    x = torch.randn(1, d, h, w, 64, device=dev).bfloat16()
+    y = torch.empty_like(x)
+    wt = torch.randn(64, 64, 3, 3, 3, device=dev) * 0.03
+    bias = torch.zeros(64, device=dev)
+    packed = ops.pack_weights(wt, 64, 64, 27, False)
+
+    def chain():
+        for i in range(10):
+            src, dst = (x, y) if i % 2 == 0 else (y, x)
+            lib.call("hpvg_conv_forward", src.data_ptr(), 1, wt.data_ptr(), packed.data_ptr(), bias.data_ptr(), dst.data_ptr(), 1, 1, 64, 64, d, h, w,
+                     3, 1, 0, 1, 0.2, None, None, torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        chain()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        chain()
+    for _ in range(3):
+        gr.replay()
+    ts = []
+    for _ in range(15):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gr.replay(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 100.0)      # ms per 10 launches -> us per launch
+    ts.sort()
+    flops = 2.0 * d * h * w * 64 * 64 * 27
+    us = ts[len(ts) // 2]
+    return {"what": "10 dependent launches of conv_tc_kernel (64 -> 64, 16 x 64 x 64) in one CUDA graph, one event pair around the replay "
+                    "(median of 15); inputs ping-pong between two 8.4 MB tensors, i.e. they come from L2 as inside the iteration",
+            "us_per_launch": us, "tflops": flops / us / 1e6, "flops_per_launch": flops}
+
+
 def parity_leg(leg):
     """The benched path against the CPU oracle: fresh copies of the workload's networks, iteration 0 eagerly (it computes the
     noise amplitude on the host), iteration 1 as the warm-up step of the recording, iteration 2 as ONE REPLAY of the recorded CUDA
@@ -649,6 +694,10 @@ def run_hpvg(args):
     if rank == 0:
         W = leg.W
         roofline = roofline_from(rows, prof_steps, leg.ms / args.steps, args.workload)
+        if roofline is not None and args.workload == "cfg2":
+            chain = dependent_chain_leg(dev)
+            chain["frac_of_peak"] = chain["tflops"] / roofline["peak"]
+            roofline["dependent_chain"] = chain
         line = {"metric": METRIC, "value": leg.value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W + leg.last.get("extra_warmup", 0),
                 "ms_per_step": leg.ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",

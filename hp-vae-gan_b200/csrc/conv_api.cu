@@ -22,6 +22,8 @@ bool wgrad_tc_supported(int x_fmt, int gy_fmt, const ConvGeom& g);
 size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+bool thin_gs_supported(int x_fmt, int y_fmt, const ConvGeom& g);
+int thin_conv_gs(const void* x, const void* w_packed, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
 bool conv_bn_fused_supported(const ConvGeom& g);
 int conv_bn_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, const ConvGeom& g, float slope,
                   const float* gamma, const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,
@@ -80,12 +82,23 @@ int hpvg_conv_forward_ex(const void* x, int x_fmt, const float* w_f32, const voi
   const int backend = conv_backend();
   const bool tc_ok = conv_tc_supported(x_fmt, y_fmt, g, w_packed) &&
                      (y_fmt == HPVG_FMT_NDHWC_BF16 || (act == HPVG_ACT_NONE && !stats && !mask_src));
-  if (backend == HPVG_BACKEND_TCGEN05 && !tc_ok) {
+  // thin_gs.cu takes the packed image with exactly Cout rows per tap; the thin tcgen05 kernel of conv_tc.cu takes 16 rows per tap:
+  // the caller says which one it packed through `transposed` bit 1 (hpvg.ops sets it when it packed for thin_gs)
+  const bool gs_ok = w_packed != nullptr && (transposed & 2) && act == HPVG_ACT_NONE && !stats && !mask_src && thin_gs_supported(x_fmt, y_fmt, g);
+  transposed &= 1;
+  if (backend == HPVG_BACKEND_TCGEN05 && !tc_ok && !gs_ok) {
     set_error("conv_forward: tcgen05 backend required but shape/format unsupported (Cin=%d Cout=%d fmt %d->%d packed=%p)", Cin, Cout,
               x_fmt, y_fmt, w_packed);
     return -1;
   }
   const double flops = 2.0 * g.N * g.Do * g.Ho * g.Wo * (double)g.Cin * g.Cout * g.taps;
+  if (backend != HPVG_BACKEND_DIRECT && gs_ok) {
+    // wide -> thin (64 -> <= 4 channels): one GEMM per input slab + shift-add gather (thin_gs.cu); w_packed = [taps][Cout][64]
+    void* ph = prof_begin(HPVG_PROF_CONV_THIN, flops, st);
+    int rc = thin_conv_gs(x, w_packed, bias, reinterpret_cast<float*>(y), g, st);
+    prof_end(ph, st);
+    return rc;
+  }
   if (tc_ok && backend != HPVG_BACKEND_DIRECT) {
     void* ph = prof_begin(HPVG_PROF_CONV_TC, flops, st);
     int rc = conv_tc(x, w_packed, bias, y, y_fmt, g, act, lrelu_slope, stats, mask_src, st);

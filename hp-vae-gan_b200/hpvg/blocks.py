@@ -124,12 +124,53 @@ def _run_chain(seq, x):
     return x
 
 
-def _run_sn_chain(blocks, x):
-    """a chain of spectral-norm blocks: one batched power iteration for all of them (the layers are independent, as in
-    the reference where every forward pre-hook runs on its own weight), then the convolutions"""
-    blocks = list(blocks)
+def _sn_weights(blocks):
+    """one batched power iteration for all blocks of a spectral-norm chain (the layers are independent, as in the reference where
+    every forward pre-hook runs on its own weight) + the bf16 operand images of W / sigma (forward + data-gradient form)"""
     weights = ops.spectral_weights([b.conv for b in blocks])
-    ops.prepack_pairs(weights)       # one launch for the bf16 operand images of all layers (forward + data-gradient form)
+    ops.prepack_pairs(weights)       # one launch for the bf16 operand images of all layers
+    return weights
+
+
+class sn_prefetch:
+    """Spectral-norm prologues ahead of time.  A critic pass starts with ~50 us of small dependent launches that do not depend on
+    its input: the power iteration of every layer (u, v updated in place: ONE iteration per forward call, exactly as the
+    reference's pre-forward hook), W / sigma, and the operand images.  `sn_prefetch(module_chain, passes, stream)` runs that
+    prologue for the next `passes` forward calls of the chain back to back on `stream` (same order, same arithmetic, same
+    buffers as the calls themselves would) and queues the results; each of those forward calls then waits for its event and
+    consumes its entry.  hpvg.train.ScaleTrainer uses it for the three critic passes of the critic step, whose weights do not
+    change until optimizerD.step()."""
+
+    def __init__(self, owner, blocks, passes, stream):
+        self.owner, self.blocks, self.passes, self.stream = owner, list(blocks), int(passes), stream
+
+    def run(self):
+        queue = []
+        main = torch.cuda.current_stream()
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            for _ in range(self.passes):
+                weights = _sn_weights(self.blocks)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                queue.append((weights, ev))
+        self.owner._sn_queue = queue
+        return self
+
+
+def _run_sn_chain(blocks, x, owner=None):
+    """a chain of spectral-norm blocks: the batched prologue (_sn_weights; taken from the owner's prefetch queue when one is
+    pending), then the convolutions"""
+    blocks = list(blocks)
+    queue = getattr(owner, '_sn_queue', None) if owner is not None else None
+    if queue:
+        weights, ev = queue.pop(0)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for w in weights:
+            w.record_stream(cur)
+    else:
+        weights = _sn_weights(blocks)
     # each block's output feeds exactly the next block, so in the first-order backward the next block's data-gradient launch
     # can apply this block's LeakyReLU derivative (and sum its bias gradient) in its epilogue: see ops.ChainLink
     link = None
@@ -206,9 +247,13 @@ def make_family(dims):
                 self.body.add_module('block%d' % i, _ConvBlockSN(nfc, nfc, opt.ker_size, half, stride=1, bn=True, act='lrelu'))
             self.tail = Conv(nfc, 1, kernel_size=opt.ker_size, padding=1, stride=1)
 
+        def prefetch_spectral_weights(self, passes, stream):
+            """run the spectral-norm prologue of the next `passes` forward calls ahead of time on `stream` (blocks.sn_prefetch)"""
+            return sn_prefetch(self, [self.head] + list(self.body), passes, stream).run()
+
         def forward(self, x):
             _check_device(x)
-            h = _run_sn_chain([self.head] + list(self.body), as5d(x).contiguous())
+            h = _run_sn_chain([self.head] + list(self.body), as5d(x).contiguous(), owner=self)
             out = ops.conv(h, self.tail.weight, self.tail.bias, 1, False)   # thin critic map [N,1,(T,)H,W]
             return like_input(out, dims)
 

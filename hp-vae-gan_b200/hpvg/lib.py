@@ -167,7 +167,7 @@ def get_conv_backend():
     return int(load().hpvg_get_conv_backend())
 
 
-PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow", 6: "conv_bn_fused"}
+PROF_KINDS = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_direct", 3: "wgrad_direct", 4: "conv_expand", 5: "wgrad_narrow", 6: "conv_bn_fused", 7: "conv_thin"}
 
 
 def set_conv_col_mode(mode):

@@ -133,6 +133,10 @@ def _kd_of(weight):
     return 3 if weight.dim() == 5 else 1
 
 
+# GEMM + shift-add kernel for the 64 -> <= 4 channel layers (thin_gs.cu).  OFF by default (HPVG_THIN_GS=1 turns it on): parity-green,
+# but measured on B200 in a dependent chain of 10 launches at 16 x 64 x 64 it takes 14.6 us per launch against 12.3 us for the
+# 16-rows-per-tap tcgen05 kernel — 8 instead of 54 MMAs per slab, but 110 KB of shared-memory traffic per slab for the partial products.
+_THIN_GS = os.environ.get('HPVG_THIN_GS', '0') == '1'
 THIN_ROWS = 16   # rows per tap of the packed weights of the thin-output tcgen05 kernel (Cout <= 16, zero padded)
 
 
@@ -234,13 +238,13 @@ def prepack_module(module, backward=True):
             if backward and w.requires_grad:
                 packed_for(wc, cin, cout, taps, True, cin)
         elif cin == 64 and cout <= THIN_ROWS:
-            packed_for(wc, cout, cin, taps, False, THIN_ROWS)
+            packed_for(wc, cout, cin, taps, False, cout if (_THIN_GS and cout <= 4) else THIN_ROWS)
             if backward and w.requires_grad:
                 expand_image_for(wc, cout, taps, True)
         elif cin <= 4 and cout == 64:
             expand_image_for(wc, cin, taps, False)
             if backward and w.requires_grad:
-                packed_for(wc, cin, cout, taps, True, THIN_ROWS)
+                packed_for(wc, cin, cout, taps, True, cin if _THIN_GS else THIN_ROWS)
 
 
 def expand_image_for(w, cin, taps, transposed):
@@ -289,7 +293,12 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
     do, ho, wo = d + 2 * pad_d - (kd - 1), h + 2 * pad - 2, wd + 2 * pad - 2
     y = _empty(n, cout, do, ho, wo, out_wide, x.device)
     packed = None
-    if _tc_eligible(cin, cout, is_wide(x), out_wide, plain=act_slope is None and stats is None and mask_src is None):
+    plain = act_slope is None and stats is None and mask_src is None
+    thin_gs = (_THIN_GS and plain and is_wide(x) and not out_wide and cin == 64 and cout <= 4
+               and lib.get_conv_backend() != lib.BACKEND_DIRECT)
+    if thin_gs:
+        packed = packed_for(w, cout, cin, taps, transposed, cout)      # [taps][Cout][64]: thin_gs.cu's resident operand tile
+    elif _tc_eligible(cin, cout, is_wide(x), out_wide, plain=plain):
         packed = packed_for(w, cout, cin, taps, transposed, cout if out_wide else THIN_ROWS)
     elif (not is_wide(x)) and out_wide and cin <= 4 and cout == 64 and mask_src is None and lib.get_conv_backend() != lib.BACKEND_DIRECT:
         packed = expand_image_for(w, cin, taps, transposed)
@@ -306,7 +315,7 @@ def conv_raw(x, w, bias, pad, transposed, out_wide, act_slope=None, stats=None, 
         if packed is None:
             raise lib.HpvgError("per-sample statistics need the tcgen05 or the expand kernel (Cin=%d Cout=%d)" % (cin, cout))
     lib.call("hpvg_conv_forward_ex", _ptr(x), fmt_of(x), _ptr(w), _ptr(packed), _ptr(bias), _ptr(y), fmt_of(y), n, cin, cout, d, h, wd,
-             kd, pad, int(transposed), ACT_LRELU if act_slope is not None else ACT_NONE, float(slope), _ptr(stats),
+             kd, pad, int(transposed) | (2 if thin_gs else 0), ACT_LRELU if act_slope is not None else ACT_NONE, float(slope), _ptr(stats),
              int(bool(stats_per_sample)), _ptr(mask_src), _stream())
     return y
 

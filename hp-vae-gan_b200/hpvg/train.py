@@ -139,7 +139,8 @@ class ScaleTrainer:
         self.skip_critic_grads = bool(skip_critic_grads)
         # the generator's 'rec' and 'rand' passes on two streams at once (needs `overlap`); HPVG_CONCURRENT_PASSES=0 serialises them
         self.concurrent_passes = os.environ.get('HPVG_CONCURRENT_PASSES', '1') != '0'
-        self._side = self._wside = None
+        self.sn_prefetch = os.environ.get('HPVG_SN_PREFETCH', '1') != '0'
+        self._side = self._wside = self._snside = None
         if self.overlap:
             # parameters receive gradients from nodes on several streams by design; the engine synchronises them
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -223,6 +224,13 @@ class ScaleTrainer:
             out.update(rec_vae_loss=rec_vae_loss.detach(), kl_loss=kl_loss.detach())
         else:
             D.zero_grad()
+            if side is not None and self.sn_prefetch and hasattr(D, 'prefetch_spectral_weights'):
+                # the three critic passes of this step (real, fake, interpolates) use the same weights: their spectral-norm
+                # prologues (power iteration, W / sigma, operand images: ~50 us of small dependent launches each) run back to back
+                # on a side stream now, off the critical path; each pass picks its own up (blocks.sn_prefetch)
+                if self._snside is None:
+                    self._snside = torch.cuda.Stream(device=real.device)
+                D.prefetch_spectral_weights(3, self._snside)
             errD_real = -D(real).mean()
             if side is not None and rec_log is None:
                 torch.cuda.current_stream().wait_stream(side)      # the 'rand' pass shares BatchNorm buffers with 'rec'

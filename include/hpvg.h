@@ -53,6 +53,7 @@ long long hpvg_launch_count(void);
 #define HPVG_PROF_CONV_EXPAND 4
 #define HPVG_PROF_WGRAD_NARROW 5
 #define HPVG_PROF_CONV_BN_FUSED 6
+#define HPVG_PROF_CONV_THIN 7
 /* development aid: when set (device pointer to >= 8 * grid int64), the tcgen05 kernels write per-CTA phase clocks */
 int hpvg_debug_set_clock_buffer(long long* device_buffer);
 int hpvg_profile_enable(int on);
@@ -93,7 +94,11 @@ int hpvg_conv_kernel_choice(int N, int Cin, int Cout, int D, int H, int W, int K
  * Output extent per filtered axis = input extent + 2*pad - 2.  D is not filtered when KD == 1.
  * `w_f32` is the float32 master weight in PyTorch layout; `w_packed` (may be NULL) is the bf16 image produced by
  * hpvg_pack_weights for the same `transposed` flag, required for the tcgen05 path (NDHWC_BF16 input with Cin in
- * {64, 128}; NDHWC_BF16 output with Cout a multiple of 64, or NCDHW_F32 output with Cout <= 16 and Cin == 64, bias only).  `bias` may be NULL.  `stats` (may be NULL) is a float32 [2*Cout] accumulator that
+ * {64, 128}; NDHWC_BF16 output with Cout a multiple of 64, or NCDHW_F32 output with Cout <= 16 and Cin == 64, bias only).
+ * transposed bit 1 (value 2, with or without bit 0): `w_packed` was packed with exactly Cout rows per tap
+ * (hpvg_pack_weights(rows = Cout), image [taps][Cout][64]) for a 64 -> <= 4 channel layer with NCDHW_F32 output: the layer then
+ * runs as one GEMM per input slab + a shift-add gather (thin_gs.cu) instead of the 16-rows-per-tap tcgen05 thin kernel.
+ * `bias` may be NULL.  `stats` (may be NULL) is a float32 [2*Cout] accumulator that
  * receives += per-channel sum and sum of squares of the *stored* output (BatchNorm batch statistics,
  * aten::native_batch_norm's reduction, fused into the conv epilogue); the caller zeroes it.
  * `mask_src` (may be NULL; NDHWC_BF16, same extents as y) multiplies the result by the LeakyReLU derivative of that

@@ -25,6 +25,7 @@ BF16_TOL = 2e-2
 # LRELU_GRAD_TOL, and the bar against the oracle's bf16 storage emulation — which
 # stores the same values and therefore reads the same signs — is EMU_BWD_TOL.
 LRELU_GRAD_TOL = 5e-2
+FUSED_GRAD_TOL = 3.5e-2     # the one-launch ConvBlock3D (fp32 statistics and sign): the bf16-operand floor, see test_convblock3d_layer
 F32_TOL = 1e-3
 EMU_FWD_TOL = 5e-4     # one layer vs the oracle with bf16 storage emulation: what is left is fp32 summation order
 EMU_BWD_TOL = 3e-3
@@ -89,8 +90,15 @@ def test_convblock3d_layer(cin, cout, shape):
     assert y.shape == y_ref.shape and y.dtype == torch.float32
     assert rel_err(y, y_ref) < BF16_TOL
     y.backward(g.cuda())
-    assert rel_err(x_gpu.grad, x_ref.grad) < LRELU_GRAD_TOL
-    _compare_grads(m, sd)
+    # 64 -> 64 3-D blocks run as ONE launch that takes BatchNorm statistics and the LeakyReLU sign from the fp32 accumulators
+    # (hpvg_conv_bn_lrelu_fused); the other blocks read the sign of a bf16-stored value.  What is left for the fused layer is the
+    # floor of bf16 OPERANDS: rounding weights and inputs to bf16 moves every pre-activation by ~3e-3 sigma, which flips the
+    # sign of a fraction f ~ 2.4e-3 of them, and each flip changes that gradient element by 0.8 |g|: sqrt(f) * 0.8 = 2-3e-2 in
+    # relative L2 (measured 2.8e-2 here; 2.3e-3 when the operands are bf16-representable, tests/test_gpu_fullsize.py).
+    tol = FUSED_GRAD_TOL if (cin == 64 and cout == 64) else LRELU_GRAD_TOL
+    print("ConvBlock3D %d -> %d %s: input-gradient error vs fp32 %.2e (bar %.0e)" % (cin, cout, shape, rel_err(x_gpu.grad, x_ref.grad), tol))
+    assert rel_err(x_gpu.grad, x_ref.grad) < tol
+    _compare_grads(m, sd, tol)
     for k in ('norm.running_mean', 'norm.running_var'):
         assert rel_err(dict(m.named_buffers())[k], sd[k]) < 1e-3, k
     assert int(m.norm.num_batches_tracked.item()) == 1

@@ -216,6 +216,60 @@ def test_recorded_iteration_equals_the_eager_iteration_and_the_reference(golden)
     assert float(rec.optimizerD.state[next(d_r.parameters())]['step']) == float(iters)
 
 
+def test_multi_stream_iteration_equals_the_single_stream_iteration(golden):
+    """Race canary (compute-sanitizer is closed on this pool): the iteration as hpvg.train.ScaleTrainer schedules it — generator
+    'rec' and 'rand' passes on two streams with logged BatchNorm statistics, weight gradients and spectral-norm prologues on side
+    streams — against the same iteration on ONE stream (overlap=False), from identical weights and draws, for several iterations
+    on the 64-channel fixture.  A missing stream dependency shows up as a difference far above the atomics' noise."""
+    from hpvg import train
+    from modules import networks_3d
+    fx = golden("train_gan_wide")
+    real, real_zero = fx['real'].cuda(), fx['real_zero'].cuda()
+    runs = {}
+    for overlap in (True, False):
+        opt = train_opt_from(fx)
+        g = networks_3d.GeneratorHPVAEGAN(opt)
+        for _ in range(fx['stages']):
+            g.init_next_stage()
+        g.load_state_dict(state_from(fx), strict=True)
+        g.cuda()
+        d = networks_3d.WDiscriminator3D(opt)
+        d.load_state_dict(state_d_from(fx), strict=True)
+        d.cuda()
+        tr = train.ScaleTrainer(opt, g, d, overlap=overlap)
+        feed = train.NoiseFeed(real.device)
+        hist = []
+        with feed:
+            for it in range(fx['iters']):
+                feed.load(_draw_list(fx['draws'][it]), fx['draws'][it]['alpha'])
+                hist.append({k: v.item() for k, v in tr.iteration(real, real_zero).items()})
+        torch.cuda.synchronize()
+        runs[overlap] = (hist, {k: v.detach().float().clone() for k, v in list(g.state_dict().items()) + [('D.' + k, v) for k, v in d.state_dict().items()]})
+    # Iterations 0 and 1 are held tight: a missing dependency (a stale operand image, a statistic read before it is complete) shows
+    # there already, because the weights change after iteration 0.  From iteration 2 on the two schedules are two realisations of
+    # the same chaotic process (atomics' summation order differs with the schedule, Adam's first steps are sign-like): measured
+    # 1.2 % on errG = -D(fake).mean() at iteration 2, the scale of the run-to-run scatter of ONE schedule (CHAOTIC above).
+    for it, (a, b) in enumerate(zip(runs[True][0], runs[False][0])):
+        for key in ('rec_loss', 'gradient_penalty', 'errD_real', 'errD_fake', 'errG'):
+            if it < 2:
+                tol = 5e-3 * abs(b[key]) + 5e-4
+            else:
+                tol = (3e-2 * abs(b[key]) + 2e-3) if key.startswith('err') else 1e-2 * abs(b[key]) + 5e-4
+            assert abs(a[key] - b[key]) <= tol, (it, key, a[key], b[key])
+    for k, b in runs[False][1].items():
+        a = runs[True][1][k]
+        if not a.is_floating_point():
+            assert torch.equal(a, b), k
+            continue
+        if 'running_' in k:
+            # statistics of activations downstream of weights that two chaotic trajectories have moved apart (every schedule is
+            # ~1 % from the fp32 oracle on these after 2 iterations, experiments/bn_stats_diag.py)
+            assert (a - b).abs().max().item() <= 3e-2 * b.abs().max().item() + 1e-3, k
+            continue
+        # an entry whose gradient sign differs between the two schedules moves lr the other way at every step: 2 x lr x iterations
+        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 2.0 * 5e-4 * fx['iters'], k
+
+
 def test_config2_iteration_against_the_oracle():
     """BASELINE configs[1] at full size — 5 pyramid levels, 64 channels, finest level 16 x 64 x 64 — two iterations of the loop of
     train_video.py:126-202 on the CUDA path against oracle/train_ref.py (fp32, CPU) on identical weights and draws: the
