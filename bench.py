@@ -742,6 +742,112 @@ def run_hpvg(args):
         os._exit(0)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# the other single-GPU BASELINE configurations: configs[0] (train_image.py, 2-D, 128 px) and configs[2] (train_video_baselines.py,
+# GeneratorSG).  Same metric (finest-level training iterations/s), value + e2e only.
+# ---------------------------------------------------------------------------------------------------------------
+def run_other(args):
+    from hpvg import lib, train
+    from hpvg.options import Options
+    from modules import networks_2d, networks_3d
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise RuntimeError("--workload %s is a single-GPU configuration" % args.workload)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    lib.load()
+    torch.manual_seed(0)
+    W = max(3, args.warmup)
+    if args.workload == "cfg1":
+        o = Options(img_size=128, vae_levels=3, nfc=64, latent_dim=128, num_layer=5, batch_size=1)
+        o.scale_idx = o.stop_scale
+        o.Noise_Amps = [1.0] + [0.07] * (o.stop_scale - 1)
+        _, h0, w0 = o.level_size(0)
+        _, h, w = o.level_size(o.scale_idx)
+        o.Z_init_size = [1, o.latent_dim, h0, w0]
+        G = networks_2d.GeneratorHPVAEGAN(o)
+        for _ in range(o.scale_idx):
+            G.init_next_stage()
+        D = networks_2d.WDiscriminator2D(o)
+        G.to(dev); D.to(dev)
+        gen = torch.Generator().manual_seed(0)
+        real_h = (torch.rand((1, 3, h, w), generator=gen) * 2 - 1).pin_memory()
+        second_h = (torch.rand((1, 3, h0, w0), generator=gen) * 2 - 1).pin_memory()
+        tr = train.ScaleTrainer(o, G, D, capturable=True, dims=2)
+        c0 = lib.launch_count()
+        tr.capture(real_h.to(dev), second_h.to(dev), warmup=W)
+        per_iter = (lib.launch_count() - c0) // (W + 1)
+        for _ in range(2):
+            tr.replay()
+        last = {}
+
+        def step():
+            tr.replay()
+
+        def step_e2e():
+            last["rec_loss"] = tr.replay(real_h, second_h)["rec_loss"].item()
+        name = ("configs[0]: train_image.py 2D HP-VAE-GAN, synthetic 3-channel 128px image, vae-levels 3, nfc 64, finest level %d of %d "
+                "(GAN), batch 1" % (o.scale_idx, o.stop_scale))
+        gflop, launch = 181.05, "one CUDA graph replay per iteration (%d libhpvg kernels recorded)" % per_iter
+    else:
+        o = Options(img_size=64, sampling_rates=[5, 3, 1], nfc=64, num_layer=5, batch_size=1, train_depth=1)
+        o.scale_idx = o.stop_scale
+        o.Noise_Amps = [1.0] + [0.07] * (o.stop_scale - 1)
+        t0, h0, w0 = o.level_size(0)
+        t, h, w = o.level_size(o.scale_idx)
+        G = networks_3d.GeneratorSG(o)
+        for _ in range(o.scale_idx):
+            G.init_next_stage()
+        D = networks_3d.WDiscriminator3D(o)
+        G.to(dev); D.to(dev)
+        gen = torch.Generator().manual_seed(0)
+        real_h = (torch.rand((1, 3, t, h, w), generator=gen) * 2 - 1).pin_memory()
+        second_h = torch.randn((1, 3, t0, h0, w0), generator=gen).pin_memory()        # opt.Z_init (train_video_baselines.py:38-43)
+        tr = train.BaselineTrainer(o, G, D)
+        real, z_init = real_h.to(dev), second_h.to(dev)
+        for _ in range(W):
+            tr.iteration(real, z_init)
+        last = {}
+        c0 = lib.launch_count()
+        tr.iteration(real, z_init)
+        per_iter = lib.launch_count() - c0
+
+        def step():
+            tr.iteration(real, z_init)
+
+        def step_e2e():
+            last["rec_loss"] = tr.iteration(real_h.to(dev, non_blocking=True), z_init)["rec_loss"].item()
+        name = ("configs[2]: train_video_baselines.py GeneratorSG (SinGAN-3D), train-depth 1, synthetic 16-frame 64x64 clip, rates 5 3 1, "
+                "finest level %d of %d, batch 1" % (o.scale_idx, o.stop_scale))
+        gflop, launch = 2090.59, "eager launches (%d libhpvg kernels per iteration; this loop has no recorded-graph form)" % per_iter
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(step, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    value = args.steps / (ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": name, "parallelism": "single GPU", "conv_gflop_per_iter": gflop, "launch": launch,
+                       "l2": "no explicit flush: the iteration's working set exceeds the 126 MB L2" if args.workload == "cfg3" else
+                             "no explicit flush (2-D working set: tens of MB)"},
+            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": real_h.numel() * 4 + (second_h.numel() * 4 if args.workload == "cfg1" else 0),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": per_iter * args.steps, "clocks": clocks, "roofline": None, "model_tflops": value * gflop / 1e3}
+    _emit(line)
+
+
 _REAL_STDOUT = [None]
 
 
@@ -773,8 +879,9 @@ def main():
                     help="record the iteration this many times and keep the recording that replays fastest (ScaleTrainer.capture)")
     ap.add_argument("--recapture", type=int, default=0, help="diagnostic: re-record the iteration this many times and time each recording")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the recorded iteration")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
-                    help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5", "cfg1", "cfg3"],
+                    help="cfg2 = BASELINE configs[1] (16 x 64 x 64, the metric's configuration); cfg5 = configs[4] (32 x 128 x 128); "
+                         "cfg1 = configs[0] (2-D, 128 px); cfg3 = configs[2] (GeneratorSG baseline): value + e2e only")
     args = ap.parse_args()
     WORKLOAD["name"] = args.workload
     # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version
@@ -784,6 +891,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("cfg1", "cfg3"):
+        run_other(args)
     else:
         run_hpvg(args)
 
