@@ -266,8 +266,11 @@ def test_multi_stream_iteration_equals_the_single_stream_iteration(golden):
             # ~1 % from the fp32 oracle on these after 2 iterations, experiments/bn_stats_diag.py)
             assert (a - b).abs().max().item() <= 3e-2 * b.abs().max().item() + 1e-3, k
             continue
+        if k.endswith('conv.bias') and k.replace('conv.bias', 'norm.weight') in runs[False][1]:
+            continue      # a conv bias in front of BatchNorm has a zero gradient: Adam turns its rounding noise into a random walk
         # an entry whose gradient sign differs between the two schedules moves lr the other way at every step: 2 x lr x iterations
-        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 2.0 * 5e-4 * fx['iters'], k
+        # (+ the same again for the second moment's normalisation early in training)
+        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 4.0 * 5e-4 * fx['iters'], k
 
 
 def test_config2_iteration_against_the_oracle():
