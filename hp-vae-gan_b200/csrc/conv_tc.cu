@@ -21,6 +21,21 @@
 #include <cstdlib>
 #include <type_traits>
 
+#ifndef HPVG_ROLL_STACK
+#define HPVG_ROLL_STACK 1      // rolled (kh, kw) issue loops: see the MMA issuer
+#endif
+// The thin-output instantiations (NOUT = 16) keep the fully unrolled issue path: with the rolled loop the batched generation leg
+// (two recorded forwards in flight on two streams, conv_col running next to the thin kernel) hit "illegal memory access" once in
+// ~10 rounds of experiments/gen_stress.py, every time; with the thin kernels unrolled (this switch) 4 x 40 rounds on 2 and 3
+// streams were clean, as were the fully unrolled builds.  The cause was not found (no sanitizer on this pool); the wide kernels
+// are the ones that matter for time (110 of the ~125 tcgen05 convolution launches of an iteration).
+#ifndef HPVG_ROLL_WIDE_ONLY
+#define HPVG_ROLL_WIDE_ONLY 1
+#endif
+#ifndef HPVG_ROLL_PLAIN
+#define HPVG_ROLL_PLAIN 1
+#endif
+
 namespace hpvg {
 
 constexpr int BH = 16, BW = 8;                      // output brick rows x columns (M = 128)
@@ -301,17 +316,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int d = d0 + j - g.pad_d;
             if (d >= 0 && d < g.Di) svalid |= 1u << j;
           }
+          // The issue code is kept SMALL on purpose: the (kh, kw) loop is rolled (one peeled first position for the
+          // "first touch" logic + one body of 4 k-steps x NACC+2 slabs executed eight times).  Fully unrolled it was ~50 KB of
+          // straight-line SASS per instantiation that one thread walks through once per unit — inside the iteration, where other
+          // kernels run in between, every launch then paid the instruction-cache misses of its whole issue path.
           auto run = [&](auto full_tag, auto grp_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             constexpr int GRP = decltype(grp_tag)::value;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-              const int kh = q / 3, kw = q % 3;
+            auto position = [&](auto first_tag, const uint32_t tapoff) {      // tapoff = ((kh * SLAB_W + kw) * 128) >> 4
+              constexpr bool FIRST = decltype(first_tag)::value;
               if (p.dbg) t_bwait -= clock64();
               mbar_wait(bar_b_full(bstage), bphase);
               if (p.dbg) t_bwait += clock64();
               tc_fence_after();
               const uint64_t bs = b_base + (uint64_t)((bstage * Cfg::STAGE_BYTES) >> 4);
+              const uint64_t aq = a_base + (uint64_t)tapoff;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -321,8 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                   const int a_hi = FULL ? (j < g_hi ? j : g_hi) : min(min(j, g_hi), amax - 1);
                   const int klo = j - a_hi, n = a_hi - a_lo + 1;
                   if (n <= 0 || !((svalid >> j) & 1u)) continue;
-                  const uint64_t ad = a_base + (uint64_t)((j * SLAB_STRIDE + (kh * SLAB_W + kw) * 128 + ks * 32) >> 4);
-                  if (q == 0 && ks == 0) {
+                  const uint64_t ad = aq + (uint64_t)((j * SLAB_STRIDE + ks * 32) >> 4);
+                  if (FIRST && ks == 0) {
                     // first touch: one MMA per accumulator so that each gets its own "overwrite" flag
                     if (!((waited >> j) & 1u)) {
                       if (p.dbg) t_swait -= clock64();
@@ -357,6 +376,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               }
               umma_commit(bar_b_empty(bstage));
               if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
+            };
+            position(std::true_type{}, 0u);
+            uint32_t kh = 0, kw = 0;
+            constexpr int QUNROLL = (HPVG_ROLL_STACK && !(HPVG_ROLL_WIDE_ONLY && Cfg::THIN)) ? 1 : 8;
+#pragma unroll QUNROLL
+            for (int q = 1; q < 9; ++q) {
+              if (++kw == 3) { kw = 0; ++kh; }
+              position(std::false_type{}, (kh * SLAB_W + kw) * 8u);
             }
           };
           if (amax == NACC) {
@@ -414,9 +441,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
             if (p.dbg) t_swait += clock64();
             tc_fence_after();
+            // rolled over the nine (kh, kw) positions: small issue code (see the stacked form above)
+            uint32_t tapoff = 0, kwc = 0;      // ((kh * SLAB_W + kw) * 128) >> 4
+#if HPVG_ROLL_PLAIN
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int q = 0; q < 9; ++q) {
-              const int kh = q / 3, kw = q % 3;
+              const uint64_t aq = a_base + (uint64_t)tapoff;
+              if (++kwc == 3) { kwc = 0; tapoff += (SLAB_W - 2) * 8u; } else tapoff += 8u;
 #pragma unroll
               for (int kc = 0; kc < KCHUNKS; ++kc) {
                 if (p.dbg) t_bwait -= clock64();
@@ -427,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
                 for (int a = grp * GACC; a < (grp + 1) * GACC; ++a) {
                   if (!((amask >> a) & 1u)) continue;
-                  const uint64_t ad = a_base + (uint64_t)((((a + kd) * KCHUNKS + kc) * SLAB_STRIDE + (kh * SLAB_W + kw) * 128) >> 4);
+                  const uint64_t ad = aq + (uint64_t)((((a + kd) * KCHUNKS + kc) * SLAB_STRIDE) >> 4);
                   const uint32_t tacc = tmem_base + acc_col(a);
                   umma_bf16(tacc, ad, bd, IDESC, (touched >> a) & 1u);
                   umma_bf16_acc(tacc, ad + 2, bd + 2, IDESC);
@@ -473,6 +507,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int amax = min(NACC, g.Do - d0);
     float* csum = reinterpret_cast<float*>(sgen + Cfg::OFF_B);      // [128] channel sums of this CTA, then [128] scale | shift
     float* ss = csum + 128;
+    // per-channel parameters the finalize step needs: fetched now, while the MMAs run, instead of as exposed global round trips
+    // behind the grid barrier (where every CTA of the grid would wait for them)
+    float gam = 0.f, bet = 0.f, rmean = 0.f, rvar = 0.f;
+    if (et < 64) {
+      gam = p.gamma[et];
+      bet = p.beta[et];
+      if (blockIdx.x == 0) {
+        if (p.running_mean) rmean = p.running_mean[et];
+        if (p.running_var) rvar = p.running_var[et];
+      }
+    }
     mbar_wait(bar_acc_full, 0);       // every MMA of the unit has completed: slabs and weight ring are dead from here on
     tc_fence_after();
     if (et < 128) csum[et] = 0.f;
@@ -527,8 +572,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       double var = (double)__ldcg(p.stats + 64 + c) * inv - mean * mean;
       if (var < 0.0) var = 0.0;
       const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
-      const float sc = p.gamma[c] * invstd;
-      const float sh = p.beta[c] - (float)mean * sc;
+      const float sc = gam * invstd;
+      const float sh = bet - (float)mean * sc;
       ss[c] = sc;
       ss[64 + c] = sh;
       if (blockIdx.x == 0) {
@@ -536,10 +581,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         p.scale_shift[64 + c] = sh;
         p.mean_invstd[c] = (float)mean;
         p.mean_invstd[64 + c] = invstd;
-        if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+        if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * rmean + p.momentum * (float)mean;
         if (p.running_var) {
           const double unbiased = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
-          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+          p.running_var[c] = (1.f - p.momentum) * rvar + p.momentum * (float)unbiased;
         }
         if (c == 0 && p.nbt) p.nbt[0] += 1;
       }
@@ -609,6 +654,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const bool row_ok = (oh < g.Ho) && (ow < g.Wo);
       const bool brick_full = (h0 + BH <= g.Ho) && (w0 + BW <= g.Wo);
       float st_s = 0.f, st_s2 = 0.f;     // BatchNorm sums of this unit: channel (et & 63), row group (et >> 6)
+      // LeakyReLU'-mask epilogue (data gradients): the sign bits of this thread's row are fetched NOW, while the MMAs of the unit
+      // run and the epilogue warps have nothing to do — one register per accumulator.  Read after the accumulators were complete,
+      // each of the unit's accumulators paid an exposed global round trip (4 x ~1 k cycles of a 6 k-cycle epilogue).
+      uint32_t mbits[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) mbits[a] = 0xffffffffu;
+      if (p.mask_src && row_ok) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const int od = d0 + a;
+          if (od >= g.Do) continue;
+          const uint4* mp = reinterpret_cast<const uint4*>(
+              p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64 + ch * CPT);
+          uint4 mv[CPT / 8];
+#pragma unroll
+          for (int c = 0; c < CPT / 8; ++c) mv[c] = __ldg(mp + c);
+          uint32_t b = 0;
+#pragma unroll
+          for (int c = 0; c < CPT / 8; ++c) {
+            const uint32_t wds[4] = {mv[c].x, mv[c].y, mv[c].z, mv[c].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack_bf16x2(wds[k]);
+              b |= (f.x > 0.f ? 1u : 0u) << (8 * c + 2 * k);
+              b |= (f.y > 0.f ? 1u : 0u) << (8 * c + 2 * k + 1);
+            }
+          }
+          mbits[a] = b;
+        }
+      }
 #pragma unroll 1
       for (int grp = 0; grp < NGRP; ++grp) {
         long long tq = clock64();
@@ -644,18 +719,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               v[4 * j + 0] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
             }
           }
-          if (p.mask_src && row_ok) {
-            const uint4* mp = reinterpret_cast<const uint4*>(
-                p.mask_src + ((((size_t)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.Cout + nb * 64 + ch * CPT);
+          if (p.mask_src) {
+            uint32_t mb = 0xffffffffu;
 #pragma unroll
-            for (int c = 0; c < CPT / 8; ++c) {
-              uint4 mv = __ldg(mp + c);
-              float2 f;
-              f = unpack_bf16x2(mv.x); v[8 * c + 0] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 1] *= f.y > 0.f ? 1.f : p.slope;
-              f = unpack_bf16x2(mv.y); v[8 * c + 2] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 3] *= f.y > 0.f ? 1.f : p.slope;
-              f = unpack_bf16x2(mv.z); v[8 * c + 4] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 5] *= f.y > 0.f ? 1.f : p.slope;
-              f = unpack_bf16x2(mv.w); v[8 * c + 6] *= f.x > 0.f ? 1.f : p.slope; v[8 * c + 7] *= f.y > 0.f ? 1.f : p.slope;
-            }
+            for (int k = 0; k < NACC; ++k)
+              if (k == a) mb = mbits[k];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) v[j] *= ((mb >> j) & 1u) ? 1.f : p.slope;
           }
           if (p.act == HPVG_ACT_LRELU) {
 #pragma unroll

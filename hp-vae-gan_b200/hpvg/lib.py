@@ -4,7 +4,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libhpvg.so")
+# HPVG_LIB: another build of the same library (A/B runs of two kernel versions); there is still no fallback
+LIB_PATH = os.environ.get("HPVG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libhpvg.so")
 
 FMT_NCDHW_F32 = 0
 FMT_NDHWC_BF16 = 1
