@@ -195,15 +195,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 
   // unit -> coordinates
-  auto decode = [&](long long u, int& nb, int& n, int& d0, int& h0, int& w0) {
-    w0 = (int)(u % p.units_w) * BW;
-    u /= p.units_w;
-    h0 = (int)(u % p.units_h) * BH;
-    u /= p.units_h;
-    d0 = (int)(u % p.units_d) * NACC;
-    u /= p.units_d;
-    n = (int)(u % g.N);
-    nb = (int)(u / g.N);
+  // 32-bit arithmetic on purpose (the host checks num_units < 2^31): 64-bit division is a subroutine of dozens of instructions, and
+  // the producer decodes its unit before it can issue the first load
+  auto decode = [&](long long u64, int& nb, int& n, int& d0, int& h0, int& w0) {
+    unsigned u = (unsigned)u64;
+    unsigned q = u / (unsigned)p.units_w;
+    w0 = (int)(u - q * (unsigned)p.units_w) * BW;
+    u = q;
+    q = u / (unsigned)p.units_h;
+    h0 = (int)(u - q * (unsigned)p.units_h) * BH;
+    u = q;
+    q = u / (unsigned)p.units_d;
+    d0 = (int)(u - q * (unsigned)p.units_d) * NACC;
+    u = q;
+    q = u / (unsigned)g.N;
+    n = (int)(u - q * (unsigned)g.N);
+    nb = (int)q;
   };
 
   if (warp == 0) {
@@ -862,6 +869,10 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const CUtenso
   p.units_w = (int)cdiv(g.Wo, BW);
   p.nblocks = NOUT == 64 ? g.Cout / 64 : 1;
   p.num_units = (long long)p.nblocks * g.N * p.units_d * p.units_h * p.units_w;
+  if (p.num_units >= (1LL << 31)) {
+    set_error("conv_tc: %lld work items exceed the 32-bit unit index of the kernel", (long long)p.num_units);
+    return -1;
+  }
   const int grid = (int)min((long long)num_sms(), p.num_units);
   launch_k(conv_tc_kernel<KCHUNKS, NACC, KDT, NGRP, NOUT, STACK, false>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, mx, mw, my, my, p);
   HPVG_CHECK_LAUNCH("conv_tc_kernel");
@@ -904,6 +915,10 @@ static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
   p.units_w = (int)cdiv(g.Wo, BW);
   p.nblocks = 1;
   p.num_units = (long long)g.N * p.units_d * p.units_h * p.units_w;
+  if (p.num_units >= (1LL << 31)) {
+    set_error("conv_bn_lrelu_fused: %lld work items exceed the 32-bit unit index of the kernel", (long long)p.num_units);
+    return -1;
+  }
   if (p.num_units > num_sms()) {
     set_error("conv_bn_fused: %lld units do not fit %d SMs", p.num_units, num_sms());
     return -1;

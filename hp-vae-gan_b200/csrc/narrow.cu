@@ -16,6 +16,13 @@
 
 namespace hpvg {
 
+bool narrow_wgrad_tc_supported(const ConvGeom& g, bool head);
+int narrow_wgrad_tc_grid(const ConvGeom& g, bool head);
+int narrow_wgrad_tc(const void* wide, const float* thin, bool head, const ConvGeom& g, float* partial, int grid, cudaStream_t st);
+bool expand_tc_supported(const ConvGeom& g);
+int expand_tc(const void* x, const float* w_tco, const float* bias, void* y, const ConvGeom& g, int act, float slope, float* stats,
+              cudaStream_t st);
+
 constexpr int EX_TH = 8, EX_TW = 32;             // output tile of the expand kernel: 1 x 8 x 32 voxels; thread = 4 voxels x 32 channels
 constexpr int EX_HW = EX_TW + 4, EX_HH = EX_TH + 2;   // halo row padded to an even length (64-bit loads)
 
@@ -382,6 +389,8 @@ int expand_conv(const void* x, const float* w, const float* w_tco, const float* 
   const int tiles_w = (int)cdiv(g.Wo, EX_TW), tiles_h = (int)cdiv(g.Ho, EX_TH);
   const long long blocks = (long long)g.N * g.Do * tiles_h * tiles_w;
   static const bool no_mma = getenv("HPVG_EXPAND_FMA") != nullptr;     // development aid: force the CUDA-core kernel
+  // tcgen05 form (narrow_tc.cu): im2col operand built in shared memory, bf16 operands; HPVG_EXPAND_TC=0 keeps the TF32 mma.sync kernel
+  if (w_tco != nullptr && !no_mma && expand_tc_supported(g)) return expand_tc(x, w_tco, bias, y, g, act, slope, stats, st);
   if (w_tco != nullptr && g.Cin <= 3 && !no_mma) {
     const size_t smem_mma = expand_mma_smem(g.KD);
     static std::atomic<unsigned long long> attr_mask{0};
@@ -720,7 +729,8 @@ __global__ void __launch_bounds__(OM_THREADS, 2) outer_corr_mma_kernel(const Out
 // dw[...] = sum over blocks of partial[b][c][k]; a block owns 32 consecutive (c, k) entries (one 128-byte line of every
 // partial row) and walks the ~300 rows with 32 threads per entry, so each thread has ~10 independent loads in flight
 __global__ void __launch_bounds__(1024) outer_corr_mma_reduce_kernel(const float* __restrict__ partial, int blocks, int taps, int J,
-                                                                     int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum) {
+                                                                     int wide_is_gy, float* __restrict__ dw, float* __restrict__ wide_sum,
+                                                                     int tap_major) {
   pdl_enter();
   __shared__ float red[32][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -743,7 +753,8 @@ __global__ void __launch_bounds__(1024) outer_corr_mma_reduce_kernel(const float
     return;
   }
   if (c > ncomb) return;
-  const int j = c / taps, t = c % taps;
+  // rows of a partial: (j, t) with t fastest (outer_corr_mma_kernel) or (t, j) with j fastest (narrow_wgrad_tc_kernel)
+  const int j = tap_major ? c % J : c / taps, t = tap_major ? c / J : c % taps;
   if (wide_is_gy)
     dw[((size_t)k * J + j) * taps + t] = s;
   else
@@ -770,7 +781,8 @@ static int oc_grid(const ConvGeom& g, bool head) {
 
 size_t narrow_wgrad_workspace(int x_fmt, const ConvGeom& g) {
   const bool head = x_fmt == HPVG_FMT_NCDHW_F32;
-  return (size_t)oc_grid(g, head) * 7 * 4 * OC_THREADS * sizeof(float);
+  const size_t tc = (size_t)narrow_wgrad_tc_grid(g, head) * 96 * 64 * sizeof(float);      // narrow_wgrad_tc_kernel: [grid][96][64]
+  return max((size_t)oc_grid(g, head) * 7 * 4 * OC_THREADS * sizeof(float), tc);
 }
 
 template <int KDT, int NC>
@@ -817,6 +829,20 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
   p.tiles = (long long)p.N * p.Dw * p.tiles_h * p.tiles_w;
   const int grid = oc_grid(g, head);
   static const bool no_mma = getenv("HPVG_WGRAD_FMA") != nullptr;      // development aid: force the CUDA-core kernel
+  if (!no_mma && narrow_wgrad_tc_supported(g, head)) {
+    // tcgen05 form (narrow_tc.cu): the im2col operand tile of the head convolution read MN-major against the wide tile
+    const int tgrid = narrow_wgrad_tc_grid(g, head);
+    const size_t need_tc = (size_t)tgrid * OM_ROWS * 64 * sizeof(float);
+    if (workspace == nullptr || ws_bytes < need_tc) {
+      set_error("narrow_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need_tc);
+      return -1;
+    }
+    if (int rc = narrow_wgrad_tc(p.wide, p.thin, head, g, reinterpret_cast<float*>(workspace), tgrid, st)) return rc;
+    launch_k(outer_corr_mma_reduce_kernel, (unsigned)cdiv(OM_ROWS * 64, 32), 1024, 0, st, reinterpret_cast<const float*>(workspace), tgrid, g.taps,
+                                                                                p.J, head ? 1 : 0, dw, p.want_sum ? dbias_wide : nullptr, 1);
+    HPVG_CHECK_LAUNCH("outer_corr_mma_reduce_kernel");
+    return 0;
+  }
   if (g.taps * p.J + 1 <= OM_ROWS && !no_mma) {
     const size_t need_mma = (size_t)grid * OM_ROWS * 64 * sizeof(float);
     if (workspace == nullptr || ws_bytes < need_mma) {
@@ -837,7 +863,7 @@ int narrow_wgrad(const void* x, int x_fmt, const void* gy, float* dw, float* dbi
       launch_k(outer_corr_mma_kernel<1>, grid, OM_THREADS, smem_mma, st, p);
     HPVG_CHECK_LAUNCH("outer_corr_mma_kernel");
     launch_k(outer_corr_mma_reduce_kernel, (unsigned)cdiv(OM_ROWS * 64, 32), 1024, 0, st, p.partial, grid, g.taps, p.J, head ? 1 : 0, dw,
-                                                                                p.want_sum ? dbias_wide : nullptr);
+                                                                                p.want_sum ? dbias_wide : nullptr, 0);
     HPVG_CHECK_LAUNCH("outer_corr_mma_reduce_kernel");
     return 0;
   }

@@ -96,13 +96,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const long long b_end = min(p.num_bricks, b_begin + p.bricks_per_split);
 
   // brick -> (n, od, h0, w0); returns false when the input slice of this kd is outside the tensor (zero contribution)
-  auto decode = [&](long long b, int& n, int& od, int& h0, int& w0) -> bool {
-    w0 = (int)(b % p.bricks_w) * WG_BW;
-    b /= p.bricks_w;
-    h0 = (int)(b % p.bricks_h) * WG_BH;
-    b /= p.bricks_h;
-    od = (int)(b % g.Do);
-    n = (int)(b / g.Do);
+  auto decode = [&](long long b64, int& n, int& od, int& h0, int& w0) -> bool {      // 32-bit arithmetic: see conv_tc.cu
+    unsigned b = (unsigned)b64;
+    unsigned q = b / (unsigned)p.bricks_w;
+    w0 = (int)(b - q * (unsigned)p.bricks_w) * WG_BW;
+    b = q;
+    q = b / (unsigned)p.bricks_h;
+    h0 = (int)(b - q * (unsigned)p.bricks_h) * WG_BH;
+    b = q;
+    q = b / (unsigned)g.Do;
+    od = (int)(b - q * (unsigned)g.Do);
+    n = (int)q;
     const int d = od + kd - g.pad_d;
     return d >= 0 && d < g.Di;
   };
@@ -296,13 +300,17 @@ wgrad_tc_kdstack_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   // work items = input slabs: num_bricks = N * Di * bricks_h * bricks_w here
   const long long b_begin = (long long)split * p.bricks_per_split;
   const long long b_end = min(p.num_bricks, b_begin + p.bricks_per_split);
-  auto decode = [&](long long b, int& n, int& d, int& h0, int& w0) {
-    w0 = (int)(b % p.bricks_w) * WG_BW;
-    b /= p.bricks_w;
-    h0 = (int)(b % p.bricks_h) * WG_BH;
-    b /= p.bricks_h;
-    d = (int)(b % g.Di);
-    n = (int)(b / g.Di);
+  auto decode = [&](long long b64, int& n, int& d, int& h0, int& w0) {      // 32-bit arithmetic: see conv_tc.cu
+    unsigned b = (unsigned)b64;
+    unsigned q = b / (unsigned)p.bricks_w;
+    w0 = (int)(b - q * (unsigned)p.bricks_w) * WG_BW;
+    b = q;
+    q = b / (unsigned)p.bricks_h;
+    h0 = (int)(b - q * (unsigned)p.bricks_h) * WG_BH;
+    b = q;
+    q = b / (unsigned)g.Di;
+    d = (int)(b - q * (unsigned)g.Di);
+    n = (int)q;
   };
 
   if (warp == 0) {
@@ -530,6 +538,10 @@ int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* 
     wgrad_plan_kdstack(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
   else
     wgrad_plan(g, p.bricks_h, p.bricks_w, p.num_bricks, p.splits, p.bricks_per_split);
+  if (p.num_bricks >= (1LL << 31)) {
+    set_error("wgrad_tc: %lld work items exceed the 32-bit brick index of the kernel", p.num_bricks);
+    return -1;
+  }
   const size_t need = (size_t)p.splits * g.taps * g.Cin * g.Cout * sizeof(float);
   if (ws_bytes < need || workspace == nullptr) {
     set_error("wgrad_tc: workspace too small (%zu < %zu bytes)", ws_bytes, need);

@@ -9,6 +9,8 @@ Citations are to files under the reference repository root.
 """
 import math
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -76,11 +78,17 @@ def _tf32(t):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+# operand precision of the thin -> wide layers: 'bf16' = the tcgen05 kernel (csrc/narrow_tc.cu, the default), 'tf32' = the
+# mma.sync kernel it replaced (HPVG_EXPAND_TC=0)
+HEAD_OPERAND = ['tf32' if os.environ.get('HPVG_EXPAND_TC') == '0' else 'bf16']
+
+
 def head_operand(t, w):
     """operands (input or weight) of a thin -> wide layer (Cin <= 3, Cout = 64): the CUDA path multiplies them on the
-    tensor cores in TF32; gradients pass straight through"""
+    tensor cores in bf16 (TF32 with HPVG_EXPAND_TC=0); gradients pass straight through"""
     if _STORAGE[-1] == 'bf16' and t.dtype == torch.float32 and w.shape[1] <= 3 and w.shape[0] == 64:
-        return t + (_tf32(t) - t).detach()
+        rounded = _tf32(t) if HEAD_OPERAND[0] == 'tf32' else t.detach().to(torch.bfloat16).to(t.dtype)
+        return t + (rounded - t).detach()
     return t
 
 
