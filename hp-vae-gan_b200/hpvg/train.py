@@ -144,7 +144,8 @@ class ScaleTrainer:
         # the generator's 'rec' and 'rand' passes on two streams at once (needs `overlap`); HPVG_CONCURRENT_PASSES=0 serialises them
         self.concurrent_passes = os.environ.get('HPVG_CONCURRENT_PASSES', '1') != '0'
         self.sn_prefetch = os.environ.get('HPVG_SN_PREFETCH', '1') != '0'
-        self._side = self._wside = self._snside = None
+        self.dreal_side = int(os.environ.get('HPVG_DREAL_SIDE', '1'))      # 0: off, 1: D(real) on its own stream, 2: D(fake) as well (measured: no further gain)
+        self._side = self._wside = self._snside = self._dside = None
         if self.overlap:
             # parameters receive gradients from nodes on several streams by design; the engine synchronises them
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -189,16 +190,19 @@ class ScaleTrainer:
         out = {}
         side = None
         if self.overlap and real.is_cuda and self._wside is None:
-            self._wside = torch.cuda.Stream(device=real.device)
+            # weight gradients: HPVG_WGRAD_STREAMS side streams (default 2: measured 3.83 ms per iteration against 3.89 / 3.86 / 3.87 ms with 1 / 3 / 4), layers dealt out round-robin (ops.wgrad_stream)
+            self._wside = [torch.cuda.Stream(device=real.device) for _ in range(max(1, int(os.environ.get('HPVG_WGRAD_STREAMS', '2'))))]
         # one zero fill for every atomically-accumulated statistic of the iteration (created before the streams fork)
         arena = ops.zero_arena(real.device, 32768) if real.is_cuda else contextlib.nullcontext()
         with arena:
             if self._wside is not None:
-                self._wside.wait_stream(torch.cuda.current_stream())     # fork (also makes it part of a graph capture)
+                for st in self._wside:
+                    st.wait_stream(torch.cuda.current_stream())     # fork (also makes them part of a graph capture)
             with ops.wgrad_stream(self._wside):
                 out = self._iteration_body(real, real_zero, noise_init, out)
         if self._wside is not None:
-            torch.cuda.current_stream().wait_stream(self._wside)     # join (the engine already did after each backward)
+            for st in self._wside:
+                torch.cuda.current_stream().wait_stream(st)     # join (the engine already did after each backward)
         return out
 
     def _iteration_body(self, real, real_zero, noise_init, out):
@@ -235,7 +239,18 @@ class ScaleTrainer:
                 if self._snside is None:
                     self._snside = torch.cuda.Stream(device=real.device)
                 D.prefetch_spectral_weights(3, self._snside)
-            errD_real = -D(real).mean()
+            # the critic's pass on the real clip depends on nothing the generator does: on a stream of its own it runs next to the
+            # generator's 'rand' pass instead of in front of it (HPVG_DREAL_SIDE=0: on the main stream, as the reference orders it)
+            dstream = None
+            if side is not None and self.dreal_side:
+                if self._dside is None:
+                    self._dside = torch.cuda.Stream(device=real.device)
+                dstream = self._dside
+                dstream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(dstream):
+                    errD_real = -D(real).mean()
+            else:
+                errD_real = -D(real).mean()
             if side is not None and rec_log is None:
                 torch.cuda.current_stream().wait_stream(side)      # the 'rand' pass shares BatchNorm buffers with 'rec'
             # concurrent_passes: the 'rand' pass starts while 'rec' is still running on the side stream.  They share BatchNorm
@@ -244,8 +259,17 @@ class ScaleTrainer:
             rand_log = ops.bn_stat_log() if rec_log is not None else None
             with (rand_log if rand_log is not None else contextlib.nullcontext()):
                 fake, _ = G(noise_init, opt.Noise_Amps, noise_init=noise_init, mode="rand")
-            errD_fake = D(fake.detach()).mean()
+            if dstream is not None and self.dreal_side > 1:
+                # ... and so does its pass on the fake clip once the 'rand' pass has produced it: the gradient-penalty chain (the
+                # critical path of the critic step) starts at once on the main stream
+                dstream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(dstream):
+                    errD_fake = D(fake.detach()).mean()
+            else:
+                errD_fake = D(fake.detach()).mean()
             gradient_penalty = calc_gradient_penalty(D, real, fake, opt.lambda_grad, real.device)
+            if dstream is not None:
+                torch.cuda.current_stream().wait_stream(dstream)      # join: errD_real, errD_fake
             errD_total = errD_real + errD_fake + gradient_penalty
             errD_total.backward()
             if self.distributed:

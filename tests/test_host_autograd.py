@@ -56,7 +56,7 @@ def test_conv_node_gradients(cpu_kernels, monkeypatch, deferred):
     x, w, b, gy = _case(1)
     ref = _reference(x, w, b, gy)
     monkeypatch.setattr(ops, "_CRITIC_WSIDE", [deferred])
-    monkeypatch.setattr(ops, "_WGRAD_STREAM", [object() if deferred else None])
+    monkeypatch.setattr(ops, "_WGRAD_STREAM", [ops._StreamRing([object()]) if deferred else None])
     w_use, token = ops.deferred_weight(w)
     assert (token is not None) == deferred
     y = ops.conv(x, w_use, b, 1, False, token=token)
@@ -74,7 +74,7 @@ def test_proxy_is_off_inside_the_gradient_penalty_pass_and_without_a_side_stream
     monkeypatch.setattr(ops, "_CRITIC_WSIDE", [True])
     monkeypatch.setattr(ops, "_WGRAD_STREAM", [None])
     assert ops.deferred_weight(w) == (w, None) or ops.deferred_weight(w)[1] is None
-    monkeypatch.setattr(ops, "_WGRAD_STREAM", [object()])
+    monkeypatch.setattr(ops, "_WGRAD_STREAM", [ops._StreamRing([object()])])
     with ops.no_wgrad_proxy():
         assert ops.deferred_weight(w)[1] is None
     with torch.no_grad():
@@ -88,7 +88,7 @@ def test_proxy_without_a_deposit_is_an_identity(cpu_kernels, monkeypatch):
     from hpvg import ops
     x, w, b, gy = _case(3)
     monkeypatch.setattr(ops, "_CRITIC_WSIDE", [True])
-    monkeypatch.setattr(ops, "_WGRAD_STREAM", [object()])
+    monkeypatch.setattr(ops, "_WGRAD_STREAM", [ops._StreamRing([object()])])
     w_use, token = ops.deferred_weight(w)
     y = ops.conv(x, w_use, b, 1, False, token=token)
     # create_graph=True: ConvFwd.backward is not `plain`, takes the differentiable ConvWgrad path and deposits nothing
@@ -120,7 +120,7 @@ def test_gradient_penalty_like_double_backward(cpu_kernels, monkeypatch, deferre
 
     ref = run(torch_conv)
     monkeypatch.setattr(ops, "_CRITIC_WSIDE", [deferred])
-    monkeypatch.setattr(ops, "_WGRAD_STREAM", [object() if deferred else None])
+    monkeypatch.setattr(ops, "_WGRAD_STREAM", [ops._StreamRing([object()]) if deferred else None])
     tokens = []
 
     def hpvg_conv():
