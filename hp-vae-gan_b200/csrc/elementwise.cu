@@ -360,6 +360,16 @@ __global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(cons
   mbar_wait(mbar, 0);
   const int cg = threadIdx.x % cvec;      // blockDim.x is a multiple of cvec: a thread's 8-channel group is fixed
   const int c0 = cg << 3;
+  // a thread's 8 channels never change: their parameters live in registers (read from shared memory per element they were
+  // 4 - 6 loads per element and pass — ncu: 7.4 M warp instructions per launch, MIO-throttle / short-scoreboard stalls)
+  float p_sc[8], p_sh[8], p_mu[8], p_is[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    p_sc[k] = prm[c0 + k];
+    p_sh[k] = prm[C + c0 + k];
+    p_mu[k] = prm[2 * C + c0 + k];
+    p_is[k] = prm[3 * C + c0 + k];
+  }
   float s0[8], s1[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s0[k] = s1[k] = 0.f;
@@ -373,12 +383,12 @@ __global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(cons
       const float ye[2] = {yf.x, yf.y}, ge[2] = {gf.x, gf.y};
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int c = c0 + 2 * k + e;
-        const bool pos = mb_base ? ((mb >> (2 * k + e)) & 1u) != 0u : fmaf(ye[e], prm[c], prm[C + c]) > 0.f;
+        const int j = 2 * k + e;
+        const bool pos = mb_base ? ((mb >> j) & 1u) != 0u : fmaf(ye[e], p_sc[j], p_sh[j]) > 0.f;
         const float dz = pos ? ge[e] : ge[e] * slope;
-        const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
-        s0[2 * k + e] += dz;
-        s1[2 * k + e] = fmaf(dz, xh, s1[2 * k + e]);
+        const float xh = (ye[e] - p_mu[j]) * p_is[j];
+        s0[j] += dz;
+        s1[j] = fmaf(dz, xh, s1[j]);
       }
     }
   }
@@ -412,6 +422,12 @@ __global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(cons
   }
   __syncthreads();
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float p_m0[8], p_m1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    p_m0[k] = prm[4 * C + c0 + k];
+    p_m1[k] = prm[5 * C + c0 + k];
+  }
   uint4* gyb = gy + row0 * cvec;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
     const uint4 yv = sy[v], gv = sg[v];
@@ -425,11 +441,11 @@ __global__ void __launch_bounds__(BNB_THREADS, 1) bn_lrelu_bwd_fused_kernel(cons
       float res[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int c = c0 + 2 * k + e;
-        const bool pos = mb_base ? ((mb >> (2 * k + e)) & 1u) != 0u : fmaf(ye[e], prm[c], prm[C + c]) > 0.f;
+        const int j = 2 * k + e;
+        const bool pos = mb_base ? ((mb >> j) & 1u) != 0u : fmaf(ye[e], p_sc[j], p_sh[j]) > 0.f;
         const float dz = pos ? ge[e] : ge[e] * slope;
-        const float xh = (ye[e] - prm[2 * C + c]) * prm[3 * C + c];
-        res[e] = prm[c] * (dz - prm[4 * C + c] - xh * prm[5 * C + c]);
+        const float xh = (ye[e] - p_mu[j]) * p_is[j];
+        res[e] = p_sc[j] * (dz - p_m0[j] - xh * p_m1[j]);
       }
       ow[k] = pack_bf16x2(res[0], res[1]);
       if (want_chsum) {     // sum of the STORED (bf16) gradient: the bias gradient of the convolution in front of this BatchNorm
