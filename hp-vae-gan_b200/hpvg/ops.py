@@ -708,6 +708,21 @@ class no_wgrad_proxy:
         _NO_PROXY[0] = self.prev
 
 
+_SMALL_GRADS_SIDE = [os.environ.get('HPVG_SMALL_GRADS_SIDE', '0') == '1']      # measured slower (3.74 vs 3.63 ms per iteration): off
+
+
+class SideGrad(Function):
+    """identity; created under a side stream so that autograd accumulates the gradient of `p` on that stream"""
+
+    @staticmethod
+    def forward(ctx, p):
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def deferred_weight(w):
     """-> (w', token): w' = w behind a WeightProxy created under the side stream, or (w, None) when the deferral does not apply"""
     if not _CRITIC_WSIDE[0] or _NO_PROXY[0] or _WGRAD_STREAM[0] is None or not torch.is_grad_enabled() or not w.requires_grad:
@@ -958,6 +973,11 @@ def conv_bn_lrelu(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, 
         token = _Deferred()
         with torch.cuda.stream(side):
             w = WeightProxy.apply(w, token)
+            if _SMALL_GRADS_SIDE[0]:
+                # bias, gamma, beta: their gradients come out of the BatchNorm-backward kernel on the data-gradient chain, and a layer used
+                # by both generator passes accumulates them with one tiny add each — inside that chain.  Behind an identity node created
+                # under the side stream the accumulation happens there (the engine orders it after the producing kernel by an event).
+                bias, gamma, beta = (SideGrad.apply(t) if (t is not None and t.requires_grad) else t for t in (bias, gamma, beta))
     return ConvBnLrelu.apply(x, w, bias, gamma, beta, running_mean, running_var, nbt, pad, momentum, eps, slope, token)
 
 
