@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 N=${NGPU:-8}
-O=gpurun_out/r02s_${N}gpu
+O=gpurun_out/r02zw_${N}gpu
 nvidia-smi --query-gpu=index,name --format=csv | head -10
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 20 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; tail -3 ${O}_bench.err
 python - ${O}_bench.json <<'PY'

@@ -23,6 +23,8 @@ size_t wgrad_tc_workspace(const ConvGeom& g);
 int wgrad_tc(const void* x, const void* gy, float* dw, const ConvGeom& g, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 bool thin_gs_supported(int x_fmt, int y_fmt, const ConvGeom& g);
+bool expand_tc_supported(const ConvGeom& g);
+bool narrow_wgrad_tc_supported(const ConvGeom& g, bool head);
 int thin_conv_gs(const void* x, const void* w_packed, const float* bias, float* y, const ConvGeom& g, cudaStream_t st);
 bool conv_bn_fused_supported(const ConvGeom& g);
 int conv_bn_fused(const void* x, const void* w_packed, const float* bias, void* y, void* out, const ConvGeom& g, float slope,
@@ -144,6 +146,12 @@ int hpvg_conv_bn_lrelu_fused(const void* x, const void* w_packed, const float* b
                          reinterpret_cast<uint32_t*>(mask_bits), st);
   prof_end(ph, st);
   return rc;
+}
+
+int hpvg_narrow_kernel_choice(int c_thin, int KD) {
+  ConvGeom g = {};
+  g.N = 1; g.Cin = c_thin; g.Cout = 64; g.KD = KD; g.taps = KD * 9;
+  return (expand_tc_supported(g) && narrow_wgrad_tc_supported(g, true)) ? 1 : 0;
 }
 
 int hpvg_conv_kernel_choice(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int y_fmt) {

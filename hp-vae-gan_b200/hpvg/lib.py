@@ -27,6 +27,7 @@ PROTOTYPES = {
     "hpvg_set_wgrad_mode": (c_int, [c_int]),
     "hpvg_profile_dump": (c_int, [c_void_p, c_int]),
     "hpvg_conv_kernel_choice": (c_int, [c_int] * 10),
+    "hpvg_narrow_kernel_choice": (c_int, [c_int] * 2),
     "hpvg_conv_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "hpvg_conv_forward_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

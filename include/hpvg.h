@@ -82,6 +82,12 @@ int hpvg_profile_dump(double* rows, int max_rows);
 #define HPVG_KERNEL_TC_COLUMN 3
 int hpvg_conv_kernel_choice(int N, int Cin, int Cout, int D, int H, int W, int KD, int pad, int x_fmt, int y_fmt);
 
+/* Do the narrow network ends with `c_thin` channels on their thin side (the 3 -> 64 head convolution, the data gradient of the
+ * 64 -> 3 / 64 -> 1 tails, both narrow weight gradients; modules/networks_3d.py:51,63,175,341,362) run on the tcgen05 kernels of
+ * narrow_tc.cu?  1 = yes, 0 = the mma.sync / CUDA-core kernels of narrow.cu (c_thin not in {1, 3}, or HPVG_EXPAND_TC=0 /
+ * HPVG_NARROW_WGRAD_TC=0).  Host logic only. */
+int hpvg_narrow_kernel_choice(int c_thin, int KD);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Convolution, 3x3x3 (KD == 3) or 3x3 (KD == 1), stride 1, zero padding `pad` in {0,1,2} on every filtered axis.
  * Replaces nn.Conv3d / nn.Conv2d forward inside ConvBlock3D / ConvBlock3DSN / the tail convs
