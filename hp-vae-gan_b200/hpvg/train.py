@@ -57,6 +57,11 @@ def generator_param_groups(opt, netG):
     return groups
 
 
+def _chain_priority():
+    """stream priority of the critical chains (main recording stream, generator 'rec' pass, critic pass on the real clip): 0 = default"""
+    return -int(os.environ.get('HPVG_CHAIN_PRIORITY', '0'))      # measured with 1: no difference (3.70 / 3.61 vs 3.64 / 3.71 ms)
+
+
 class GradBucket:
     """per-backward gradient all-reduce (average over ranks): the gradients are packed into ONE flat fp32 bucket (one multi-tensor
     copy), all-reduced with one NCCL call (ReduceOp.AVG on NCCL; SUM + divide on other backends), and unpacked.  Measured on
@@ -220,7 +225,7 @@ class ScaleTrainer:
         early = False
         if self.gan and self.overlap and real.is_cuda:
             if self._side is None:
-                self._side = torch.cuda.Stream(device=real.device)
+                self._side = torch.cuda.Stream(device=real.device, priority=_chain_priority())
             side, main = self._side, torch.cuda.current_stream()
             # the two generator passes share every weight: bring the cached operand images up to date HERE, on the main stream,
             # so that neither pass packs an image the other one reads without a stream dependency (ops.prepack_module)
@@ -260,7 +265,7 @@ class ScaleTrainer:
             dstream = None
             if side is not None and self.dreal_side:
                 if self._dside is None:
-                    self._dside = torch.cuda.Stream(device=real.device)
+                    self._dside = torch.cuda.Stream(device=real.device, priority=_chain_priority())
                 dstream = self._dside
                 dstream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(dstream):
@@ -389,7 +394,10 @@ class ScaleTrainer:
         torch.cuda.empty_cache()      # torch.cuda.graph() does the same on entry: take the baseline after it
         reserved0 = torch.cuda.memory_reserved()
         try:
-            with torch.cuda.graph(self.graph):
+            # the recording's own stream carries the data-gradient chains: with HPVG_CHAIN_PRIORITY it is a high-priority stream, so that
+            # its kernels get free SMs before the weight-gradient kernels queued on the (default-priority) side streams
+            cap = torch.cuda.Stream(priority=_chain_priority()) if _chain_priority() != 0 else None
+            with (torch.cuda.graph(self.graph, stream=cap) if cap is not None else torch.cuda.graph(self.graph)):
                 self.static_out = self.iteration(self.static_real, self.static_real_zero)
         finally:
             ops._GpAlpha.external = False
