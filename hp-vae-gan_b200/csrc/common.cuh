@@ -233,6 +233,9 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src,
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+#ifndef HPVG_STORE_WAIT_READ
+#define HPVG_STORE_WAIT_READ 1
+#endif
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

@@ -386,7 +386,11 @@ conv_col_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_arrive(bar_hempty(half));
       ++si;
     }
+#if HPVG_STORE_WAIT_READ
+    if (et == 0) tma_store_wait_read<0>();      // the staging tiles have been read: the CTA may leave (the writes land by the end of the grid)
+#else
     if (et == 0) tma_store_wait_all<0>();
+#endif
     if (p.dbg && et == 0) {
       p.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;   // epilogue warps, whole run
       p.dbg[blockIdx.x * 8 + 4] = t_accwait;             // of which waiting for accumulators

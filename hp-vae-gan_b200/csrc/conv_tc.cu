@@ -149,6 +149,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   unsigned long long gt0 = 0;
   if (p.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 
+  // unit -> coordinates
+  // 32-bit arithmetic on purpose (the host checks num_units < 2^31): 64-bit division is a subroutine of dozens of instructions, and
+  // the producer decodes its unit before it can issue the first load
+  auto decode = [&](long long u64, int& nb, int& n, int& d0, int& h0, int& w0) {
+    unsigned u = (unsigned)u64;
+    unsigned q = u / (unsigned)p.units_w;
+    w0 = (int)(u - q * (unsigned)p.units_w) * BW;
+    u = q;
+    q = u / (unsigned)p.units_h;
+    h0 = (int)(u - q * (unsigned)p.units_h) * BH;
+    u = q;
+    q = u / (unsigned)p.units_d;
+    d0 = (int)(u - q * (unsigned)p.units_d) * NACC;
+    u = q;
+    q = u / (unsigned)g.N;
+    n = (int)(u - q * (unsigned)g.N);
+    nb = (int)q;
+  };
+
+  // the loads a unit needs first: (kd-stacked form) the weight stage of position 0 into ring stage `wstage`, then the input slabs
+  auto issue_front = [&](long long u, uint32_t wstage) {
+    int nb, n, d0, h0, w0;
+    decode(u, nb, n, d0, h0, w0);
+    if (STACK) {
+      // the first weight stage goes out BEFORE the slabs: it is small and L2-resident, and the first MMAs need it
+      // together with slab 0 — behind 138 KB of slab traffic it arrived ~2 us late
+      mbar_expect_tx(bar_b_full(wstage), Cfg::STAGE_BYTES);
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+        tma_load_2d(s_b + wstage * Cfg::STAGE_BYTES + kd * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(wstage), 0, (kd * 9 + 0) * p.nblocks * NOUT + nb * NOUT);
+    }
+#pragma unroll
+    for (int j = 0; j < NACC + KDT - 1; ++j) {
+      const int d = d0 + j - g.pad_d;
+      if (d < 0 || d >= g.Di) continue;
+      // slice needed only if some valid accumulator reads it
+      bool needed = false;
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        const int kd = j - a;
+        if (kd >= 0 && kd < KDT && d0 + a < g.Do) needed = true;
+      }
+      if (!needed) continue;
+#pragma unroll
+      for (int kc = 0; kc < KCHUNKS; ++kc) {
+        const int si = j * KCHUNKS + kc;
+        mbar_expect_tx(bar_slab_full(si), SLAB_BYTES);
+        tma_load_5d(s_slab + si * SLAB_STRIDE, &tmap_x, bar_slab_full(si), kc * 64, w0 - g.pad, h0 - g.pad, d, n);
+      }
+    }
+  };
+
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::NSLAB; ++i) mbar_init(bar_slab_full(i), 1);
     for (int i = 0; i < Cfg::NB; ++i) {
@@ -159,6 +211,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     mbar_init(bar_acc_empty, NEPI_THREADS);
     mbar_init(bar_slabs_free, NMMA);
     mbar_fence_init();
+    // (Tried: this thread issuing the first unit's loads right here, before the CTA-wide barrier — ~0.3 us earlier.  Parity tests were
+    // green, but the recorded multi-stream iteration then died with "illegal memory access" on every run, with or without a
+    // fence.proxy.async after the barrier initialisation; the cause was not found, the loads stay behind the barrier.)
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     if (!Cfg::THIN) tma_prefetch_desc(&tmap_y);
@@ -194,25 +249,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tmem_base = *tmem_slot;
   }
 
-  // unit -> coordinates
-  // 32-bit arithmetic on purpose (the host checks num_units < 2^31): 64-bit division is a subroutine of dozens of instructions, and
-  // the producer decodes its unit before it can issue the first load
-  auto decode = [&](long long u64, int& nb, int& n, int& d0, int& h0, int& w0) {
-    unsigned u = (unsigned)u64;
-    unsigned q = u / (unsigned)p.units_w;
-    w0 = (int)(u - q * (unsigned)p.units_w) * BW;
-    u = q;
-    q = u / (unsigned)p.units_h;
-    h0 = (int)(u - q * (unsigned)p.units_h) * BH;
-    u = q;
-    q = u / (unsigned)p.units_d;
-    d0 = (int)(u - q * (unsigned)p.units_d) * NACC;
-    u = q;
-    q = u / (unsigned)g.N;
-    n = (int)(u - q * (unsigned)g.N);
-    nb = (int)q;
-  };
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -221,39 +257,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
         int nb, n, d0, h0, w0;
         decode(u, nb, n, d0, h0, w0);
+        const int q_first = STACK ? 1 : 0;
         if (it > 0) mbar_wait(bar_slabs_free, (uint32_t)((it - 1) & 1));
-        int q_first = 0;
-        if (STACK) {
-          // the first weight stage goes out BEFORE the slabs: it is small and L2-resident, and the first MMAs need it
-          // together with slab 0 — behind 138 KB of slab traffic it arrived ~2 us late
-          mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
-          mbar_expect_tx(bar_b_full(bstage), Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int kd = 0; kd < 3; ++kd)
-            tma_load_2d(s_b + bstage * Cfg::STAGE_BYTES + kd * Cfg::BTILE_BYTES, &tmap_w, bar_b_full(bstage), 0,
-                        (kd * 9 + 0) * p.nblocks * NOUT + nb * NOUT);
-          if (++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
-          q_first = 1;
-        }
-#pragma unroll
-        for (int j = 0; j < NACC + KDT - 1; ++j) {
-          const int d = d0 + j - g.pad_d;
-          if (d < 0 || d >= g.Di) continue;
-          // slice needed only if some valid accumulator reads it
-          bool needed = false;
-#pragma unroll
-          for (int a = 0; a < NACC; ++a) {
-            const int kd = j - a;
-            if (kd >= 0 && kd < KDT && d0 + a < g.Do) needed = true;
-          }
-          if (!needed) continue;
-#pragma unroll
-          for (int kc = 0; kc < KCHUNKS; ++kc) {
-            const int si = j * KCHUNKS + kc;
-            mbar_expect_tx(bar_slab_full(si), SLAB_BYTES);
-            tma_load_5d(s_slab + si * SLAB_STRIDE, &tmap_x, bar_slab_full(si), kc * 64, w0 - g.pad, h0 - g.pad, d, n);
-          }
-        }
+        if (STACK) mbar_wait(bar_b_empty(bstage), bphase ^ 1u);
+        issue_front(u, bstage);
+        if (STACK && ++bstage == Cfg::NB) { bstage = 0; bphase ^= 1u; }
         if (STACK) {
 #pragma unroll 1
           for (int q = q_first; q < 9 * NGRP; ++q) {       // one stage = the kd = 0, 1, 2 tiles of position q % 9 = kh * 3 + kw
@@ -639,7 +647,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tma_store_commit();
       }
     }
+#if HPVG_STORE_WAIT_READ
+    if (et == 0) tma_store_wait_read<0>();      // the staging tiles have been read: the CTA may leave (the writes land by the end of the grid)
+#else
     if (et == 0) tma_store_wait_all<0>();
+#endif
   } else if (!Cfg::THIN) {
     // ===================== epilogue, wide output: NEPI warps, TMEM lane quadrant = warp & 3, CPT columns per thread ==========
     // Measured (bench_kernels.py clk): of the ~6.5 k cycles after the last MMA about half is this chain and half the
@@ -793,7 +805,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc_fence_before();
       mbar_arrive(bar_acc_empty);
     }
+#if HPVG_STORE_WAIT_READ
+    if (et == 0) tma_store_wait_read<0>();      // the staging tiles have been read: the CTA may leave (the writes land by the end of the grid)
+#else
     if (et == 0) tma_store_wait_all<0>();
+#endif
     if (p.dbg && et == 0) {
       p.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;   // epilogue warps, all units
       p.dbg[blockIdx.x * 8 + 4] = t_accwait;             // of which waiting for the accumulators

@@ -428,7 +428,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) expand_tc_kernel(const __grid_c
       }
     }
     flush_stats();
+#if HPVG_STORE_WAIT_READ
+    if (et == 0) tma_store_wait_read<0>();      // the staging tiles have been read: the CTA may leave (the writes land by the end of the grid)
+#else
     if (et == 0) tma_store_wait_all<0>();
+#endif
     if (dbg && et == 0) dbg[15] = nt_now();
   }
   tc_fence_before();

@@ -390,3 +390,42 @@ def test_recorded_iteration_replays_with_the_library_optimizer(golden):
     # the recorded path is pinned by test_recorded_iteration_equals_the_eager_iteration_and_the_reference above
     ref = fx['losses'][min(4, fx['iters'] - 1)]['rec_loss']
     assert 0.5 * ref < rec[-1] < 2.0 * ref, (rec, ref)
+
+
+def test_two_recorded_generation_forwards_in_flight_at_config2_size():
+    """BASELINE configs[3] the way bench.py runs it: batches of 32 draws through the full configs[1] pyramid (finest level
+    16 x 64 x 64), per-draw BatchNorm statistics, two recorded forwards in flight on two streams — persistent tcgen05 kernels with
+    ~27 units per CTA of the brick, thin-output and column kernels interleaving on the SMs.  A build whose thin-output kernel used a
+    rolled issue loop faulted here ("illegal memory access", once in ~10 rounds: DESIGN.md §4 item 5); this test keeps ten rounds of
+    that schedule in the suite, and checks that both streams' outputs are finite, bounded by tanh and differ from draw to draw."""
+    from hpvg import train
+    from hpvg.options import Options
+    from modules import networks_3d
+    from oracle import port
+
+    o = Options(img_size=64, sampling_rates=[5, 3, 1], vae_levels=3, nfc=64, latent_dim=128, num_layer=5, batch_size=1)
+    o.scale_idx = o.stop_scale
+    o.Noise_Amps = [1.0] + [0.07] * o.stop_scale      # one amplitude per level, the finest included
+    t0, h0, w0 = o.level_size(0)
+    o.Z_init_size = [1, 128, t0, h0, w0]
+    g = networks_3d.GeneratorHPVAEGAN(o)
+    for _ in range(o.scale_idx):
+        g.init_next_stage()
+    port.det_fill(g.state_dict(), 5)
+    g.cuda()
+    torch.manual_seed(3)
+    sampler = train.Sampler(g, o, torch.device("cuda", 0), batch=32, graph=True, streams=2, static_weights=True)
+    outs = []
+    for r in range(10):
+        sampler.begin()
+        last = [sampler.sample() for _ in range(8)][-2:]
+        sampler.wait()
+        torch.cuda.synchronize()
+        if r in (0, 9):
+            outs.append([t.clone() for t in last])
+    for pair in outs:
+        for t in pair:
+            assert tuple(t.shape) == (32, 3, 16, 64, 64)
+            assert torch.isfinite(t).all() and float(t.abs().max()) <= 1.0
+            assert float((t[0] - t[1]).abs().max()) > 1e-3          # different latents: different draws
+    assert float((outs[0][0] - outs[1][0]).abs().max()) > 1e-3      # and every replay draws fresh latents
