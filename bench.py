@@ -701,7 +701,7 @@ def run_hpvg(args):
         line = {"metric": METRIC, "value": leg.value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W + leg.last.get("extra_warmup", 0),
                 "ms_per_step": leg.ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat NCCL grad all-reduce)" % world if distributed else "single GPU",
+                "config": {"workload": workload_name(o), "parallelism": "dp%d (one clip per GPU, flat gradient bucket averaged %s)" % (world, ALLREDUCE_KINDS.get(trainer.bucketG.kind, str(trainer.bucketG.kind))) if distributed else "single GPU",
                            "l2": "no explicit flush: one iteration writes and re-reads a %.0f MB working set (activations saved for the "
                                  "backward passes, gradients), %s the 126 MB L2" % (work_mb, "above" if work_mb > 126 else "NOT above"),
                            "conv_gflop_per_iter": leg.gflop, "conv_gflop_per_iter_executed": leg.gflop_executed,
@@ -716,6 +716,7 @@ def run_hpvg(args):
                 "generation": generation}
         if distributed:
             line["allreduce_bytes_per_step"] = trainer.allreduce_bytes_per_iter
+            line["allreduce"] = {"critic": trainer.bucketD.kind, "generator": trainer.bucketG.kind}
             if dp_named is not None:
                 line["dp_named_config"] = dp_named
         if world == 1 and not args.no_cpu_baseline:
@@ -746,6 +747,10 @@ def run_hpvg(args):
 # the other single-GPU BASELINE configurations: configs[0] (train_image.py, 2-D, 128 px) and configs[2] (train_video_baselines.py,
 # GeneratorSG).  Same metric (finest-level training iterations/s), value + e2e only.
 # ---------------------------------------------------------------------------------------------------------------
+ALLREDUCE_KINDS = {"peer": "by one libhpvg kernel over NVLink peer memory (hpvg_peer_allreduce_avg)", "nccl": "by one NCCL all-reduce",
+                   "nccl-coalesced": "by a coalesced NCCL group call", "sum": "by all-reduce SUM + divide"}
+
+
 def run_other(args):
     from hpvg import lib, train
     from hpvg.options import Options

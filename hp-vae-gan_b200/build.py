@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libhpvg.so")
-SOURCES = ["api.cu", "conv_api.cu", "conv_direct.cu", "conv_tc.cu", "conv_col.cu", "thin_gs.cu", "wgrad_tc.cu", "narrow.cu", "narrow_tc.cu", "elementwise.cu", "wide_ops.cu", "frames.cu", "optim.cu"]
+SOURCES = ["api.cu", "conv_api.cu", "conv_direct.cu", "conv_tc.cu", "conv_col.cu", "thin_gs.cu", "wgrad_tc.cu", "narrow.cu", "narrow_tc.cu", "elementwise.cu", "wide_ops.cu", "frames.cu", "optim.cu", "peer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

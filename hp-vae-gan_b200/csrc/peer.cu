@@ -1,0 +1,204 @@
+// Gradient averaging over NVLink peer memory: ONE kernel per backward instead of a library collective (include/hpvg.h,
+// "Gradient averaging over NVLink peer memory").
+//
+// Replaces the reduction of the replicas' gradients in nn.DataParallel's backward (train_video.py:91-94, :182, :200) for the
+// one-process-per-GPU mode.  The buckets are small (1.3 MB for the critic, 2.7 - 5.4 MB for the generator at BASELINE configs[1]),
+// so what a collective costs here is latency, not bandwidth: the kernel is two flag exchanges around one pull of a 1/world slice
+// from every peer and one push of the mean to every peer — every GPU reads and writes (world - 1) / world of a bucket over
+// NVLink / NVSwitch, all pairs at once.
+//
+// Memory model: the flags are written with st.release.sys and polled with ld.acquire.sys; a rank's bucket was filled by earlier
+// kernels of its stream (performed before this kernel starts), the pushed means are followed by __threadfence_system() in the
+// writing thread and a CTA barrier before the flag thread releases.  Peer data is pulled with ld.volatile (never from L1).
+#include "common.cuh"
+
+namespace hpvg {
+
+constexpr int PEER_MAX_BLOCKS = 64, PEER_THREADS = 256, PEER_UNROLL = 4;
+constexpr int PEER_EPOCH_OFF = 2 * PEER_MAX_BLOCKS * HPVG_PEER_MAX_RANKS;      // unsigned index of the per-CTA call counts in the pad
+static_assert((PEER_EPOCH_OFF + PEER_MAX_BLOCKS) * 4 <= HPVG_PEER_SIGNAL_BYTES, "signal pad layout");
+
+struct PeerArgs {
+  float4* buf[HPVG_PEER_MAX_RANKS];
+  unsigned* sig[HPVG_PEER_MAX_RANKS];
+  int rank, world;
+  long long n4;      // float4 elements per rank slice
+  float scale;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// CTA b of this rank meets CTA b of every other rank: thread q tells rank q "call e, phase ph reached" and waits for rank q's word
+__device__ __forceinline__ void peer_barrier(const PeerArgs& a, int ph, unsigned e) {
+  if ((int)threadIdx.x < a.world) {
+    const int q = threadIdx.x;
+    const int slot = (ph * PEER_MAX_BLOCKS + blockIdx.x) * HPVG_PEER_MAX_RANKS;
+    st_release_sys(a.sig[q] + slot + a.rank, e);
+    const unsigned* theirs = a.sig[a.rank] + slot + q;
+    unsigned long long t0 = 0;
+    while ((int)(ld_acquire_sys(theirs) - e) < 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      if (t - t0 > 60000000000ull) {
+        printf("hpvg: peer all-reduce timed out (rank %d block %d phase %d waits for rank %d, call %u)\n", a.rank, blockIdx.x, ph, q, e);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerArgs a) {
+  __shared__ unsigned s_epoch;
+  unsigned* epoch = a.sig[a.rank] + PEER_EPOCH_OFF + blockIdx.x;
+  if (threadIdx.x == 0) s_epoch = *epoch + 1u;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  peer_barrier(a, 0, e);      // every rank's bucket is filled
+
+  const int W = a.world;
+  const long long base = (long long)a.rank * a.n4;
+  const long long step = (long long)gridDim.x * PEER_THREADS;
+  for (long long i0 = (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i0 < a.n4; i0 += step * PEER_UNROLL) {
+    float4 v[PEER_UNROLL][HPVG_PEER_MAX_RANKS];
+#pragma unroll
+    for (int k = 0; k < PEER_UNROLL; ++k) {
+      const long long i = i0 + k * step;
+#pragma unroll
+      for (int q = 0; q < HPVG_PEER_MAX_RANKS; ++q)
+        if (q < W && i < a.n4) v[k][q] = ld_volatile_f4(a.buf[q] + base + i);
+    }
+#pragma unroll
+    for (int k = 0; k < PEER_UNROLL; ++k) {
+      const long long i = i0 + k * step;
+      if (i >= a.n4) break;
+      float4 s = v[k][0];      // rank order: the same sum on every rank, whoever arrives first
+#pragma unroll
+      for (int q = 1; q < HPVG_PEER_MAX_RANKS; ++q)
+        if (q < W) {
+          s.x += v[k][q].x; s.y += v[k][q].y; s.z += v[k][q].z; s.w += v[k][q].w;
+        }
+      s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
+#pragma unroll
+      for (int q = 0; q < HPVG_PEER_MAX_RANKS; ++q)
+        if (q < W) a.buf[q][base + i] = s;
+    }
+  }
+  __threadfence_system();      // this thread's pushes are performed at system scope before the CTA's flags go out
+  __syncthreads();
+  peer_barrier(a, 1, e);       // all means have landed here; nobody reads this rank's bucket any more
+  if (threadIdx.x == 0) *epoch = e;
+}
+
+}  // namespace hpvg
+
+using namespace hpvg;
+
+#define PEER_CUDA(call, what)                                                \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      (void)cudaGetLastError();                                              \
+      set_error("%s: %s", what, cudaGetErrorString(e_));                     \
+      return -2;                                                             \
+    }                                                                        \
+  } while (0)
+
+extern "C" {
+
+int hpvg_peer_alloc(size_t bytes, void** ptr) {
+  HPVG_CHECK_ARG(ptr && bytes > 0, "peer_alloc: null argument or zero size");
+  static_assert(sizeof(cudaIpcMemHandle_t) == HPVG_PEER_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  PEER_CUDA(cudaMalloc(&p, bytes), "peer_alloc: cudaMalloc");
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    (void)cudaGetLastError();
+    set_error("peer_alloc: zero fill: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  *ptr = p;
+  return 0;
+}
+
+int hpvg_peer_free(void* ptr) {
+  if (ptr) PEER_CUDA(cudaFree(ptr), "peer_free");
+  return 0;
+}
+
+int hpvg_peer_export(const void* ptr, void* handle) {
+  HPVG_CHECK_ARG(ptr && handle, "peer_export: null argument");
+  cudaIpcMemHandle_t h;
+  PEER_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)), "peer_export: cudaIpcGetMemHandle");
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+int hpvg_peer_import(const void* handle, void** ptr) {
+  HPVG_CHECK_ARG(ptr && handle, "peer_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  PEER_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "peer_import: cudaIpcOpenMemHandle");
+  *ptr = p;
+  return 0;
+}
+
+int hpvg_peer_close(void* ptr) {
+  if (ptr) PEER_CUDA(cudaIpcCloseMemHandle(ptr), "peer_close");
+  return 0;
+}
+
+int hpvg_peer_can_access(int device, int peer_device) {
+  if (device == peer_device) return 1;
+  int ok = 0;
+  if (cudaDeviceCanAccessPeer(&ok, device, peer_device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return ok;
+}
+
+int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, int world, long long numel, void* stream) {
+  HPVG_CHECK_ARG(bufs && signals, "peer_allreduce_avg: null argument");
+  HPVG_CHECK_ARG(world >= 1 && world <= HPVG_PEER_MAX_RANKS && rank >= 0 && rank < world, "peer_allreduce_avg: rank %d of %d (at most %d ranks)",
+                 rank, world, HPVG_PEER_MAX_RANKS);
+  HPVG_CHECK_ARG(numel > 0 && numel % (4LL * world) == 0, "peer_allreduce_avg: %lld floats are not a multiple of 4 x %d", numel, world);
+  PeerArgs a;
+  for (int q = 0; q < HPVG_PEER_MAX_RANKS; ++q) {
+    a.buf[q] = nullptr;
+    a.sig[q] = nullptr;
+  }
+  for (int q = 0; q < world; ++q) {
+    HPVG_CHECK_ARG(bufs[q] && signals[q], "peer_allreduce_avg: rank %d's bucket or signal pad is not mapped", q);
+    a.buf[q] = reinterpret_cast<float4*>(bufs[q]);
+    a.sig[q] = reinterpret_cast<unsigned*>(signals[q]);
+  }
+  a.rank = rank;
+  a.world = world;
+  a.n4 = numel / (4LL * world);
+  a.scale = 1.0f / (float)world;
+  // the CTAs of all ranks pair up by number: the grid is a function of the arguments every rank shares
+  const int grid = (int)min((long long)PEER_MAX_BLOCKS, max(1LL, cdiv(a.n4, (long long)PEER_THREADS * PEER_UNROLL)));
+  // no programmatic launch here: the kernel's first act publishes what the preceding kernels of the stream wrote
+  peer_allreduce_kernel<<<grid, PEER_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  HPVG_CHECK_LAUNCH("peer_allreduce_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -93,6 +93,13 @@ PROTOTYPES = {
     "hpvg_grad_clip_coef": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "hpvg_adam_step": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double,
                                c_int, c_int, c_void_p, c_void_p]),
+    "hpvg_peer_alloc": (c_int, [c_size_t, c_void_p]),
+    "hpvg_peer_free": (c_int, [c_void_p]),
+    "hpvg_peer_export": (c_int, [c_void_p, c_void_p]),
+    "hpvg_peer_import": (c_int, [c_void_p, c_void_p]),
+    "hpvg_peer_close": (c_int, [c_void_p]),
+    "hpvg_peer_can_access": (c_int, [c_int, c_int]),
+    "hpvg_peer_allreduce_avg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p]),
 }
 
 _lib = None
@@ -132,6 +139,7 @@ OPT_BLOCKS = 64           # HPVG_OPT_BLOCKS: partial sums per tensor
 OPT_STATE_FLOATS = 8
 SN_MAX_LAYERS = 8
 BN_LOG_MAX = 48           # HPVG_BN_LOG_MAX: entries per hpvg_bn_running_update_batched call
+PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_SIGNAL_BYTES = 8, 64, 8192      # HPVG_PEER_*
 SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the spectral-norm backward
 
 

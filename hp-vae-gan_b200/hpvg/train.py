@@ -7,7 +7,8 @@ and logging layers.  Hyper-parameters are read from the same `opt` fields the sc
 
 Multi-GPU ("batched-noise data-parallel training", BASELINE.json config 5): one process per GPU, one clip + its
 noise per rank, replicated weights.  After each backward the parameter gradients that exist on this rank are
-averaged over ranks with ONE flat-bucket NCCL all-reduce: the critic's after errD_total.backward(),
+averaged over ranks through ONE flat bucket — by one libhpvg kernel over NVLink peer memory (hpvg/peer.py),
+or one NCCL all-reduce where peer memory cannot be mapped: the critic's after errD_total.backward(),
 the generator's after total_loss.backward() and before clip_grad_norm_, so every rank clips with the same norm and
 takes the same Adam step.  BatchNorm statistics stay per rank, as under the reference's nn.DataParallel.
 """
@@ -63,15 +64,34 @@ def _chain_priority():
 
 
 class GradBucket:
-    """per-backward gradient all-reduce (average over ranks): the gradients are packed into ONE flat fp32 bucket (one multi-tensor
-    copy), all-reduced with one NCCL call (ReduceOp.AVG on NCCL; SUM + divide on other backends), and unpacked.  Measured on
-    8 x B200 (configs[1], one clip per GPU): 4.37 ms per step with the flat bucket against 4.52 ms with a coalesced NCCL group call
-    over the ~80 gradient tensors in place (HPVG_COALESCED_ALLREDUCE=1) — NCCL's per-operation cost beats the two pack / unpack
-    launches at 8 ranks; at 2 ranks the two are equal (4.45 / 4.46 ms)."""
+    """per-backward gradient averaging over ranks: the gradients are packed into ONE flat fp32 bucket (one multi-tensor copy),
+    averaged, and unpacked.
+
+    On NCCL process groups the bucket lives in NVLink peer memory and ONE libhpvg kernel averages it (hpvg/peer.py,
+    csrc/peer.cu: flag exchange, every rank pulls one slice from all peers and pushes the mean back to all of them) — `kind` ==
+    'peer'.  When the ranks cannot map each other's memory, or with HPVG_PEER_ALLREDUCE=0, it is one NCCL all-reduce
+    (ReduceOp.AVG) of the flat bucket ('nccl'); other backends (gloo, the CPU tests): SUM + divide ('sum').
+    Measured on 8 x B200 with NCCL (configs[1], one clip per GPU): 4.37 ms per step with the flat bucket against 4.52 ms with a
+    coalesced NCCL group call over the ~80 gradient tensors in place (HPVG_COALESCED_ALLREDUCE=1) — NCCL's per-operation cost
+    beats the two pack / unpack launches at 8 ranks; at 2 ranks the two are equal (4.45 / 4.46 ms)."""
 
     def __init__(self, group=None):
         self.group = group
         self.flat = None
+        self.peer = None            # hpvg.peer.PeerBucket once set up
+        self.peer_refused = False   # set-up failed on some rank: stay on NCCL
+        self.kind = None
+
+    def _peer_bucket(self, n, device):
+        from . import peer
+        if self.peer_refused or not peer.enabled():
+            return None
+        if self.peer is None or self.peer.numel < n:
+            if self.peer is not None:
+                self.peer.close()
+            self.peer = peer.PeerBucket.create(n, device, self.group)
+            self.peer_refused = self.peer is None
+        return self.peer
 
     def average(self, params):
         import torch.distributed as dist
@@ -81,22 +101,33 @@ class GradBucket:
         n = sum(g.numel() for g in grads)
         nccl = grads[0].is_cuda and dist.get_backend(self.group) == "nccl"
         if nccl and os.environ.get("HPVG_COALESCED_ALLREDUCE", "0") == "1":
+            self.kind = "nccl-coalesced"
             with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
                 for g in grads:
                     dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             return n * 4
-        if self.flat is None or self.flat.numel() != n or self.flat.device != grads[0].device:
-            self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+        bucket = self._peer_bucket(n, grads[0].device) if nccl else None
+        if bucket is not None:
+            flat = bucket.flat
+        else:
+            if self.flat is None or self.flat.numel() != n or self.flat.device != grads[0].device:
+                self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            flat = self.flat
         views, off = [], 0
         for g in grads:
-            views.append(self.flat[off:off + g.numel()].view_as(g))
+            views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
         torch._foreach_copy_(views, grads)
-        if nccl:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        if bucket is not None:
+            self.kind = "peer"
+            bucket.allreduce()      # the padding floats behind the last gradient are averaged along: they are never read
+        elif nccl:
+            self.kind = "nccl"
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(dist.get_world_size(self.group))
+            self.kind = "sum"
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(dist.get_world_size(self.group))
         torch._foreach_copy_(grads, views)
         return n * 4
 
@@ -151,9 +182,10 @@ class ScaleTrainer:
         self.sn_prefetch = os.environ.get('HPVG_SN_PREFETCH', '1') != '0'
         # the reconstruction path's backward starts as soon as its forward has finished, on the side stream, under the critic step
         # (it depends on nothing the critic step does); the generator step then only runs the adversarial path's backward
-        # (HPVG_EARLY_REC_BWD=1; measured 3.62 / 3.68 ms against 3.74 / 3.66 ms: within the run-to-run spread — the two paths' backward passes
-        # already ran side by side in the generator step — so it stays off)
-        self.early_rec_bwd = os.environ.get('HPVG_EARLY_REC_BWD', '0') == '1'
+        # (HPVG_EARLY_REC_BWD=1 / 0).  On one GPU: 3.62 / 3.68 ms against 3.74 / 3.66 ms, within the run-to-run spread — the two paths'
+        # backward passes already ran side by side in the generator step — so it stays off there.  In the multi-GPU mode it is ON: this
+        # backward is work that does not wait for the critic's gradient averaging (2 GPUs: 3.807 / 3.808 ms against 3.837 / 3.850 ms).
+        self.early_rec_bwd = os.environ.get('HPVG_EARLY_REC_BWD', '1' if distributed else '0') == '1'
         self.dreal_side = int(os.environ.get('HPVG_DREAL_SIDE', '1'))      # 0: off, 1: D(real) on its own stream, 2: D(fake) as well (measured: no further gain)
         self._side = self._wside = self._snside = self._dside = None
         if self.overlap:

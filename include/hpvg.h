@@ -342,6 +342,36 @@ int hpvg_adam_step(int n, float* const* params, float* const* grads, float* cons
                    const long long* numel, const float* lr, double beta1, double beta2, double eps, int use_clip,
                    int advance_step, float* state, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Gradient averaging over NVLink peer memory (multi-GPU mode, one process per GPU): replaces the reduction of the replicas'
+ * gradients that nn.DataParallel's backward performs (train_video.py:91-94, :182, :200) — here one clip per rank and ONE kernel per
+ * backward instead of a library collective.
+ *
+ * Every rank owns one bucket (numel floats, numel a multiple of 4 * world) and one signal pad (HPVG_PEER_SIGNAL_BYTES, zero
+ * filled), both allocated with hpvg_peer_alloc (an allocation of its own: an IPC handle covers a whole allocation), exported
+ * with hpvg_peer_export (64-byte handle, sent to the other ranks by any host channel) and mapped there with hpvg_peer_import.
+ * hpvg_peer_allreduce_avg(bufs, signals, rank, world, numel, stream): bufs[q] / signals[q] are rank q's bucket / pad as mapped in
+ * THIS process (q == rank: the local allocations).  The kernel (two-shot):
+ *   1. flag barrier with the same-numbered CTA of every peer (st.release.sys into the peer's pad, ld.acquire.sys on the own pad):
+ *      every rank's bucket has been filled by the kernels that precede the call on its stream;
+ *   2. rank r reduces slice r: pulls it from every bucket in rank order (bit-identical result whatever the arrival order),
+ *      multiplies by 1 / world and pushes the mean into slice r of EVERY bucket;
+ *   3. second flag barrier: all pushes have landed, nobody reads this rank's bucket any more — the next kernel of the stream
+ *      finds the averaged gradients in the local bucket, and the bucket may be refilled.
+ * Flags count calls (the count lives in the pad: a recorded CUDA graph advances it at every replay), so nothing is reset between
+ * calls.  Every wait is bounded (60 s) and traps.  All ranks must issue the same sequence of calls.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define HPVG_PEER_MAX_RANKS 8
+#define HPVG_PEER_HANDLE_BYTES 64
+#define HPVG_PEER_SIGNAL_BYTES 8192
+int hpvg_peer_alloc(size_t bytes, void** ptr);
+int hpvg_peer_free(void* ptr);
+int hpvg_peer_export(const void* ptr, void* handle);
+int hpvg_peer_import(const void* handle, void** ptr);
+int hpvg_peer_close(void* ptr);
+int hpvg_peer_can_access(int device, int peer_device);
+int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, int world, long long numel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

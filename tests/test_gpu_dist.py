@@ -1,7 +1,7 @@
 """Multi-GPU modes on real devices: needs >= 2 visible GPUs (skipped otherwise; run with `gpurun --gpus 2`).
 
-Batched-noise data-parallel training: one clip per rank, replicated weights, one NCCL all-reduce (average) of the gradients per
-backward.  The critic has no BatchNorm, so the gradient of the two-clip batch is exactly the mean of the per-clip gradients: the
+Batched-noise data-parallel training: one clip per rank, replicated weights, the gradients averaged over ranks once per backward
+(one libhpvg kernel over NVLink peer memory, hpvg/peer.py; NCCL where peer memory cannot be mapped).  The critic has no BatchNorm, so the gradient of the two-clip batch is exactly the mean of the per-clip gradients: the
 averaged gradients a rank holds after the distributed iteration must equal the mean of the gradients two single-GPU iterations
 produce on the two clips, and both ranks must take the same optimizer steps."""
 import os
@@ -84,7 +84,7 @@ def _worker(rank, world, port, out):
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         spread = max((t - gathered[0]).abs().max().item() for t in gathered)
-        out[rank] = (worst, spread, tr_d.allreduce_bytes_per_iter)
+        out[rank] = (worst, spread, tr_d.allreduce_bytes_per_iter, tr_d.bucketD.kind)
     finally:
         dist.destroy_process_group()
 
@@ -100,7 +100,96 @@ def test_distributed_critic_gradients_equal_the_mean_of_single_gpu_gradients():
     res = dict(out)
     print("worst relative error of the averaged critic gradients, weight spread across ranks, all-reduce bytes:", res)
     assert set(res) == {0, 1}
-    for worst, spread, nbytes in res.values():
+    for worst, spread, nbytes, kind in res.values():
         assert worst < 5e-3, res          # same kernels on the same inputs: atomics' summation order only
         assert spread == 0.0, res         # identical averaged gradients -> bit-identical steps on every rank
         assert nbytes > 0
+        assert kind == "peer", res        # the buckets of a single-node NVLink box live in peer memory
+
+
+def _peer_worker(rank, world, port, out):
+    for p in (os.path.join(ROOT, "hp-vae-gan_b200"), ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from hpvg import train
+        sizes = [(64, 64, 3, 3, 3), (64,), (3, 64, 3, 3, 3), (7,), (1, 5, 1)]      # ragged: 110 592 + 64 + 5 184 + 7 + 5 floats
+
+        def fill(params, seed):
+            g = torch.Generator(device=dev).manual_seed(1000 * seed + rank)
+            for p in params:
+                p.grad = torch.randn(p.shape, generator=g, device=dev) * (1.0 + rank)
+
+        def expected(params):
+            flat = torch.cat([p.grad.flatten() for p in params])
+            both = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            acc = both[0].clone()
+            for t in both[1:]:
+                acc += t          # rank order, as the kernel sums
+            return acc * (1.0 / world)
+
+        params = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
+        bucket = train.GradBucket()
+        worst = 0.0
+        for it in range(6):      # eager calls: the flags count calls, nothing is reset in between
+            fill(params, it)
+            want = expected(params)
+            nbytes = bucket.average(params)
+            got = torch.cat([p.grad.flatten() for p in params])
+            worst = max(worst, (got - want).abs().max().item())
+        # the same call recorded into a CUDA graph and replayed on fresh gradients
+        static = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
+        for p in static:
+            p.grad = torch.zeros_like(p)
+        graph_bucket = train.GradBucket()
+        graph_bucket.average(static)          # set-up (allocation, handle exchange) happens outside the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_bucket.average(static)
+        worst_replay = 0.0
+        for it in range(5):
+            fill(params, 100 + it)
+            for p, q in zip(static, params):
+                p.grad.copy_(q.grad)
+            want = expected(static)
+            graph.replay()
+            got = torch.cat([p.grad.flatten() for p in static])
+            worst_replay = max(worst_replay, (got - want).abs().max().item())
+        torch.cuda.synchronize()
+        # every rank holds the same bits
+        got = torch.cat([p.grad.flatten() for p in static])
+        both = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(both, got)
+        spread = max((t - both[0]).abs().max().item() for t in both)
+        out[rank] = (bucket.kind, graph_bucket.kind, worst, worst_replay, spread, nbytes)
+        del graph
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_gradient_bucket_equals_the_mean_over_ranks():
+    """hpvg_peer_allreduce_avg (csrc/peer.cu) through train.GradBucket: ragged gradient lists, repeated eager calls and replays of a
+    recorded call against the mean formed from an NCCL all-gather in the kernel's (rank) order — bit-exact, identical on every rank"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = dict(out)
+    print("bucket kinds, worst |difference| eager / replayed, spread across ranks, bytes:", res)
+    assert set(res) == {0, 1}
+    for kind, kind_graph, worst, worst_replay, spread, nbytes in res.values():
+        assert kind == "peer" and kind_graph == "peer", res
+        assert worst == 0.0 and worst_replay == 0.0, res
+        assert spread == 0.0, res
+        assert nbytes == 4 * (110592 + 64 + 5184 + 7 + 5)
