@@ -242,3 +242,20 @@ def test_wgrad_workspace_plan():
         s = splits(*shape)
         blocks = (shape[1] // 64) * (shape[2] // 64)
         assert 1 <= s and s * shape[6] * blocks <= 148
+
+
+def test_peer_allreduce_argument_checks_need_no_gpu():
+    """hpvg_peer_allreduce_avg validates ranks, bucket size and pointers on the host before it launches anything"""
+    import ctypes
+    from hpvg import lib
+    handle = lib.load()
+    two = (ctypes.c_void_p * 2)(None, None)
+    assert handle.hpvg_peer_allreduce_avg(two, two, 0, lib.PEER_MAX_RANKS + 1, 64, None) == -1
+    assert b"at most" in handle.hpvg_last_error()
+    assert handle.hpvg_peer_allreduce_avg(two, two, 2, 2, 64, None) == -1                 # rank outside the world
+    assert handle.hpvg_peer_allreduce_avg(two, two, 0, 2, 12, None) == -1                 # not a multiple of 4 x world floats
+    assert b"multiple" in handle.hpvg_last_error()
+    assert handle.hpvg_peer_allreduce_avg(two, two, 0, 2, 64, None) == -1                 # unmapped bucket
+    assert b"not mapped" in handle.hpvg_last_error()
+    assert handle.hpvg_peer_allreduce_avg(None, two, 0, 2, 64, None) == -1
+    assert lib.PEER_HANDLE_BYTES == 64 and lib.PEER_SIGNAL_BYTES == 8192
