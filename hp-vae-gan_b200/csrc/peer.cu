@@ -61,14 +61,8 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int ph, unsigned
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerArgs a) {
-  __shared__ unsigned s_epoch;
-  unsigned* epoch = a.sig[a.rank] + PEER_EPOCH_OFF + blockIdx.x;
-  if (threadIdx.x == 0) s_epoch = *epoch + 1u;
-  __syncthreads();
-  const unsigned e = s_epoch;
-  peer_barrier(a, 0, e);      // every rank's bucket is filled
-
+// rank r's share of the work: pull slice r from every bucket, sum in rank order, push the mean into slice r of every bucket
+__device__ __forceinline__ void peer_reduce_slice(const PeerArgs& a) {
   const int W = a.world;
   const long long base = (long long)a.rank * a.n4;
   const long long step = (long long)gridDim.x * PEER_THREADS;
@@ -97,9 +91,92 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
         if (q < W) a.buf[q][base + i] = s;
     }
   }
+}
+
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerArgs a) {
+  __shared__ unsigned s_epoch;
+  unsigned* epoch = a.sig[a.rank] + PEER_EPOCH_OFF + blockIdx.x;
+  if (threadIdx.x == 0) s_epoch = *epoch + 1u;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  peer_barrier(a, 0, e);      // every rank's bucket is filled
+  peer_reduce_slice(a);
   __threadfence_system();      // this thread's pushes are performed at system scope before the CTA's flags go out
   __syncthreads();
   peer_barrier(a, 1, e);       // all means have landed here; nobody reads this rank's bucket any more
+  if (threadIdx.x == 0) *epoch = e;
+}
+
+// ---- the same exchange with the bucket filled from, and emptied into, the gradient tensors by the kernel itself -----------------
+// Bucket layout: tensor t occupies float4 slots [start4[t], start4[t + 1]) (its last slot zero-padded), so every slot belongs to one
+// tensor and is 16-byte aligned on both sides.  CTA b packs and unpacks exactly the slots CTA b of the peers pulls and pushes — slot
+// i of every slice with (i / PEER_THREADS) % gridDim.x == b — so the per-CTA flag exchange still orders everything.
+struct PeerTensors {
+  float* ptr[HPVG_PEER_MAX_TENSORS];
+  unsigned start4[HPVG_PEER_MAX_TENSORS + 1];
+  unsigned numel[HPVG_PEER_MAX_TENSORS];
+  int n;
+};
+
+template <bool PACK>
+__device__ __forceinline__ void peer_copy_slots(const PeerArgs& a, float* const* s_ptr, const unsigned* s_start4, const unsigned* s_numel, int nt) {
+  float4* mine = a.buf[a.rank];
+  const unsigned total4 = s_start4[nt];
+  const long long step = (long long)gridDim.x * PEER_THREADS;
+  for (int q = 0; q < a.world; ++q)
+    for (long long i = (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i < a.n4; i += step) {
+      const long long idx = (long long)q * a.n4 + i;
+      if (idx >= total4) break;      // padding behind the last tensor
+      int lo = 0, hi = nt - 1;       // largest t with start4[t] <= idx
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_start4[mid] <= (unsigned)idx) lo = mid; else hi = mid - 1;
+      }
+      const unsigned off = ((unsigned)idx - s_start4[lo]) * 4u, left = s_numel[lo] - off;
+      float* g = s_ptr[lo] + off;
+      if (PACK) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (left >= 4u) v = *reinterpret_cast<const float4*>(g);
+        else {
+          v.x = g[0];
+          if (left > 1u) v.y = g[1];
+          if (left > 2u) v.z = g[2];
+        }
+        mine[idx] = v;
+      } else {
+        const float4 v = ld_volatile_f4(mine + idx);
+        if (left >= 4u) *reinterpret_cast<float4*>(g) = v;
+        else {
+          g[0] = v.x;
+          if (left > 1u) g[1] = v.y;
+          if (left > 2u) g[2] = v.z;
+        }
+      }
+    }
+}
+
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_tensors_kernel(const PeerArgs a, const PeerTensors t) {
+  __shared__ unsigned s_epoch;
+  __shared__ float* s_ptr[HPVG_PEER_MAX_TENSORS];
+  __shared__ unsigned s_start4[HPVG_PEER_MAX_TENSORS + 1], s_numel[HPVG_PEER_MAX_TENSORS];
+  unsigned* epoch = a.sig[a.rank] + PEER_EPOCH_OFF + blockIdx.x;
+  if (threadIdx.x == 0) s_epoch = *epoch + 1u;
+  if ((int)threadIdx.x < t.n) {
+    s_ptr[threadIdx.x] = t.ptr[threadIdx.x];
+    s_numel[threadIdx.x] = t.numel[threadIdx.x];
+  }
+  if ((int)threadIdx.x <= t.n) s_start4[threadIdx.x] = t.start4[threadIdx.x];
+  __syncthreads();
+  const unsigned e = s_epoch;
+  peer_copy_slots<true>(a, s_ptr, s_start4, s_numel, t.n);      // gradients -> this rank's bucket
+  __threadfence_system();
+  __syncthreads();
+  peer_barrier(a, 0, e);
+  peer_reduce_slice(a);
+  __threadfence_system();
+  __syncthreads();
+  peer_barrier(a, 1, e);
+  peer_copy_slots<false>(a, s_ptr, s_start4, s_numel, t.n);     // averaged bucket -> gradients
   if (threadIdx.x == 0) *epoch = e;
 }
 
@@ -174,18 +251,17 @@ int hpvg_peer_can_access(int device, int peer_device) {
   return ok;
 }
 
-int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, int world, long long numel, void* stream) {
-  HPVG_CHECK_ARG(bufs && signals, "peer_allreduce_avg: null argument");
-  HPVG_CHECK_ARG(world >= 1 && world <= HPVG_PEER_MAX_RANKS && rank >= 0 && rank < world, "peer_allreduce_avg: rank %d of %d (at most %d ranks)",
-                 rank, world, HPVG_PEER_MAX_RANKS);
-  HPVG_CHECK_ARG(numel > 0 && numel % (4LL * world) == 0, "peer_allreduce_avg: %lld floats are not a multiple of 4 x %d", numel, world);
-  PeerArgs a;
+static int peer_args(PeerArgs& a, void* const* bufs, void* const* signals, int rank, int world, long long numel, const char* who) {
+  HPVG_CHECK_ARG(bufs && signals, "%s: null argument", who);
+  HPVG_CHECK_ARG(world >= 1 && world <= HPVG_PEER_MAX_RANKS && rank >= 0 && rank < world, "%s: rank %d of %d (at most %d ranks)", who, rank, world,
+                 HPVG_PEER_MAX_RANKS);
+  HPVG_CHECK_ARG(numel > 0 && numel % (4LL * world) == 0, "%s: %lld floats are not a multiple of 4 x %d", who, numel, world);
   for (int q = 0; q < HPVG_PEER_MAX_RANKS; ++q) {
     a.buf[q] = nullptr;
     a.sig[q] = nullptr;
   }
   for (int q = 0; q < world; ++q) {
-    HPVG_CHECK_ARG(bufs[q] && signals[q], "peer_allreduce_avg: rank %d's bucket or signal pad is not mapped", q);
+    HPVG_CHECK_ARG(bufs[q] && signals[q], "%s: rank %d's bucket or signal pad is not mapped", who, q);
     a.buf[q] = reinterpret_cast<float4*>(bufs[q]);
     a.sig[q] = reinterpret_cast<unsigned*>(signals[q]);
   }
@@ -193,11 +269,54 @@ int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, i
   a.world = world;
   a.n4 = numel / (4LL * world);
   a.scale = 1.0f / (float)world;
-  // the CTAs of all ranks pair up by number: the grid is a function of the arguments every rank shares
-  const int grid = (int)min((long long)PEER_MAX_BLOCKS, max(1LL, cdiv(a.n4, (long long)PEER_THREADS * PEER_UNROLL)));
+  return 0;
+}
+
+// the CTAs of all ranks pair up by number: the grid is a function of the arguments every rank shares
+static int peer_grid(const PeerArgs& a) { return (int)min((long long)PEER_MAX_BLOCKS, max(1LL, cdiv(a.n4, (long long)PEER_THREADS * PEER_UNROLL))); }
+
+int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, int world, long long numel, void* stream) {
+  PeerArgs a;
+  if (int rc = peer_args(a, bufs, signals, rank, world, numel, "peer_allreduce_avg")) return rc;
   // no programmatic launch here: the kernel's first act publishes what the preceding kernels of the stream wrote
-  peer_allreduce_kernel<<<grid, PEER_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  peer_allreduce_kernel<<<peer_grid(a), PEER_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   HPVG_CHECK_LAUNCH("peer_allreduce_kernel");
+  return 0;
+}
+
+long long hpvg_peer_bucket_numel(int n, const long long* numel, int world) {
+  if (n < 0 || !numel || world < 1) return -1;
+  long long slots = 0;
+  for (int i = 0; i < n; ++i) {
+    if (numel[i] < 0) return -1;
+    slots += (numel[i] + 3) / 4;
+  }
+  const long long per_rank = (max(slots, 1LL) + world - 1) / world;
+  return per_rank * 4 * world;
+}
+
+int hpvg_peer_allreduce_avg_tensors(void* const* bufs, void* const* signals, int rank, int world, long long bucket_numel, int n,
+                                    float* const* grads, const long long* numel, void* stream) {
+  PeerArgs a;
+  if (int rc = peer_args(a, bufs, signals, rank, world, bucket_numel, "peer_allreduce_avg_tensors")) return rc;
+  HPVG_CHECK_ARG(grads && numel && n >= 1 && n <= HPVG_PEER_MAX_TENSORS, "peer_allreduce_avg_tensors: %d tensors (1 .. %d per call)", n, HPVG_PEER_MAX_TENSORS);
+  HPVG_CHECK_ARG(bucket_numel >= hpvg_peer_bucket_numel(n, numel, world), "peer_allreduce_avg_tensors: the bucket (%lld floats) is smaller than the gradients need",
+                 bucket_numel);
+  PeerTensors t;
+  unsigned long long slots = 0;
+  for (int i = 0; i < n; ++i) {
+    HPVG_CHECK_ARG(grads[i] && numel[i] > 0 && numel[i] < (1LL << 31), "peer_allreduce_avg_tensors: gradient %d is null, empty or too large", i);
+    HPVG_CHECK_ARG((reinterpret_cast<uintptr_t>(grads[i]) & 15u) == 0, "peer_allreduce_avg_tensors: gradient %d is not 16-byte aligned", i);
+    t.ptr[i] = grads[i];
+    t.numel[i] = (unsigned)numel[i];
+    t.start4[i] = (unsigned)slots;
+    slots += (unsigned long long)((numel[i] + 3) / 4);
+  }
+  HPVG_CHECK_ARG(slots < (1ull << 31), "peer_allreduce_avg_tensors: bucket too large");
+  t.start4[n] = (unsigned)slots;
+  t.n = n;
+  peer_allreduce_tensors_kernel<<<peer_grid(a), PEER_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, t);
+  HPVG_CHECK_LAUNCH("peer_allreduce_tensors_kernel");
   return 0;
 }
 

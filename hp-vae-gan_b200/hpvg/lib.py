@@ -100,6 +100,8 @@ PROTOTYPES = {
     "hpvg_peer_close": (c_int, [c_void_p]),
     "hpvg_peer_can_access": (c_int, [c_int, c_int]),
     "hpvg_peer_allreduce_avg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_void_p]),
+    "hpvg_peer_bucket_numel": (c_longlong, [c_int, c_void_p, c_int]),
+    "hpvg_peer_allreduce_avg_tensors": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -139,7 +141,7 @@ OPT_BLOCKS = 64           # HPVG_OPT_BLOCKS: partial sums per tensor
 OPT_STATE_FLOATS = 8
 SN_MAX_LAYERS = 8
 BN_LOG_MAX = 48           # HPVG_BN_LOG_MAX: entries per hpvg_bn_running_update_batched call
-PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_SIGNAL_BYTES = 8, 64, 8192      # HPVG_PEER_*
+PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_SIGNAL_BYTES, PEER_MAX_TENSORS = 8, 64, 8192, 64      # HPVG_PEER_*
 SN_DOT_PARTS = 32     # HPVG_SN_DOT_PARTS: floats of scratch per layer of the spectral-norm backward
 
 

@@ -1,9 +1,10 @@
 """Gradient buckets in NVLink peer memory (multi-GPU mode, one process per GPU).
 
 `PeerBucket` owns this rank's flat fp32 gradient bucket and signal pad (allocations of libhpvg's own, exported to the other ranks
-as CUDA IPC handles over the process group) and the mapped buckets / pads of every peer; `allreduce()` launches
-hpvg_peer_allreduce_avg (csrc/peer.cu) on the current stream: ONE kernel per backward, recorded into the iteration's CUDA graph
-like any other.  It stands where nn.DataParallel's backward reduces the replicas' gradients (train_video.py:91-94, :182, :200).
+as CUDA IPC handles over the process group) and the mapped buckets / pads of every peer; `allreduce_tensors(grads)` launches
+hpvg_peer_allreduce_avg_tensors (csrc/peer.cu) on the current stream: ONE kernel per backward — it gathers the gradients into the
+bucket, exchanges, and scatters the means back — recorded into the iteration's CUDA graph like any other (`allreduce()`: the
+exchange alone, on a bucket the caller packed).  It stands where nn.DataParallel's backward reduces the replicas' gradients (train_video.py:91-94, :182, :200).
 
 `PeerBucket.create` returns None — on every rank alike — when the ranks cannot map each other's memory (no peer access between
 two of the GPUs, more than 8 ranks, a rank on another host): `train.GradBucket` then keeps the NCCL all-reduce, the collective
@@ -108,6 +109,24 @@ class PeerBucket:
     def allreduce(self):
         """flat <- mean over ranks of flat, on the current stream (every rank must call it)"""
         lib.call("hpvg_peer_allreduce_avg", self._bufs, self._sigs, self.rank, self.world, self.numel,
+                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    @staticmethod
+    def numel_for(grads, world):
+        """floats a bucket needs for these gradients in the slot layout of hpvg_peer_allreduce_avg_tensors (>= their total size)"""
+        return int(lib.load().hpvg_peer_bucket_numel(len(grads), lib.longlong_array([g.numel() for g in grads]), world))
+
+    @staticmethod
+    def can_gather(grads):
+        """the kernel reads and writes the gradient tensors themselves: fp32, contiguous, 16-byte aligned, at most 64 per call"""
+        return (os.environ.get("HPVG_PEER_FUSED_PACK", "1") != "0" and 0 < len(grads) <= lib.PEER_MAX_TENSORS and
+                all(g.dtype == torch.float32 and g.is_contiguous() and g.numel() > 0 and g.data_ptr() % 16 == 0 for g in grads))
+
+    def allreduce_tensors(self, grads):
+        """grads[i] <- mean over ranks of grads[i], in place, ONE launch on the current stream: the kernel fills the bucket from the
+        tensors, exchanges, and writes the means back (every rank must call it with the same shapes)"""
+        lib.call("hpvg_peer_allreduce_avg_tensors", self._bufs, self._sigs, self.rank, self.world, self.numel, len(grads),
+                 lib.ptr_array(grads), lib.longlong_array([g.numel() for g in grads]),
                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 
     def close(self):

@@ -67,9 +67,10 @@ class GradBucket:
     """per-backward gradient averaging over ranks: the gradients are packed into ONE flat fp32 bucket (one multi-tensor copy),
     averaged, and unpacked.
 
-    On NCCL process groups the bucket lives in NVLink peer memory and ONE libhpvg kernel averages it (hpvg/peer.py,
-    csrc/peer.cu: flag exchange, every rank pulls one slice from all peers and pushes the mean back to all of them) — `kind` ==
-    'peer'.  When the ranks cannot map each other's memory, or with HPVG_PEER_ALLREDUCE=0, it is one NCCL all-reduce
+    On NCCL process groups the bucket lives in NVLink peer memory and ONE libhpvg kernel does all of it (hpvg/peer.py,
+    csrc/peer.cu: gradients gathered into the bucket, flag exchange, every rank pulls one slice from all peers and pushes the mean
+    back to all of them, means scattered to the gradients; HPVG_PEER_FUSED_PACK=0: the exchange alone between the two copies) —
+    `kind` == 'peer'.  When the ranks cannot map each other's memory, or with HPVG_PEER_ALLREDUCE=0, it is one NCCL all-reduce
     (ReduceOp.AVG) of the flat bucket ('nccl'); other backends (gloo, the CPU tests): SUM + divide ('sum').
     Measured on 8 x B200 with NCCL (configs[1], one clip per GPU): 4.37 ms per step with the flat bucket against 4.52 ms with a
     coalesced NCCL group call over the ~80 gradient tensors in place (HPVG_COALESCED_ALLREDUCE=1) — NCCL's per-operation cost
@@ -106,7 +107,14 @@ class GradBucket:
                 for g in grads:
                     dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             return n * 4
-        bucket = self._peer_bucket(n, grads[0].device) if nccl else None
+        bucket = None
+        if nccl:
+            from . import peer
+            bucket = self._peer_bucket(peer.PeerBucket.numel_for(grads, dist.get_world_size(self.group)), grads[0].device)
+        if bucket is not None and bucket.can_gather(grads):
+            self.kind = "peer"
+            bucket.allreduce_tensors(grads)      # ONE launch: gather, exchange, scatter (no pack / unpack copies)
+            return n * 4
         if bucket is not None:
             flat = bucket.flat
         else:
@@ -117,6 +125,8 @@ class GradBucket:
         for g in grads:
             views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+            if bucket is not None:
+                off = (off + 3) // 4 * 4      # the slot layout of hpvg_peer_allreduce_avg_tensors: a rank that gathers and one that packs agree
         torch._foreach_copy_(views, grads)
         if bucket is not None:
             self.kind = "peer"

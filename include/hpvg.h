@@ -371,6 +371,13 @@ int hpvg_peer_import(const void* handle, void** ptr);
 int hpvg_peer_close(void* ptr);
 int hpvg_peer_can_access(int device, int peer_device);
 int hpvg_peer_allreduce_avg(void* const* bufs, void* const* signals, int rank, int world, long long numel, void* stream);
+/* The same exchange with the bucket filled from, and emptied into, n gradient tensors (16-byte aligned, numel[i] floats) by the kernel
+ * itself: no pack / unpack launches around it.  Tensor i occupies the float4 slots behind tensor i - 1 (its last slot zero-padded);
+ * hpvg_peer_bucket_numel(n, numel, world) is the bucket size that layout needs (host only).  grads[i] <- mean over ranks, in place. */
+#define HPVG_PEER_MAX_TENSORS 64
+long long hpvg_peer_bucket_numel(int n, const long long* numel, int world);
+int hpvg_peer_allreduce_avg_tensors(void* const* bufs, void* const* signals, int rank, int world, long long bucket_numel, int n,
+                                    float* const* grads, const long long* numel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -259,3 +259,16 @@ def test_peer_allreduce_argument_checks_need_no_gpu():
     assert b"not mapped" in handle.hpvg_last_error()
     assert handle.hpvg_peer_allreduce_avg(None, two, 0, 2, 64, None) == -1
     assert lib.PEER_HANDLE_BYTES == 64 and lib.PEER_SIGNAL_BYTES == 8192
+
+
+def test_peer_bucket_layout_is_host_logic():
+    """hpvg_peer_bucket_numel: every tensor starts on a float4 slot, the slots are dealt out evenly over the ranks"""
+    from hpvg import lib
+    handle = lib.load()
+    assert handle.hpvg_peer_bucket_numel(3, lib.longlong_array([7, 5, 64]), 2) == 80          # 2 + 2 + 16 slots -> 10 per rank
+    assert handle.hpvg_peer_bucket_numel(3, lib.longlong_array([7, 5, 64]), 8) == 96          # 20 slots -> 3 per rank
+    assert handle.hpvg_peer_bucket_numel(1, lib.longlong_array([110592]), 8) == 110592
+    assert handle.hpvg_peer_bucket_numel(1, lib.longlong_array([-1]), 2) == -1
+    import ctypes
+    two = (ctypes.c_void_p * 2)(None, None)
+    assert handle.hpvg_peer_allreduce_avg_tensors(two, two, 0, 2, 64, 0, None, None, None) == -1

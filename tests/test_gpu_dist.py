@@ -135,48 +135,52 @@ def _peer_worker(rank, world, port, out):
                 acc += t          # rank order, as the kernel sums
             return acc * (1.0 / world)
 
-        params = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
-        bucket = train.GradBucket()
-        worst = 0.0
-        for it in range(6):      # eager calls: the flags count calls, nothing is reset in between
-            fill(params, it)
-            want = expected(params)
-            nbytes = bucket.average(params)
-            got = torch.cat([p.grad.flatten() for p in params])
-            worst = max(worst, (got - want).abs().max().item())
-        # the same call recorded into a CUDA graph and replayed on fresh gradients
-        static = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
-        for p in static:
-            p.grad = torch.zeros_like(p)
-        graph_bucket = train.GradBucket()
-        graph_bucket.average(static)          # set-up (allocation, handle exchange) happens outside the capture
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            graph_bucket.average(static)
-        worst_replay = 0.0
-        for it in range(5):
-            fill(params, 100 + it)
-            for p, q in zip(static, params):
-                p.grad.copy_(q.grad)
-            want = expected(static)
-            graph.replay()
+        res = {}
+        for mode in ("1", "0"):      # the kernel gathers / scatters the gradients itself (default); pack and unpack copies around the exchange
+            os.environ["HPVG_PEER_FUSED_PACK"] = mode
+            params = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
+            bucket = train.GradBucket()
+            worst = 0.0
+            for it in range(6):      # eager calls: the flags count calls, nothing is reset in between
+                fill(params, it)
+                want = expected(params)
+                nbytes = bucket.average(params)
+                got = torch.cat([p.grad.flatten() for p in params])
+                worst = max(worst, (got - want).abs().max().item())
+            # the same call recorded into a CUDA graph and replayed on fresh gradients
+            static = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
+            for p in static:
+                p.grad = torch.zeros_like(p)
+            graph_bucket = train.GradBucket()
+            graph_bucket.average(static)          # set-up (allocation, handle exchange) happens outside the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_bucket.average(static)
+            worst_replay = 0.0
+            for it in range(5):
+                fill(params, 100 + it)
+                for p, q in zip(static, params):
+                    p.grad.copy_(q.grad)
+                want = expected(static)
+                graph.replay()
+                got = torch.cat([p.grad.flatten() for p in static])
+                worst_replay = max(worst_replay, (got - want).abs().max().item())
+            torch.cuda.synchronize()
+            # every rank holds the same bits
             got = torch.cat([p.grad.flatten() for p in static])
-            worst_replay = max(worst_replay, (got - want).abs().max().item())
-        torch.cuda.synchronize()
-        # every rank holds the same bits
-        got = torch.cat([p.grad.flatten() for p in static])
-        both = [torch.empty_like(got) for _ in range(world)]
-        dist.all_gather(both, got)
-        spread = max((t - both[0]).abs().max().item() for t in both)
-        out[rank] = (bucket.kind, graph_bucket.kind, worst, worst_replay, spread, nbytes)
-        del graph
+            both = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(both, got)
+            spread = max((t - both[0]).abs().max().item() for t in both)
+            res[mode] = (bucket.kind, graph_bucket.kind, worst, worst_replay, spread, nbytes)
+            del graph
+        out[rank] = res
     finally:
         dist.destroy_process_group()
 
 
 def test_peer_memory_gradient_bucket_equals_the_mean_over_ranks():
-    """hpvg_peer_allreduce_avg (csrc/peer.cu) through train.GradBucket: ragged gradient lists, repeated eager calls and replays of a
+    """hpvg_peer_allreduce_avg_tensors / hpvg_peer_allreduce_avg (csrc/peer.cu) through train.GradBucket: ragged gradient lists, repeated eager calls and replays of a
     recorded call against the mean formed from an NCCL all-gather in the kernel's (rank) order — bit-exact, identical on every rank"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two visible GPUs")
@@ -188,8 +192,10 @@ def test_peer_memory_gradient_bucket_equals_the_mean_over_ranks():
     res = dict(out)
     print("bucket kinds, worst |difference| eager / replayed, spread across ranks, bytes:", res)
     assert set(res) == {0, 1}
-    for kind, kind_graph, worst, worst_replay, spread, nbytes in res.values():
-        assert kind == "peer" and kind_graph == "peer", res
-        assert worst == 0.0 and worst_replay == 0.0, res
-        assert spread == 0.0, res
-        assert nbytes == 4 * (110592 + 64 + 5184 + 7 + 5)
+    for per_mode in res.values():
+        assert set(per_mode) == {"1", "0"}
+        for kind, kind_graph, worst, worst_replay, spread, nbytes in per_mode.values():
+            assert kind == "peer" and kind_graph == "peer", res
+            assert worst == 0.0 and worst_replay == 0.0, res
+            assert spread == 0.0, res
+            assert nbytes == 4 * (110592 + 64 + 5184 + 7 + 5)
