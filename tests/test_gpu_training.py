@@ -216,48 +216,47 @@ def test_recorded_iteration_equals_the_eager_iteration_and_the_reference(golden)
     assert float(rec.optimizerD.state[next(d_r.parameters())]['step']) == float(iters)
 
 
-def test_multi_stream_iteration_equals_the_single_stream_iteration(golden):
-    """Race canary (compute-sanitizer is closed on this pool): the iteration as hpvg.train.ScaleTrainer schedules it — generator
-    'rec' and 'rand' passes on two streams with logged BatchNorm statistics, weight gradients and spectral-norm prologues on side
-    streams — against the same iteration on ONE stream (overlap=False), from identical weights and draws, for several iterations
-    on the 64-channel fixture.  A missing stream dependency shows up as a difference far above the atomics' noise."""
+def _run_schedule(golden, overlap, early=False):
+    """fx['iters'] iterations of the 64-channel GAN fixture under one stream schedule -> (per-iteration losses, final state)"""
     from hpvg import train
     from modules import networks_3d
     fx = golden("train_gan_wide")
     real, real_zero = fx['real'].cuda(), fx['real_zero'].cuda()
-    runs = {}
-    for overlap in (True, False):
-        opt = train_opt_from(fx)
-        g = networks_3d.GeneratorHPVAEGAN(opt)
-        for _ in range(fx['stages']):
-            g.init_next_stage()
-        g.load_state_dict(state_from(fx), strict=True)
-        g.cuda()
-        d = networks_3d.WDiscriminator3D(opt)
-        d.load_state_dict(state_d_from(fx), strict=True)
-        d.cuda()
-        tr = train.ScaleTrainer(opt, g, d, overlap=overlap)
-        feed = train.NoiseFeed(real.device)
-        hist = []
-        with feed:
-            for it in range(fx['iters']):
-                feed.load(_draw_list(fx['draws'][it]), fx['draws'][it]['alpha'])
-                hist.append({k: v.item() for k, v in tr.iteration(real, real_zero).items()})
-        torch.cuda.synchronize()
-        runs[overlap] = (hist, {k: v.detach().float().clone() for k, v in list(g.state_dict().items()) + [('D.' + k, v) for k, v in d.state_dict().items()]})
+    opt = train_opt_from(fx)
+    g = networks_3d.GeneratorHPVAEGAN(opt)
+    for _ in range(fx['stages']):
+        g.init_next_stage()
+    g.load_state_dict(state_from(fx), strict=True)
+    g.cuda()
+    d = networks_3d.WDiscriminator3D(opt)
+    d.load_state_dict(state_d_from(fx), strict=True)
+    d.cuda()
+    tr = train.ScaleTrainer(opt, g, d, overlap=overlap)
+    tr.early_rec_bwd = bool(early)
+    feed = train.NoiseFeed(real.device)
+    hist = []
+    with feed:
+        for it in range(fx['iters']):
+            feed.load(_draw_list(fx['draws'][it]), fx['draws'][it]['alpha'])
+            hist.append({k: v.item() for k, v in tr.iteration(real, real_zero).items()})
+    torch.cuda.synchronize()
+    return hist, {k: v.detach().float().clone() for k, v in list(g.state_dict().items()) + [('D.' + k, v) for k, v in d.state_dict().items()]}, fx['iters']
+
+
+def _assert_same_trajectory(run, ref, iters):
     # Iterations 0 and 1 are held tight: a missing dependency (a stale operand image, a statistic read before it is complete) shows
     # there already, because the weights change after iteration 0.  From iteration 2 on the two schedules are two realisations of
     # the same chaotic process (atomics' summation order differs with the schedule, Adam's first steps are sign-like): measured
     # 1.2 % on errG = -D(fake).mean() at iteration 2, the scale of the run-to-run scatter of ONE schedule (CHAOTIC above).
-    for it, (a, b) in enumerate(zip(runs[True][0], runs[False][0])):
+    for it, (a, b) in enumerate(zip(run[0], ref[0])):
         for key in ('rec_loss', 'gradient_penalty', 'errD_real', 'errD_fake', 'errG'):
             if it < 2:
                 tol = 5e-3 * abs(b[key]) + 5e-4
             else:
                 tol = (3e-2 * abs(b[key]) + 2e-3) if key.startswith('err') else 1e-2 * abs(b[key]) + 5e-4
             assert abs(a[key] - b[key]) <= tol, (it, key, a[key], b[key])
-    for k, b in runs[False][1].items():
-        a = runs[True][1][k]
+    for k, b in ref[1].items():
+        a = run[1][k]
         if not a.is_floating_point():
             assert torch.equal(a, b), k
             continue
@@ -266,11 +265,30 @@ def test_multi_stream_iteration_equals_the_single_stream_iteration(golden):
             # ~1 % from the fp32 oracle on these after 2 iterations, experiments/bn_stats_diag.py)
             assert (a - b).abs().max().item() <= 3e-2 * b.abs().max().item() + 1e-3, k
             continue
-        if k.endswith('conv.bias') and k.replace('conv.bias', 'norm.weight') in runs[False][1]:
+        if k.endswith('conv.bias') and k.replace('conv.bias', 'norm.weight') in ref[1]:
             continue      # a conv bias in front of BatchNorm has a zero gradient: Adam turns its rounding noise into a random walk
         # an entry whose gradient sign differs between the two schedules moves lr the other way at every step: 2 x lr x iterations
         # (+ the same again for the second moment's normalisation early in training)
-        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 4.0 * 5e-4 * fx['iters'], k
+        assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item() + 4.0 * 5e-4 * iters, k
+
+
+def test_multi_stream_iteration_equals_the_single_stream_iteration(golden):
+    """Race canary (compute-sanitizer is closed on this pool): the iteration as hpvg.train.ScaleTrainer schedules it — generator
+    'rec' and 'rand' passes on two streams with logged BatchNorm statistics, weight gradients and spectral-norm prologues on side
+    streams — against the same iteration on ONE stream (overlap=False), from identical weights and draws, for several iterations
+    on the 64-channel fixture.  A missing stream dependency shows up as a difference far above the atomics' noise."""
+    ref = _run_schedule(golden, overlap=False)
+    run = _run_schedule(golden, overlap=True)
+    _assert_same_trajectory(run, ref, ref[2])
+
+
+def test_early_reconstruction_backward_equals_the_single_stream_iteration(golden):
+    """The schedule of the multi-GPU mode (HPVG_EARLY_REC_BWD, on by default when distributed): the reconstruction path's backward
+    runs on the side stream under the critic step, the generator step runs the adversarial path's backward only and accumulates into
+    the same gradients — against the single-stream iteration, same bars as the default schedule."""
+    ref = _run_schedule(golden, overlap=False)
+    run = _run_schedule(golden, overlap=True, early=True)
+    _assert_same_trajectory(run, ref, ref[2])
 
 
 def test_config2_iteration_against_the_oracle():
