@@ -12,8 +12,10 @@ clipping and both Adam steps.  1 720.43 GFLOP of convolution work per step (SURV
   value : iterations/s with the clip resident in HBM, CUDA-event timed, max over ranks.
   e2e   : the same loop fed from pinned HOST buffers every step (H2D of the clip inside the timed region) with a
           device->host read of the step's reconstruction loss.
-  N > 1 : batched-noise data-parallel training — one clip + its noise per GPU, replicated weights, one flat NCCL
-          all-reduce of the gradients per backward (weak scaling: value = N clip-iterations per iteration time).
+  N > 1 : batched-noise data-parallel training — one clip + its noise per GPU, replicated weights, the gradients of each
+          backward averaged by one libhpvg kernel over NVLink peer memory (hpvg_peer_allreduce_avg_tensors; NCCL all-reduce
+          where the GPUs cannot map each other's memory; `allreduce` in the line says which ran)
+          (weak scaling: value = N clip-iterations per iteration time).
   roofline : the dominant kernel's per-launch time (CUDA events on its stream) against the MEASURED burst bf16 peak.
   gpu_eager_baseline : the reference's PyTorch path (oracle/port.py restates it op for op) in torch eager + cuDNN TF32 on the
           same GPU — what the unmodified reference resolves to on this hardware.
