@@ -66,3 +66,29 @@ def test_draws_partition_over_ranks():
                 pos += count
             counts = [c for _, c in spans]
             assert max(counts) - min(counts) <= 1
+
+
+def _peer_refusal_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hpvg import peer, train
+        # no CUDA device here: the allocation fails on every rank, and every rank must learn that the bucket stays on the library collective
+        bucket = peer.PeerBucket.create(1000, "cuda:0")
+        # ... and a GradBucket that was refused once does not try again (no set-up collective per backward)
+        gb = train.GradBucket()
+        gb.peer_refused = bucket is None
+        out[rank] = (bucket is None, gb._peer_bucket(1000, "cuda:0") is None)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_bucket_refusal_is_collective():
+    """hpvg.peer.PeerBucket.create: when a rank cannot set its bucket up, ALL ranks return None from the same call (two all-gathers of
+    the error state), so that no rank launches the peer kernel while another one calls NCCL"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_refusal_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: (True, True), 1: (True, True)}
