@@ -121,38 +121,63 @@ struct PeerTensors {
 template <bool PACK>
 __device__ __forceinline__ void peer_copy_slots(const PeerArgs& a, float* const* s_ptr, const unsigned* s_start4, const unsigned* s_numel, int nt) {
   float4* mine = a.buf[a.rank];
-  const unsigned total4 = s_start4[nt];
+  const long long total4 = s_start4[nt];
   const long long step = (long long)gridDim.x * PEER_THREADS;
-  for (int q = 0; q < a.world; ++q)
-    for (long long i = (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i < a.n4; i += step) {
-      const long long idx = (long long)q * a.n4 + i;
-      if (idx >= total4) break;      // padding behind the last tensor
-      int lo = 0, hi = nt - 1;       // largest t with start4[t] <= idx
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_start4[mid] <= (unsigned)idx) lo = mid; else hi = mid - 1;
-      }
-      const unsigned off = ((unsigned)idx - s_start4[lo]) * 4u, left = s_numel[lo] - off;
-      float* g = s_ptr[lo] + off;
-      if (PACK) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (left >= 4u) v = *reinterpret_cast<const float4*>(g);
-        else {
-          v.x = g[0];
-          if (left > 1u) v.y = g[1];
-          if (left > 2u) v.z = g[2];
+  for (int q = 0; q < a.world; ++q) {
+    const long long qbase = (long long)q * a.n4;
+    if (qbase >= total4) break;      // this slice and the ones behind it are padding
+    // PEER_UNROLL slots per pass: all look-ups, then all loads, then all stores (one slot at a time the loop ran at one memory round
+    // trip per slot: 18 us for 2.7 MB of gradients on 64 CTAs)
+    for (long long i0 = (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i0 < a.n4; i0 += step * PEER_UNROLL) {
+      float* g[PEER_UNROLL];
+      unsigned left[PEER_UNROLL];
+      float4 v[PEER_UNROLL];
+#pragma unroll
+      for (int k = 0; k < PEER_UNROLL; ++k) {
+        const long long i = i0 + k * step, idx = qbase + i;
+        left[k] = 0u;
+        g[k] = nullptr;
+        if (i < a.n4 && idx < total4) {
+          int lo = 0, hi = nt - 1;       // largest t with start4[t] <= idx
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_start4[mid] <= (unsigned)idx) lo = mid; else hi = mid - 1;
+          }
+          const unsigned off = ((unsigned)idx - s_start4[lo]) * 4u;
+          left[k] = s_numel[lo] - off;      // > 0: floats of the tensor from this slot on
+          g[k] = s_ptr[lo] + off;
         }
-        mine[idx] = v;
-      } else {
-        const float4 v = ld_volatile_f4(mine + idx);
-        if (left >= 4u) *reinterpret_cast<float4*>(g) = v;
-        else {
-          g[0] = v.x;
-          if (left > 1u) g[1] = v.y;
-          if (left > 2u) g[2] = v.z;
+      }
+#pragma unroll
+      for (int k = 0; k < PEER_UNROLL; ++k) {
+        if (left[k] == 0u) continue;
+        if (PACK) {
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (left[k] >= 4u) v[k] = *reinterpret_cast<const float4*>(g[k]);
+          else {
+            v[k].x = g[k][0];
+            if (left[k] > 1u) v[k].y = g[k][1];
+            if (left[k] > 2u) v[k].z = g[k][2];
+          }
+        } else {
+          v[k] = ld_volatile_f4(mine + qbase + i0 + k * step);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PEER_UNROLL; ++k) {
+        if (left[k] == 0u) continue;
+        if (PACK) {
+          mine[qbase + i0 + k * step] = v[k];
+        } else if (left[k] >= 4u) {
+          *reinterpret_cast<float4*>(g[k]) = v[k];
+        } else {
+          g[k][0] = v[k].x;
+          if (left[k] > 1u) g[k][1] = v[k].y;
+          if (left[k] > 2u) g[k][2] = v[k].z;
         }
       }
     }
+  }
 }
 
 __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_tensors_kernel(const PeerArgs a, const PeerTensors t) {
